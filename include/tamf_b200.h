@@ -1,0 +1,179 @@
+/* tamf_b200.h -- C ABI of libtamf_b200.so: the B200 (sm_100a) sampling hot path of OakInk2-TaMF.
+ *
+ * The reference has no FFI for this path (it is pure Python over torch / pytorch3d); each entry point
+ * below names the reference interface it replaces (paths relative to the reference tree).  The Python
+ * drop-in classes in oakink2-tamf_b200/tamf_b200/ bind these with ctypes (INTEGRATION.md shows the
+ * stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  Unless a name ends in `_host`, pointers are
+ *     DEVICE pointers, contiguous, 16-byte aligned, owned by the caller.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous.
+ *   - every entry returns 0 on success or a negative TAMF_E_* code; tamf_last_error() gives the
+ *     thread-local message.  Nothing throws across the ABI.
+ *   - handles are not thread-safe; one handle per device per process (the reference is one process
+ *     per GPU, launch/sample.py:272-289).
+ *   - the library refuses to run on anything but compute capability 10.x (TAMF_E_ARCH): there is no
+ *     CPU fallback.
+ */
+#ifndef TAMF_B200_H_
+#define TAMF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAMF_OK 0
+#define TAMF_E_BADARG (-1) /* bad shape / null pointer / unsupported size */
+#define TAMF_E_CUDA (-2)   /* a CUDA runtime or driver call failed */
+#define TAMF_E_ARCH (-3)   /* device is not sm_100 */
+#define TAMF_E_ALIGN (-4)  /* pointer not 16-byte aligned */
+#define TAMF_E_STATE (-5)  /* call order violated (e.g. forward before bind / set_cond) */
+
+int tamf_version(void);
+const char* tamf_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Chamfer nearest neighbour (K=1).
+ * Replaces pytorch3d.ops.knn_points(x, y, K=1) as called by
+ *   thirdparty/chamfer_distance/chamfer_distance/chamfer_distance.py:147-148 (ChamferDistance.forward)
+ * and consumed by src/oakink2_tamf/model/loss/chamfer_distance.py:36-62 (point2point_signed).
+ * x [N,P1,3], y [N,P2,3] fp32 -> d2 [N,P1] fp32 (squared L2), idx [N,P1] int64.
+ * Arithmetic: (dx*dx + dy*dy) + dz*dz, each op rounded to fp32 (no FMA), lowest index on ties.
+ * `idx` doubles as the packed (d2,idx) scratch during the call.                                    */
+int tamf_nn_query(const float* x, const float* y, int N, int P1, int P2, float* d2, int64_t* idx, void* stream);
+
+/* Fused hand->object distance.
+ * Replaces SegmentRefineModel.multi_object_h2o_dist (src/oakink2_tamf/model/segment_refine_model.py:142-168):
+ * per sequence b and frame t the canonical clouds of its objects are moved by tslrot6d_to_transf /
+ * transf_point_array (src/dev_fn/transform/transform.py:148-154,36-53), concatenated, and every hand
+ * vertex gets the unsigned distance to its nearest object point.
+ *   verts     [B,T,V,3]            hand vertices (world)
+ *   obj_traj  [B,nobj_max,T,9]     tsl(3)+rot6d(6), zero padded over objects
+ *   obj_points[sum_b nobj_b, P, 3] canonical clouds, packed in batch order
+ *   obj_first [B+1] int32          prefix sums of nobj_b (host pointer)
+ *   dist      [B,T,V] fp32         |v - nearest|  (sqrt of the squared distance)
+ *   idx       [B,T,V] int64        index into the concatenated cloud of that sequence (scratch + output) */
+int tamf_h2o_dist(const float* verts, const float* obj_traj, const float* obj_points, const int32_t* obj_first_host,
+                  int B, int T, int V, int nobj_max, int P, float* dist, int64_t* idx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MANO forward kinematics.
+ * Replaces manotorch ManoLayer(rot_mode="quat", center_idx=0, use_pca=False, flat_hand_mean=True)
+ *   thirdparty/manotorch/manotorch/manolayer.py:39-98 (buffers), :128-266 (skinning_layer), :268-285 (forward)
+ * and the pose_repr front end of SegmentRefineModel.batch_recover_mano_from_pose_repr
+ *   src/oakink2_tamf/model/segment_refine_model.py:117-131.
+ * Asset pointers are HOST fp32 arrays with the ManoLayer buffer shapes:
+ *   shapedirs [778,3,10], posedirs [778,3,135], v_template [778,3], J_regressor [16,778], weights [778,16]. */
+typedef struct tamf_mano tamf_mano;
+int tamf_mano_create(const float* shapedirs_host, const float* posedirs_host, const float* v_template_host,
+                     const float* j_regressor_host, const float* weights_host, int is_right, tamf_mano** out);
+int tamf_mano_destroy(tamf_mano* h);
+#define TAMF_POSE_QUAT 0      /* pose [N,16,4] quaternions (w,x,y,z): ManoLayer.forward(pose_coeffs, betas)   */
+#define TAMF_POSE_REPR 1      /* pose [N,99] = tsl(3) + 16 x rot6d: batch_recover_mano_from_pose_repr (+tsl)  */
+/* betas [N,10]; verts [N,778,3]; joints [N,21,3] (root-centred; +tsl in TAMF_POSE_REPR mode). */
+int tamf_mano_fk(const tamf_mano* h, int pose_mode, const float* pose, const float* betas, int N, float* verts,
+                 float* joints, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MF-MDM G denoiser + ancestral DDPM sampler.
+ * Replaces InterationSegmentMDM.forward(x, timesteps, batch)
+ *   src/oakink2_tamf/model/interaction_segment_mdm.py:134-174 (+ sub-modules :181-318)
+ * and GaussianDiffusion.p_sample / p_sample_loop
+ *   src/oakink2_tamf/model/diffusion/gaussian_diffusion.py:412-460, 506-640 (START_X, FIXED_SMALL).  */
+typedef struct tamf_denoiser tamf_denoiser;
+
+typedef struct tamf_cfg {
+  int32_t input_dim;      /* 99  */
+  int32_t obj_input_dim;  /* 9   */
+  int32_t hand_shape_dim; /* 10  */
+  int32_t obj_embed_dim;  /* 768 */
+  int32_t latent_dim;     /* 256 | 512 */
+  int32_t ff_size;        /* 1024 | 2048 */
+  int32_t num_layers;     /* 8 */
+  int32_t num_heads;      /* 4 */
+  int32_t clip_dim;       /* 512 */
+  int32_t num_steps;      /* 1000 diffusion steps (cosine schedule is built by the caller) */
+} tamf_cfg;
+
+/* HOST fp32 weight pointers, reference state_dict names in comments. */
+typedef struct tamf_layer_weights {
+  const float *in_proj_w, *in_proj_b;   /* seqTransEncoder.layers.L.self_attn.in_proj_{weight,bias}  [3d,d],[3d] */
+  const float *out_proj_w, *out_proj_b; /* ...self_attn.out_proj.{weight,bias}                         [d,d],[d]  */
+  const float *lin1_w, *lin1_b;         /* ...linear1.{weight,bias}                                     [ff,d],[ff]*/
+  const float *lin2_w, *lin2_b;         /* ...linear2.{weight,bias}                                     [d,ff],[d] */
+  const float *norm1_w, *norm1_b;       /* ...norm1.{weight,bias}                                       [d]        */
+  const float *norm2_w, *norm2_b;       /* ...norm2.{weight,bias}                                       [d]        */
+} tamf_layer_weights;
+
+typedef struct tamf_g_weights {
+  const float *shape_w, *shape_b;         /* hand_shape_process.shape_embed      [d,10]   */
+  const float *objemb_w, *objemb_b;       /* obj_embed_process.embedding         [d,768]  */
+  const float *pose_w, *pose_b;           /* input_process.poseEmbedding         [d,99]   */
+  const float *objtraj_w, *objtraj_b;     /* obj_input_process.poseEmbedding     [d,9]    */
+  const float *merge0_w, *merge0_b;       /* input_merge.0                       [d,2d]   */
+  const float *merge2_w, *merge2_b;       /* input_merge.2                       [d,d]    */
+  const float *time0_w, *time0_b;         /* embed_timestep.time_embed.0         [d,d]    */
+  const float *time2_w, *time2_b;         /* embed_timestep.time_embed.2         [d,d]    */
+  const float *text_w, *text_b;           /* embed_text                          [d,clip] */
+  const float *final_w, *final_b;         /* output_process.poseFinal            [99,d]   */
+  const float *pe;                        /* sequence_pos_encoder.pe             [>=max(num_steps,5+T), d] */
+  int32_t pe_rows;
+  const tamf_layer_weights* layers;       /* [num_layers] */
+  /* float64 schedule tables, [num_steps] each (GaussianDiffusion.__init__, gaussian_diffusion.py:149-157) */
+  const double *posterior_mean_coef1, *posterior_mean_coef2, *posterior_log_variance_clipped;
+} tamf_g_weights;
+
+int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w, tamf_denoiser** out);
+int tamf_denoiser_destroy(tamf_denoiser* h);
+
+/* Workspace protocol: the library never allocates in the hot path. */
+size_t tamf_denoiser_workspace_bytes(const tamf_denoiser* h, int B, int T);
+int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* workspace, size_t workspace_bytes);
+
+/* Per-sample conditioning, computed ONCE per batch (constant over the reverse chain):
+ *   text_feat [B,clip_dim]        = clip_model.encode_text(tokens).float()   (interaction_segment_mdm.py:132)
+ *   hand_side [B] int32           0 = "rh", 1 = "lh"                          (:270-274)
+ *   shape     [B,T,10], obj_traj [B,nobj_max,T,9], obj_emb [B,nobj_max,768]  (zero padded over objects) */
+int tamf_denoiser_set_cond(tamf_denoiser* h, const float* text_feat, const int32_t* hand_side, const float* shape,
+                           const float* obj_traj, const float* obj_emb, int nobj_max, void* stream);
+
+/* x0 = model(x_t, t): x_t, x0_out [B,99,1,T] fp32; t [B] int32 (device). */
+int tamf_denoiser_forward(tamf_denoiser* h, const float* x_t, const int32_t* t, float* x0_out, void* stream);
+
+/* One ancestral step p_sample (all rows at the same t):
+ *   x_{t-1} = c1[t] x0 + c2[t] x_t + 1[t!=0] exp(0.5 logvar[t]) eps,   x0 = model(x_t, t)
+ * x_io is updated in place.  eps = `noise` [B,99,1,T] if non-NULL, else Philox4x32-10(seed, t, element) normals.
+ * x0_out may be NULL. */
+int tamf_p_sample_step(tamf_denoiser* h, float* x_io, int t, const float* noise, uint64_t seed, float* x0_out,
+                       void* stream);
+
+/* Steps t_start, t_start-1, ..., t_end (inclusive) with in-kernel Philox noise, replayed from one captured
+ * CUDA graph per step (p_sample_loop_progressive, gaussian_diffusion.py:621-640).  x_io [B,99,1,T] in place. */
+int tamf_p_sample_chain(tamf_denoiser* h, float* x_io, int t_start, int t_end, uint64_t seed, void* stream);
+
+/* Whole p_sample_loop with HOST buffers (what the e2e figure times): copies the conditioning in, draws
+ * x_T ~ N(0,I) (Philox, counter t = num_steps) unless x_T_host is given, runs the chain, copies the sample out.
+ * Synchronous. */
+int tamf_p_sample_loop_host(tamf_denoiser* h, const float* text_feat_host, const int32_t* hand_side_host,
+                            const float* shape_host, const float* obj_traj_host, const float* obj_emb_host,
+                            int nobj_max, const float* x_T_host, uint64_t seed, float* sample_out_host, void* stream);
+
+/* Number of kernels this library launched since load (for bench.py's gpu_launches claim). */
+uint64_t tamf_kernel_launch_count(void);
+
+/* The raw Philox normal generator used by the sampler, exposed for parity tests: out [n] fp32. */
+int tamf_philox_normal(float* out, size_t n, uint64_t seed, uint32_t t, void* stream);
+
+/* Self-test of the tcgen05 GEMM against caller-provided data: C[M,N] fp32 = A[M,K] bf16 . W[N,K]^T bf16 + bias.
+ * a, w are device bf16 (uint16 bit patterns), bias device fp32 [N] or NULL, c device fp32. */
+int tamf_gemm_selftest(const uint16_t* a, const uint16_t* w, const float* bias, float* c, int M, int N, int K,
+                       int tile_n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAMF_B200_H_ */

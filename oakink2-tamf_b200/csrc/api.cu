@@ -1,0 +1,138 @@
+// api.cu -- library-wide state: version, thread-local error, device check, TMA descriptor encoding,
+// GEMM self-test and Philox test entry points.
+#include <mutex>
+
+#include "gemm.cuh"
+
+namespace tamf {
+
+static thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+void set_error(const std::string& msg) { g_err = msg; }
+
+int check_device() {
+  static thread_local int cached_dev = -1, cached_rc = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("no CUDA device: libtamf_b200 has no CPU fallback");
+    return TAMF_E_CUDA;
+  }
+  if (dev == cached_dev) return cached_rc;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    set_error("cudaDeviceGetAttribute failed");
+    return TAMF_E_CUDA;
+  }
+  cached_dev = dev;
+  cached_rc = TAMF_OK;
+  if (major != 10) {
+    set_error("libtamf_b200 is built for sm_100a (B200) only; device has compute capability major " +
+              std::to_string(major));
+    cached_rc = TAMF_E_ARCH;
+  }
+  return cached_rc;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2D bf16 row-major tensor [rows][inner], TMA box [box_rows][box_inner] with 128-byte swizzle (box_inner*2 == 128).
+int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes,
+                      uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  TAMF_REQUIRE(enc != nullptr, TAMF_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  TAMF_REQUIRE(aligned16(gptr) && (row_pitch_bytes % 16) == 0, TAMF_E_ALIGN, "TMA tensor must be 16-byte aligned");
+  TAMF_REQUIRE(box_inner * 2 == 128 && box_rows <= 256, TAMF_E_BADARG, "TMA box must be 64 bf16 x <=256 rows");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return TAMF_E_CUDA;
+  }
+  return TAMF_OK;
+}
+
+__global__ void philox_fill_kernel(float* out, size_t n, unsigned long long seed, uint32_t t) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = philox_normal(seed, t, i);
+}
+
+int philox_fill(float* out, size_t n, uint64_t seed, uint32_t t, cudaStream_t stream) {
+  philox_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(out, n, seed, t);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}
+
+}  // namespace tamf
+
+using namespace tamf;
+
+extern "C" int tamf_version(void) { return 100; }
+extern "C" const char* tamf_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t tamf_kernel_launch_count(void) { return g_launches.load(); }
+
+extern "C" int tamf_philox_normal(float* out, size_t n, uint64_t seed, uint32_t t, void* stream) {
+  TAMF_REQUIRE(out != nullptr, TAMF_E_BADARG, "tamf_philox_normal: null pointer");
+  int rc = check_device();
+  if (rc) return rc;
+  if (n == 0) return TAMF_OK;
+  return philox_fill(out, n, seed, t, (cudaStream_t)stream);
+}
+
+extern "C" int tamf_gemm_selftest(const uint16_t* a, const uint16_t* w, const float* bias, float* c, int M, int N, int K,
+                                  int tile_n, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_device();
+  if (rc) return rc;
+  TAMF_REQUIRE(a && w && c, TAMF_E_BADARG, "tamf_gemm_selftest: null pointer");
+  TAMF_REQUIRE(M > 0 && N > 0 && K > 0 && (K % 8) == 0 && (N % 32) == 0, TAMF_E_BADARG,
+               "tamf_gemm_selftest: need K % 8 == 0 and N % 32 == 0");
+  TAMF_REQUIRE(tile_n == 128 || tile_n == 256 || tile_n == 512, TAMF_E_BADARG, "tamf_gemm_selftest: tile_n");
+  CUtensorMap tmA, tmB;
+  rc = make_tmap_2d_bf16(&tmA, a, K, M, (uint64_t)K * 2, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, w, K, N, (uint64_t)K * 2, 64, tile_n > 256 ? 256 : tile_n);
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = M, p.N = N, p.K = K, p.bias = bias, p.out_f32 = c, p.ld_f32 = N;
+  if (tile_n == 128) {
+    if ((rc = configure_gemm<128, EPI_F32>())) return rc;
+    return launch_gemm<128, EPI_F32>(tmA, tmB, p, stream);
+  }
+  if (tile_n == 256) {
+    if ((rc = configure_gemm<256, EPI_F32>())) return rc;
+    return launch_gemm<256, EPI_F32>(tmA, tmB, p, stream);
+  }
+  if ((rc = configure_gemm<512, EPI_F32>())) return rc;
+  return launch_gemm<512, EPI_F32>(tmA, tmB, p, stream);
+}

@@ -1,0 +1,684 @@
+// denoiser.cu -- MF-MDM G denoiser + DDPM ancestral sampler: weights, workspace, conditioning, per-step launch
+// sequence and the CUDA-graph chain.
+//
+// Replaces InterationSegmentMDM.forward (src/oakink2_tamf/model/interaction_segment_mdm.py:134-174) and
+// GaussianDiffusion.p_sample / p_sample_loop_progressive (model/diffusion/gaussian_diffusion.py:412-460, 573-640).
+//
+// Per step (everything else is hoisted, SURVEY.md 8a'):
+//   prep        x_t [B,99,1,T] fp32 -> A0 [B*T,128] bf16 (frame-major, K zero-padded); token 0 = ttab[t]+pe[0];
+//               tokens 1..4 = cached prefix
+//   embed-a     H0 = silu(A0 . Wf^T + obj_half)          Wf = merge0[:, :d] . poseEmbedding (folded, [d,128])
+//   embed-b     tok[5+tau] = nan_to_num(H0 . merge2^T + b) + pe[5+tau]     -> X fp32 / Xb bf16, rows b*S+5+tau
+//   8 x layer   QKV = Xb . Win^T + b ; ATT = softmax(QK^T/sqrt(hd)) V ; X = LN1(X + ATT . Wo^T + b)
+//               H = gelu(Xb . W1^T + b) ; X = LN2(X + H . W2^T + b)
+//   final       x0 = nan_to_num(Xb . Wf^T + b) ; x_{t-1} = c1[t] x0 + c2[t] x_t + sigma[t] eps   (fused epilogue)
+// = 2 + 5*L + 2 = 44 kernel launches for L = 8, captured once in a CUDA graph and replayed per step.
+//
+// HBM layout (row = token index b*S + s, S = 5 + T; all row-major):
+//   X  fp32 [M,d] residual stream | Xb bf16 [M,d] GEMM operand copy | QKV bf16 [M,3d] | ATT bf16 [M,d] | H bf16 [M,ff]
+//   A0 bf16 [B*T,128] | H0 bf16 [B*T,d] | obj_half fp32 [B*T,d] | prefix fp32 [B,4,d] | ttab fp32 [steps,d]
+#include <vector>
+
+#include "attn.cuh"
+#include "gemm.cuh"
+
+namespace tamf {
+
+int philox_fill(float* out, size_t n, uint64_t seed, uint32_t t, cudaStream_t stream);
+
+constexpr int KPAD = 128;      // input_dim 99 zero-padded to the GEMM K tile
+constexpr int MAX_NOBJ = 8;    // staging capacity of tamf_p_sample_loop_host
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+
+// out[r, n] = post( sum_k in[r,k] W[n,k] + bias[n] )   fp32 SIMT, 64x64 tile, 16-wide k slab, 4x4 per thread.
+// post: 0 none, 1 silu, 2 nan_to_num(.) + add[r % add_rows, n]
+__global__ void __launch_bounds__(256)
+    linear_f32_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ W, int ld_w,
+                      const float* __restrict__ bias, float* __restrict__ out, int ld_out, int R, int N, int K, int post,
+                      const float* __restrict__ add, int ld_add) {
+  __shared__ float sI[16][65], sW[16][65];
+  const int r0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int rr = i / 16, kk = i % 16;
+      sI[kk][rr] = (r0 + rr < R && k0 + kk < K) ? in[(size_t)(r0 + rr) * ld_in + k0 + kk] : 0.f;
+      sW[kk][rr] = (n0 + rr < N && k0 + kk < K) ? W[(size_t)(n0 + rr) * ld_w + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sI[kk][ty * 4 + i], b[i] = sW[kk][tx * 4 + i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (post == 1) v = v / (1.0f + expf(-v));
+      if (post == 2) v = nan_to_num(v) + add[(size_t)r * ld_add + n];
+      out[(size_t)r * ld_out + n] = v;
+    }
+  }
+}
+
+static int linear_f32(const float* in, int ld_in, const float* W, int ld_w, const float* bias, float* out, int ld_out,
+                      int R, int N, int K, int post, const float* add, int ld_add, cudaStream_t s) {
+  dim3 grid((N + 63) / 64, (R + 63) / 64);
+  linear_f32_kernel<<<grid, 256, 0, s>>>(in, ld_in, W, ld_w, bias, out, ld_out, R, N, K, post, add, ld_add);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}
+
+// out[o, i] = mean_r in[o, r, i]   (in viewed as [outer, red, inner]; torch.mean(x, dim) in fp32)
+__global__ void mean_axis_kernel(const float* __restrict__ in, float* __restrict__ out, int outer, int red, int inner) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)outer * inner) return;
+  const int o = (int)(i / inner), c = (int)(i % inner);
+  float acc = 0.f;
+  for (int r = 0; r < red; ++r) acc += in[((size_t)o * red + r) * inner + c];
+  out[i] = acc / (float)red;
+}
+
+// obj_traj [B,nobj,T,9] -> mean over objects, frame-major [B*T, 9]
+__global__ void traj_mean_kernel(const float* __restrict__ traj, float* __restrict__ out, int B, int nobj, int T) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * T * 9) return;
+  const int c = (int)(i % 9), tau = (int)((i / 9) % T), b = (int)(i / (9 * (size_t)T));
+  float acc = 0.f;
+  for (int o = 0; o < nobj; ++o) acc += traj[(((size_t)b * nobj + o) * T + tau) * 9 + c];
+  out[i] = acc / (float)nobj;
+}
+
+// prefix[b,1,:] = hand-side token (rh -> 0, lh -> e0), then nan_to_num(prefix) + pe[1..4]
+__global__ void prefix_finish_kernel(float* __restrict__ prefix, const int* __restrict__ hand_side,
+                                     const float* __restrict__ pe, int B, int d) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * 4 * d) return;
+  const int c = (int)(i % d), s = (int)((i / d) % 4), b = (int)(i / (4 * (size_t)d));
+  float v = prefix[i];
+  if (s == 1) v = (hand_side[b] == 1 && c == 0) ? 1.f : 0.f;
+  prefix[i] = nan_to_num(v) + pe[(size_t)(1 + s) * d + c];
+}
+
+// fp32 [rows, cols] -> bf16 [rows, ld_out] with zero padding of columns cols..ld_out-1
+__global__ void to_bf16_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows, int cols,
+                                   int ld_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * ld_out) return;
+  const int c = (int)(i % ld_out), r = (int)(i / ld_out);
+  out[i] = __float2bfloat16_rn(c < cols ? in[(size_t)r * cols + c] : 0.f);
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void add_int_kernel(int* p, int n, int dv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += dv;
+}
+
+// prep: grid (ceil(T/32), B), 256 threads.
+//  (a) A0[b*T+tau, k] = bf16(x[b,k,0,tau]) (k < nfeat), 0 for the K padding -- transposed through shared memory so
+//      both the read (along tau) and the write (along k) are coalesced.
+//  (b) blockIdx.x == 0 also writes the 5 prefix token rows of sequence b into X / Xb.
+__global__ void __launch_bounds__(256)
+    prep_kernel(const float* __restrict__ x, const int* __restrict__ t_ptr, const float* __restrict__ ttab,
+                const float* __restrict__ pe, const float* __restrict__ prefix, __nv_bfloat16* __restrict__ A0,
+                float* __restrict__ X, __nv_bfloat16* __restrict__ Xb, int T, int S, int d, int nfeat) {
+  __shared__ float tile[KPAD][33];
+  const int b = blockIdx.y, tau0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = w; k < nfeat; k += 8) {
+    const int tau = tau0 + lane;
+    tile[k][lane] = (tau < T) ? x[((size_t)b * nfeat + k) * T + tau] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * (KPAD / 2); i += 256) {
+    const int j = i / (KPAD / 2), kp = (i % (KPAD / 2)) * 2;
+    const int tau = tau0 + j;
+    if (tau < T) {
+      const float v0 = kp < nfeat ? tile[kp][j] : 0.f, v1 = (kp + 1) < nfeat ? tile[kp + 1][j] : 0.f;
+      *reinterpret_cast<uint32_t*>(A0 + ((size_t)b * T + tau) * KPAD + kp) = pack_bf16x2(v0, v1);
+    }
+  }
+  if (blockIdx.x == 0) {
+    const int t = t_ptr[b];
+    for (int i = threadIdx.x; i < 5 * d; i += 256) {
+      const int s = i / d, c = i % d;
+      float v;
+      if (s == 0)
+        v = nan_to_num(ttab[(size_t)t * d + c]) + pe[c];  // interaction_segment_mdm.py:142,158,170
+      else
+        v = prefix[((size_t)b * 4 + (s - 1)) * d + c];
+      X[((size_t)b * S + s) * d + c] = v;
+      Xb[((size_t)b * S + s) * d + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct LayerDev {
+  __nv_bfloat16 *w_in, *w_out, *w1, *w2;
+  float *b_in, *b_out, *b1, *b2, *g1, *be1, *g2, *be2;
+  CUtensorMap tm_in, tm_out, tm_w1, tm_w2;
+};
+
+}  // namespace tamf
+
+using namespace tamf;
+
+struct tamf_denoiser {
+  tamf_cfg cfg{};
+  int d = 0, ff = 0, L = 0, H = 0, nfeat = 0;
+  std::vector<void*> owned;  // device allocations freed by destroy
+  std::vector<LayerDev> layers;
+  // fp32 conditioning weights (exact fp32 SIMT path, once per sample)
+  float *shape_w, *shape_b, *objemb_w, *objemb_b, *objtraj_w, *objtraj_b, *merge0_w, *merge_bias /* b1 + W1a.bp */,
+      *text_w, *text_b, *pe, *ttab;
+  int pe_rows = 0;
+  // bf16 hot-path weights
+  __nv_bfloat16 *wfold /*[d,128]*/, *wm2 /*[d,d]*/, *wfin /*[99,d]*/;
+  float *b_m2, *b_fin;
+  CUtensorMap tm_wfold, tm_wm2, tm_wfin;
+  float *c1, *c2, *sigma;  // [num_steps]
+  // bound workspace
+  int B = 0, T = 0, S = 0, M = 0, Mf = 0;
+  bool bound = false, cond_set = false;
+  float *X, *objhalf, *prefix, *objtok, *trajmean, *shapemean, *embmean, *xbuf;
+  float *st_text, *st_shape, *st_traj, *st_emb;  // host-API staging
+  int *st_side, *t_dev;
+  __nv_bfloat16 *Xb, *QKV, *ATT, *Hb, *A0, *H0;
+  CUtensorMap tm_Xb, tm_ATT, tm_H, tm_A0, tm_H0;
+  // cached step graph
+  cudaGraphExec_t graph_exec = nullptr;
+  float* graph_x = nullptr;
+  uint64_t graph_seed = 0;
+  cudaStream_t graph_stream = nullptr;
+};
+
+namespace tamf {
+
+static int dev_alloc(tamf_denoiser* h, void** p, size_t bytes) {
+  TAMF_CUDA_CHECK(cudaMalloc(p, bytes));
+  h->owned.push_back(*p);
+  return TAMF_OK;
+}
+static int upload_f32(tamf_denoiser* h, float** dst, const float* src, size_t n) {
+  TAMF_REQUIRE(src != nullptr, TAMF_E_BADARG, "tamf_denoiser_create: null weight pointer");
+  int rc = dev_alloc(h, (void**)dst, n * sizeof(float));
+  if (rc) return rc;
+  TAMF_CUDA_CHECK(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return TAMF_OK;
+}
+// fp32 host [rows, cols] -> bf16 device [rows, ld] (zero padded), via a device conversion kernel
+static int upload_bf16(tamf_denoiser* h, __nv_bfloat16** dst, const float* src, int rows, int cols, int ld) {
+  TAMF_REQUIRE(src != nullptr, TAMF_E_BADARG, "tamf_denoiser_create: null weight pointer");
+  float* tmp = nullptr;
+  TAMF_CUDA_CHECK(cudaMalloc(&tmp, (size_t)rows * cols * sizeof(float)));
+  cudaError_t e = cudaMemcpy(tmp, src, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice);
+  int rc = (e == cudaSuccess) ? dev_alloc(h, (void**)dst, (size_t)rows * ld * sizeof(__nv_bfloat16)) : TAMF_E_CUDA;
+  if (rc == TAMF_OK) {
+    const size_t n = (size_t)rows * ld;
+    to_bf16_pad_kernel<<<(unsigned)((n + 255) / 256), 256>>>(tmp, *dst, rows, cols, ld);
+    count_launch();
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = TAMF_E_CUDA;
+  }
+  cudaFree(tmp);
+  if (rc == TAMF_E_CUDA) set_error(std::string("upload_bf16: ") + cudaGetErrorString(cudaGetLastError()));
+  return rc;
+}
+
+// One denoiser evaluation (+ optional posterior update) enqueued on `s`.
+static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, float* x_out, float* x0_out,
+                        const float* noise, uint64_t seed, cudaStream_t s) {
+  const int d = h->d, ff = h->ff, B = h->B, T = h->T, S = h->S, M = h->M, Mf = h->Mf;
+  int rc;
+  prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, h->ttab, h->pe, h->prefix, h->A0, h->X, h->Xb, T, S, d,
+                                                     h->nfeat);
+  TAMF_LAUNCH_CHECK();
+  {  // embed-a
+    GemmParams p{};
+    p.M = Mf, p.N = d, p.K = KPAD, p.bias = nullptr, p.addmat = h->objhalf, p.out_bf16 = h->H0, p.ld_bf16 = d;
+    if ((rc = launch_gemm<256, EPI_ADD_SILU_BF16>(h->tm_A0, h->tm_wfold, p, s))) return rc;
+  }
+  {  // embed-b
+    GemmParams p{};
+    p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = 5, p.X = h->X, p.Xb = h->Xb;
+    if ((rc = launch_gemm<256, EPI_TOKEN_OUT>(h->tm_H0, h->tm_wm2, p, s))) return rc;
+  }
+  for (int l = 0; l < h->L; ++l) {
+    LayerDev& w = h->layers[l];
+    {
+      GemmParams p{};
+      p.M = M, p.N = 3 * d, p.K = d, p.bias = w.b_in, p.out_bf16 = h->QKV, p.ld_bf16 = 3 * d;
+      if ((rc = launch_gemm<256, EPI_BIAS_BF16>(h->tm_Xb, w.tm_in, p, s))) return rc;
+    }
+    if (d / h->H == 128)
+      rc = launch_attn<128>(h->QKV, h->ATT, B, S, h->H, d, s);
+    else
+      rc = launch_attn<64>(h->QKV, h->ATT, B, S, h->H, d, s);
+    if (rc) return rc;
+    {
+      GemmParams p{};
+      p.M = M, p.N = d, p.K = d, p.bias = w.b_out, p.X = h->X, p.Xb = h->Xb, p.gamma = w.g1, p.beta = w.be1;
+      rc = (d == 512) ? launch_gemm<512, EPI_RES_LN>(h->tm_ATT, w.tm_out, p, s)
+                      : launch_gemm<256, EPI_RES_LN>(h->tm_ATT, w.tm_out, p, s);
+      if (rc) return rc;
+    }
+    {
+      GemmParams p{};
+      p.M = M, p.N = ff, p.K = d, p.bias = w.b1, p.out_bf16 = h->Hb, p.ld_bf16 = ff;
+      if ((rc = launch_gemm<256, EPI_BIAS_GELU_BF16>(h->tm_Xb, w.tm_w1, p, s))) return rc;
+    }
+    {
+      GemmParams p{};
+      p.M = M, p.N = d, p.K = ff, p.bias = w.b2, p.X = h->X, p.Xb = h->Xb, p.gamma = w.g2, p.beta = w.be2;
+      rc = (d == 512) ? launch_gemm<512, EPI_RES_LN>(h->tm_H, w.tm_w2, p, s)
+                      : launch_gemm<256, EPI_RES_LN>(h->tm_H, w.tm_w2, p, s);
+      if (rc) return rc;
+    }
+  }
+  {  // final projection + DDPM posterior
+    GemmParams p{};
+    p.M = M, p.N = h->nfeat, p.K = d, p.bias = h->b_fin, p.T = T, p.S = S, p.P0 = 5, p.nfeat = h->nfeat;
+    p.x_t = x_t, p.x_out = x_out, p.x0_out = x0_out, p.noise = noise, p.t_ptr = t_ptr, p.c1 = h->c1, p.c2 = h->c2,
+    p.sigma = h->sigma, p.seed = seed;
+    if ((rc = launch_gemm<128, EPI_POSTERIOR>(h->tm_Xb, h->tm_wfin, p, s))) return rc;
+  }
+  return TAMF_OK;
+}
+
+static void drop_graph(tamf_denoiser* h) {
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  h->graph_exec = nullptr;
+}
+
+}  // namespace tamf
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int tamf_denoiser_destroy(tamf_denoiser* h) {
+  if (!h) return TAMF_OK;
+  drop_graph(h);
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+  return TAMF_OK;
+}
+
+extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w, tamf_denoiser** out) {
+  TAMF_REQUIRE(cfg && w && out, TAMF_E_BADARG, "tamf_denoiser_create: null argument");
+  int rc = check_device();
+  if (rc) return rc;
+  const int d = cfg->latent_dim, ff = cfg->ff_size, L = cfg->num_layers, H = cfg->num_heads, nf = cfg->input_dim;
+  TAMF_REQUIRE(d == 256 || d == 512, TAMF_E_BADARG, "latent_dim must be 256 or 512 (arch_mdm / arch_mdm_l)");
+  TAMF_REQUIRE(H > 0 && d % H == 0 && (d / H == 64 || d / H == 128), TAMF_E_BADARG, "head_dim must be 64 or 128");
+  TAMF_REQUIRE(ff % 256 == 0 && ff >= 256, TAMF_E_BADARG, "ff_size must be a multiple of 256");
+  TAMF_REQUIRE(nf > 0 && nf <= KPAD, TAMF_E_BADARG, "input_dim must be <= 128");
+  TAMF_REQUIRE(L > 0 && L <= 64 && w->layers, TAMF_E_BADARG, "bad num_layers");
+  TAMF_REQUIRE(cfg->num_steps > 0 && w->pe && w->pe_rows >= cfg->num_steps, TAMF_E_BADARG,
+               "pe table must cover num_steps rows");
+  TAMF_REQUIRE(w->posterior_mean_coef1 && w->posterior_mean_coef2 && w->posterior_log_variance_clipped, TAMF_E_BADARG,
+               "missing schedule tables");
+  tamf_denoiser* h = new tamf_denoiser();
+  h->cfg = *cfg, h->d = d, h->ff = ff, h->L = L, h->H = H, h->nfeat = nf;
+#define TRY(x)                  \
+  if ((rc = (x)) != TAMF_OK) {  \
+    tamf_denoiser_destroy(h);   \
+    return rc;                  \
+  }
+  TRY(upload_f32(h, &h->shape_w, w->shape_w, (size_t)d * cfg->hand_shape_dim));
+  TRY(upload_f32(h, &h->shape_b, w->shape_b, d));
+  TRY(upload_f32(h, &h->objemb_w, w->objemb_w, (size_t)d * cfg->obj_embed_dim));
+  TRY(upload_f32(h, &h->objemb_b, w->objemb_b, d));
+  TRY(upload_f32(h, &h->objtraj_w, w->objtraj_w, (size_t)d * cfg->obj_input_dim));
+  TRY(upload_f32(h, &h->objtraj_b, w->objtraj_b, d));
+  TRY(upload_f32(h, &h->merge0_w, w->merge0_w, (size_t)d * 2 * d));
+  TRY(upload_f32(h, &h->text_w, w->text_w, (size_t)d * cfg->clip_dim));
+  TRY(upload_f32(h, &h->text_b, w->text_b, d));
+  h->pe_rows = w->pe_rows;
+  TRY(upload_f32(h, &h->pe, w->pe, (size_t)w->pe_rows * d));
+  TRY(upload_f32(h, &h->b_m2, w->merge2_b, d));
+  TRY(upload_f32(h, &h->b_fin, w->final_b, nf));
+  {
+    // fold input_process.poseEmbedding through the hand half of input_merge.0 (exact in real arithmetic):
+    //   W1a (Wp x + bp) = (W1a Wp) x + W1a bp ;  accumulated in double, rounded once.
+    TAMF_REQUIRE(w->pose_w && w->pose_b && w->merge0_w && w->merge0_b, TAMF_E_BADARG, "null weight pointer");
+    std::vector<float> wf((size_t)d * nf), mb(d);
+    std::vector<double> row(nf);
+    for (int n = 0; n < d; ++n) {
+      for (int k = 0; k < nf; ++k) row[k] = 0.0;
+      double bacc = (double)w->merge0_b[n];
+      for (int j = 0; j < d; ++j) {
+        const double a = (double)w->merge0_w[(size_t)n * 2 * d + j];
+        const float* pr = w->pose_w + (size_t)j * nf;
+        for (int k = 0; k < nf; ++k) row[k] += a * (double)pr[k];
+        bacc += a * (double)w->pose_b[j];
+      }
+      for (int k = 0; k < nf; ++k) wf[(size_t)n * nf + k] = (float)row[k];
+      mb[n] = (float)bacc;
+    }
+    TRY(upload_bf16(h, &h->wfold, wf.data(), d, nf, KPAD));
+    TRY(upload_f32(h, &h->merge_bias, mb.data(), d));
+  }
+  TRY(upload_bf16(h, &h->wm2, w->merge2_w, d, d, d));
+  TRY(upload_bf16(h, &h->wfin, w->final_w, nf, d, d));
+  TRY(make_tmap_2d_bf16(&h->tm_wfold, h->wfold, KPAD, d, (uint64_t)KPAD * 2, 64, 256));
+  TRY(make_tmap_2d_bf16(&h->tm_wm2, h->wm2, d, d, (uint64_t)d * 2, 64, 256));
+  TRY(make_tmap_2d_bf16(&h->tm_wfin, h->wfin, d, nf, (uint64_t)d * 2, 64, 128));
+  h->layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    const tamf_layer_weights& s = w->layers[l];
+    LayerDev& o = h->layers[l];
+    TRY(upload_bf16(h, &o.w_in, s.in_proj_w, 3 * d, d, d));
+    TRY(upload_bf16(h, &o.w_out, s.out_proj_w, d, d, d));
+    TRY(upload_bf16(h, &o.w1, s.lin1_w, ff, d, d));
+    TRY(upload_bf16(h, &o.w2, s.lin2_w, d, ff, ff));
+    TRY(upload_f32(h, &o.b_in, s.in_proj_b, 3 * d));
+    TRY(upload_f32(h, &o.b_out, s.out_proj_b, d));
+    TRY(upload_f32(h, &o.b1, s.lin1_b, ff));
+    TRY(upload_f32(h, &o.b2, s.lin2_b, d));
+    TRY(upload_f32(h, &o.g1, s.norm1_w, d));
+    TRY(upload_f32(h, &o.be1, s.norm1_b, d));
+    TRY(upload_f32(h, &o.g2, s.norm2_w, d));
+    TRY(upload_f32(h, &o.be2, s.norm2_b, d));
+    TRY(make_tmap_2d_bf16(&o.tm_in, o.w_in, d, 3 * d, (uint64_t)d * 2, 64, 256));
+    TRY(make_tmap_2d_bf16(&o.tm_out, o.w_out, d, d, (uint64_t)d * 2, 64, 256));
+    TRY(make_tmap_2d_bf16(&o.tm_w1, o.w1, d, ff, (uint64_t)d * 2, 64, 256));
+    TRY(make_tmap_2d_bf16(&o.tm_w2, o.w2, ff, d, (uint64_t)ff * 2, 64, 256));
+  }
+  {
+    // schedule: fp32 lookups exactly like _extract_into_tensor(...).float() (gaussian_diffusion.py:1275);
+    // sigma[t] = 1[t != 0] * exp(0.5 * logvar[t]) evaluated in fp32 (:459)
+    const int n = cfg->num_steps;
+    std::vector<float> c1(n), c2(n), sg(n);
+    for (int t = 0; t < n; ++t) {
+      c1[t] = (float)w->posterior_mean_coef1[t];
+      c2[t] = (float)w->posterior_mean_coef2[t];
+      sg[t] = (t == 0) ? 0.f : expf(0.5f * (float)w->posterior_log_variance_clipped[t]);
+    }
+    TRY(upload_f32(h, &h->c1, c1.data(), n));
+    TRY(upload_f32(h, &h->c2, c2.data(), n));
+    TRY(upload_f32(h, &h->sigma, sg.data(), n));
+  }
+  {
+    // timestep-token table ttab[t] = time_embed(pe[t]) (TimestepEmbedder, interaction_segment_mdm.py:208-215)
+    float *t0w, *t0b, *t2w, *t2b, *tmp;
+    TRY(upload_f32(h, &t0w, w->time0_w, (size_t)d * d));
+    TRY(upload_f32(h, &t0b, w->time0_b, d));
+    TRY(upload_f32(h, &t2w, w->time2_w, (size_t)d * d));
+    TRY(upload_f32(h, &t2b, w->time2_b, d));
+    const int n = cfg->num_steps;
+    TRY(dev_alloc(h, (void**)&tmp, (size_t)n * d * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&h->ttab, (size_t)n * d * sizeof(float)));
+    TRY(linear_f32(h->pe, d, t0w, d, t0b, tmp, d, n, d, d, 1, nullptr, 0, 0));
+    TRY(linear_f32(tmp, d, t2w, d, t2b, h->ttab, d, n, d, d, 0, nullptr, 0, 0));
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      set_error("tamf_denoiser_create: timestep table kernels failed");
+      tamf_denoiser_destroy(h);
+      return TAMF_E_CUDA;
+    }
+  }
+  TRY((configure_gemm<256, EPI_ADD_SILU_BF16>()));
+  TRY((configure_gemm<256, EPI_TOKEN_OUT>()));
+  TRY((configure_gemm<256, EPI_BIAS_BF16>()));
+  TRY((configure_gemm<256, EPI_BIAS_GELU_BF16>()));
+  TRY((configure_gemm<256, EPI_RES_LN>()));
+  TRY((configure_gemm<512, EPI_RES_LN>()));
+  TRY((configure_gemm<128, EPI_POSTERIOR>()));
+  TRY(configure_attn<64>());
+  TRY(configure_attn<128>());
+#undef TRY
+  *out = h;
+  return TAMF_OK;
+}
+
+namespace tamf {
+struct WsLayout {
+  size_t off[32];
+  size_t total;
+};
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+static WsLayout ws_layout(const tamf_denoiser* h, int B, int T) {
+  const size_t d = h->d, ff = h->ff, S = T + 5, M = (size_t)B * S, Mf = (size_t)B * T;
+  const size_t sz[] = {
+      M * d * 4,                                 // 0 X
+      M * d * 2,                                 // 1 Xb
+      M * 3 * d * 2,                             // 2 QKV
+      M * d * 2,                                 // 3 ATT
+      M * ff * 2,                                // 4 H
+      Mf * KPAD * 2,                             // 5 A0
+      Mf * d * 2,                                // 6 H0
+      Mf * d * 4,                                // 7 objhalf
+      (size_t)B * 4 * d * 4,                     // 8 prefix
+      Mf * d * 4,                                // 9 objtok
+      Mf * 9 * 4,                                // 10 trajmean
+      (size_t)B * 16 * 4,                        // 11 shapemean
+      (size_t)B * h->cfg.obj_embed_dim * 4,      // 12 embmean
+      (size_t)B * h->nfeat * T * 4,              // 13 xbuf
+      (size_t)B * h->cfg.clip_dim * 4,           // 14 st_text
+      (size_t)B * T * 10 * 4,                    // 15 st_shape
+      (size_t)B * MAX_NOBJ * T * 9 * 4,          // 16 st_traj
+      (size_t)B * MAX_NOBJ * h->cfg.obj_embed_dim * 4,  // 17 st_emb
+      (size_t)B * 4,                             // 18 st_side
+      (size_t)B * 4,                             // 19 t_dev
+  };
+  WsLayout L{};
+  size_t o = 0;
+  for (int i = 0; i < 20; ++i) {
+    L.off[i] = o;
+    o += al(sz[i]);
+  }
+  L.total = o;
+  return L;
+}
+}  // namespace tamf
+
+extern "C" size_t tamf_denoiser_workspace_bytes(const tamf_denoiser* h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return ws_layout(h, B, T).total;
+}
+
+extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size_t ws_bytes) {
+  TAMF_REQUIRE(h && ws, TAMF_E_BADARG, "tamf_denoiser_bind: null argument");
+  TAMF_REQUIRE(B > 0 && T > 0, TAMF_E_BADARG, "tamf_denoiser_bind: B and T must be positive");
+  TAMF_REQUIRE(T + 5 <= ATT_KP, TAMF_E_BADARG, "tamf_denoiser_bind: T + 5 tokens must be <= 176");
+  TAMF_REQUIRE(T + 5 <= h->pe_rows, TAMF_E_BADARG, "tamf_denoiser_bind: pe table too short");
+  TAMF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, TAMF_E_ALIGN, "workspace must be 256-byte aligned");
+  WsLayout L = ws_layout(h, B, T);
+  TAMF_REQUIRE(ws_bytes >= L.total, TAMF_E_BADARG, "tamf_denoiser_bind: workspace too small");
+  drop_graph(h);
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  h->B = B, h->T = T, h->S = T + 5, h->M = B * (T + 5), h->Mf = B * T;
+  h->X = (float*)(p + L.off[0]);
+  h->Xb = (__nv_bfloat16*)(p + L.off[1]);
+  h->QKV = (__nv_bfloat16*)(p + L.off[2]);
+  h->ATT = (__nv_bfloat16*)(p + L.off[3]);
+  h->Hb = (__nv_bfloat16*)(p + L.off[4]);
+  h->A0 = (__nv_bfloat16*)(p + L.off[5]);
+  h->H0 = (__nv_bfloat16*)(p + L.off[6]);
+  h->objhalf = (float*)(p + L.off[7]);
+  h->prefix = (float*)(p + L.off[8]);
+  h->objtok = (float*)(p + L.off[9]);
+  h->trajmean = (float*)(p + L.off[10]);
+  h->shapemean = (float*)(p + L.off[11]);
+  h->embmean = (float*)(p + L.off[12]);
+  h->xbuf = (float*)(p + L.off[13]);
+  h->st_text = (float*)(p + L.off[14]);
+  h->st_shape = (float*)(p + L.off[15]);
+  h->st_traj = (float*)(p + L.off[16]);
+  h->st_emb = (float*)(p + L.off[17]);
+  h->st_side = (int*)(p + L.off[18]);
+  h->t_dev = (int*)(p + L.off[19]);
+  const int d = h->d, ff = h->ff;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&h->tm_Xb, h->Xb, d, h->M, (uint64_t)d * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&h->tm_ATT, h->ATT, d, h->M, (uint64_t)d * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&h->tm_H, h->Hb, ff, h->M, (uint64_t)ff * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&h->tm_A0, h->A0, KPAD, h->Mf, (uint64_t)KPAD * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&h->tm_H0, h->H0, d, h->Mf, (uint64_t)d * 2, 64, 128))) return rc;
+  h->bound = true;
+  h->cond_set = false;
+  return TAMF_OK;
+}
+
+extern "C" int tamf_denoiser_set_cond(tamf_denoiser* h, const float* text_feat, const int32_t* hand_side,
+                                      const float* shape, const float* obj_traj, const float* obj_emb, int nobj_max,
+                                      void* stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  TAMF_REQUIRE(h && h->bound, TAMF_E_STATE, "tamf_denoiser_set_cond: bind a workspace first");
+  TAMF_REQUIRE(text_feat && hand_side && shape && obj_traj && obj_emb, TAMF_E_BADARG, "set_cond: null pointer");
+  TAMF_REQUIRE(nobj_max >= 1, TAMF_E_BADARG, "set_cond: nobj_max must be >= 1");
+  const int d = h->d, B = h->B, T = h->T, Mf = h->Mf;
+  const tamf_cfg& c = h->cfg;
+  int rc;
+  // means over frames / (padded) objects: interaction_segment_mdm.py:300, :260, :245
+  {
+    size_t n = (size_t)B * c.hand_shape_dim;
+    mean_axis_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(shape, h->shapemean, B, T, c.hand_shape_dim);
+    TAMF_LAUNCH_CHECK();
+    n = (size_t)B * c.obj_embed_dim;
+    mean_axis_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(obj_emb, h->embmean, B, nobj_max, c.obj_embed_dim);
+    TAMF_LAUNCH_CHECK();
+    n = (size_t)Mf * 9;
+    TAMF_REQUIRE(c.obj_input_dim == 9, TAMF_E_BADARG, "obj_input_dim must be 9");
+    traj_mean_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(obj_traj, h->trajmean, B, nobj_max, T);
+    TAMF_LAUNCH_CHECK();
+  }
+  // prefix tokens 1..4 -> prefix[b, 0..3, :]
+  if ((rc = linear_f32(text_feat, c.clip_dim, h->text_w, c.clip_dim, h->text_b, h->prefix + 0 * d, 4 * d, B, d,
+                       c.clip_dim, 0, nullptr, 0, s)))
+    return rc;
+  if ((rc = linear_f32(h->shapemean, c.hand_shape_dim, h->shape_w, c.hand_shape_dim, h->shape_b, h->prefix + 2 * d,
+                       4 * d, B, d, c.hand_shape_dim, 0, nullptr, 0, s)))
+    return rc;
+  if ((rc = linear_f32(h->embmean, c.obj_embed_dim, h->objemb_w, c.obj_embed_dim, h->objemb_b, h->prefix + 3 * d, 4 * d,
+                       B, d, c.obj_embed_dim, 0, nullptr, 0, s)))
+    return rc;
+  {
+    const size_t n = (size_t)B * 4 * d;
+    prefix_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->prefix, hand_side, h->pe, B, d);
+    TAMF_LAUNCH_CHECK();
+  }
+  // object half of input_merge.0 (+ all constant biases): obj_half = obj_tok . W1b^T + (b1 + W1a bp)
+  if ((rc = linear_f32(h->trajmean, 9, h->objtraj_w, 9, h->objtraj_b, h->objtok, d, Mf, d, 9, 0, nullptr, 0, s)))
+    return rc;
+  if ((rc = linear_f32(h->objtok, d, h->merge0_w + d, 2 * d, h->merge_bias, h->objhalf, d, Mf, d, d, 0, nullptr, 0, s)))
+    return rc;
+  h->cond_set = true;
+  return TAMF_OK;
+}
+
+extern "C" int tamf_denoiser_forward(tamf_denoiser* h, const float* x_t, const int32_t* t, float* x0_out, void* stream) {
+  TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_denoiser_forward: bind + set_cond first");
+  TAMF_REQUIRE(x_t && t && x0_out, TAMF_E_BADARG, "tamf_denoiser_forward: null pointer");
+  return enqueue_step(h, x_t, t, nullptr, x0_out, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int tamf_p_sample_step(tamf_denoiser* h, float* x_io, int t, const float* noise, uint64_t seed,
+                                  float* x0_out, void* stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_p_sample_step: bind + set_cond first");
+  TAMF_REQUIRE(x_io, TAMF_E_BADARG, "tamf_p_sample_step: null pointer");
+  TAMF_REQUIRE(t >= 0 && t < h->cfg.num_steps, TAMF_E_BADARG, "tamf_p_sample_step: t out of range");
+  fill_int_kernel<<<(h->B + 255) / 256, 256, 0, s>>>(h->t_dev, h->B, t);
+  TAMF_LAUNCH_CHECK();
+  return enqueue_step(h, x_io, h->t_dev, x_io, x0_out, noise, seed, s);
+}
+
+extern "C" int tamf_p_sample_chain(tamf_denoiser* h, float* x_io, int t_start, int t_end, uint64_t seed,
+                                   void* stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_p_sample_chain: bind + set_cond first");
+  TAMF_REQUIRE(x_io, TAMF_E_BADARG, "tamf_p_sample_chain: null pointer");
+  TAMF_REQUIRE(t_start < h->cfg.num_steps && t_end >= 0 && t_end <= t_start, TAMF_E_BADARG,
+               "tamf_p_sample_chain: need num_steps > t_start >= t_end >= 0");
+  if (!h->graph_exec || h->graph_x != x_io || h->graph_seed != seed || h->graph_stream != s) {
+    drop_graph(h);
+    cudaStream_t cap = s;
+    cudaStream_t own = nullptr;
+    if (cap == nullptr) {  // the legacy default stream cannot be captured
+      TAMF_CUDA_CHECK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+      cap = own;
+    }
+    cudaGraph_t g = nullptr;
+    TAMF_CUDA_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    const uint64_t before = g_launches.load();
+    int rc = enqueue_step(h, x_io, h->t_dev, x_io, nullptr, nullptr, seed, cap);
+    if (rc == TAMF_OK) {
+      add_int_kernel<<<(h->B + 255) / 256, 256, 0, cap>>>(h->t_dev, h->B, -1);
+      count_launch();
+    }
+    g_launches.store(before);  // capture records, it does not launch; replays are counted below
+    cudaError_t e = cudaStreamEndCapture(cap, &g);
+    if (own) cudaStreamDestroy(own);
+    if (rc != TAMF_OK) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    TAMF_CUDA_CHECK(e);
+    e = cudaGraphInstantiate(&h->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    TAMF_CUDA_CHECK(e);
+    h->graph_x = x_io, h->graph_seed = seed, h->graph_stream = s;
+  }
+  fill_int_kernel<<<(h->B + 255) / 256, 256, 0, s>>>(h->t_dev, h->B, t_start);
+  TAMF_LAUNCH_CHECK();
+  const int per_step = 2 + 5 * h->L + 2 + 1;
+  for (int t = t_start; t >= t_end; --t) {
+    TAMF_CUDA_CHECK(cudaGraphLaunch(h->graph_exec, s));
+    count_launch(per_step);
+  }
+  return TAMF_OK;
+}
+
+extern "C" int tamf_p_sample_loop_host(tamf_denoiser* h, const float* text_feat, const int32_t* hand_side,
+                                       const float* shape, const float* obj_traj, const float* obj_emb, int nobj_max,
+                                       const float* x_T, uint64_t seed, float* sample_out, void* stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  TAMF_REQUIRE(h && h->bound, TAMF_E_STATE, "tamf_p_sample_loop_host: bind a workspace first");
+  TAMF_REQUIRE(text_feat && hand_side && shape && obj_traj && obj_emb && sample_out, TAMF_E_BADARG,
+               "tamf_p_sample_loop_host: null pointer");
+  TAMF_REQUIRE(nobj_max >= 1 && nobj_max <= MAX_NOBJ, TAMF_E_BADARG, "tamf_p_sample_loop_host: 1 <= nobj_max <= 8");
+  const int B = h->B, T = h->T;
+  const tamf_cfg& c = h->cfg;
+  const size_t nx = (size_t)B * h->nfeat * T;
+  TAMF_CUDA_CHECK(cudaMemcpyAsync(h->st_text, text_feat, (size_t)B * c.clip_dim * 4, cudaMemcpyHostToDevice, s));
+  TAMF_CUDA_CHECK(cudaMemcpyAsync(h->st_side, hand_side, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+  TAMF_CUDA_CHECK(cudaMemcpyAsync(h->st_shape, shape, (size_t)B * T * 10 * 4, cudaMemcpyHostToDevice, s));
+  TAMF_CUDA_CHECK(cudaMemcpyAsync(h->st_traj, obj_traj, (size_t)B * nobj_max * T * 9 * 4, cudaMemcpyHostToDevice, s));
+  TAMF_CUDA_CHECK(
+      cudaMemcpyAsync(h->st_emb, obj_emb, (size_t)B * nobj_max * c.obj_embed_dim * 4, cudaMemcpyHostToDevice, s));
+  int rc = tamf_denoiser_set_cond(h, h->st_text, h->st_side, h->st_shape, h->st_traj, h->st_emb, nobj_max, s);
+  if (rc) return rc;
+  if (x_T) {
+    TAMF_CUDA_CHECK(cudaMemcpyAsync(h->xbuf, x_T, nx * 4, cudaMemcpyHostToDevice, s));
+  } else {
+    if ((rc = philox_fill(h->xbuf, nx, seed, (uint32_t)c.num_steps, s))) return rc;  // th.randn(*shape), :604
+  }
+  if ((rc = tamf_p_sample_chain(h, h->xbuf, c.num_steps - 1, 0, seed, s))) return rc;
+  TAMF_CUDA_CHECK(cudaMemcpyAsync(sample_out, h->xbuf, nx * 4, cudaMemcpyDeviceToHost, s));
+  TAMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  return TAMF_OK;
+}

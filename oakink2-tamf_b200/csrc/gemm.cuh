@@ -1,0 +1,389 @@
+// gemm.cuh -- persistent warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   C[M,N] = A[M,K] (bf16, K-major) . W[N,K]^T (bf16, K-major = nn.Linear layout), fp32 accumulation in TMEM.
+//
+// One CTA per SM, 320 threads:
+//   warps 0-7  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (warp w owns TMEM lanes 32*(w%4).., column half
+//              w/4), apply the fused epilogue, store to global.
+//   warp 8     TMA producer: cp.async.bulk.tensor 2D loads of the 128x64 A tile and BNx64 W tile (128B swizzle)
+//              into a STAGES-deep shared-memory ring, signalled through mbarriers (expect_tx / complete_tx).
+//   warp 9     MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256, K=16) on
+//              shared-memory descriptors; tcgen05.commit releases ring slots and publishes accumulators.
+// The accumulator is double-buffered in TMEM when 2*BN <= 512 columns, so the epilogue of tile i overlaps the
+// mainloop of tile i+1 (persistent static round-robin tile schedule).
+//
+// Epilogues (what the reference runs as separate ATen kernels, SURVEY.md 2.4 K1,K3-K6,K9):
+//   EPI_BIAS_BF16      y = acc + b                                   -> bf16            (QKV in_proj)
+//   EPI_BIAS_GELU_BF16 y = gelu_erf(acc + b)                         -> bf16            (linear1 + F.gelu)
+//   EPI_ADD_SILU_BF16  y = silu(acc + addmat[m,n])                   -> bf16            (input_merge.0, hand half)
+//   EPI_TOKEN_OUT      y = nan_to_num(acc + b) + pe[P0+tau]          -> fp32 + bf16 token rows (input_merge.2)
+//   EPI_RES_LN         x = LayerNorm(x + acc + b) (eps 1e-5, biased var) in place -> fp32 + bf16 (BN == N == d)
+//   EPI_POSTERIOR      x0 = nan_to_num(acc + b); x_{t-1} = c1 x0 + c2 x_t + sigma eps  -> [B,99,1,T] fp32
+//   EPI_F32            y = acc + b -> fp32 (self-test)
+#pragma once
+#include "common.cuh"
+
+namespace tamf {
+
+enum GemmEpi {
+  EPI_BIAS_BF16 = 0,
+  EPI_BIAS_GELU_BF16 = 1,
+  EPI_ADD_SILU_BF16 = 2,
+  EPI_TOKEN_OUT = 3,
+  EPI_RES_LN = 4,
+  EPI_POSTERIOR = 5,
+  EPI_F32 = 6,
+};
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;  // [N] (may be null -> 0)
+  // bf16 / fp32 row-major outputs
+  __nv_bfloat16* out_bf16;
+  int ld_bf16;
+  float* out_f32;
+  int ld_f32;
+  // EPI_ADD_SILU_BF16
+  const float* addmat;  // [M,N]
+  // EPI_TOKEN_OUT: GEMM row m = b*T + tau  ->  token row b*S + P0 + tau
+  const float* pe;  // [rows, N]
+  int T, S, P0;
+  // EPI_RES_LN: X fp32 [M,N] residual in / normalised out; Xb bf16 copy
+  float* X;
+  __nv_bfloat16* Xb;
+  const float* gamma;
+  const float* beta;
+  // EPI_POSTERIOR: GEMM row m = b*S + s (token); frame tau = s - P0
+  const float* x_t;    // [B,nfeat,1,T]
+  float* x_out;        // x_{t-1}, may alias x_t; null -> forward only
+  float* x0_out;       // may be null
+  const float* noise;  // null -> Philox
+  const int* t_ptr;    // [B]
+  const float *c1, *c2, *sigma;  // [num_steps] fp32
+  unsigned long long seed;
+  int nfeat;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 320;
+constexpr int GEMM_EPI_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 128) ? 6 : (BN == 256 ? 4 : 2);
+  static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 256) ? 256 : 512;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2048 /*barriers + scratch*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES, ACC = Cfg::ACC_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;      // [ACC]
+  uint64_t* tempty_bar = bars + 2 * STAGES + ACC;  // [ACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC);
+  float* s_red = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // [2][128] LN exchange
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < ACC; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);  // one elected lane per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, m0);
+#pragma unroll
+          for (int h = 0; h < (BN + 255) / 256; ++h)  // TMA box rows <= 256
+            tma_load_2d(sB + stage * Cfg::B_BYTES + h * 256 * GEMM_BK * 2, &tmB, &full_bar[stage], kb * GEMM_BK,
+                        n0 + h * 256);
+          if (++stage == STAGES) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr int UN = (BN > 256) ? 256 : BN;  // N per instruction
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, UN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t ad = umma_desc_k_sw128(a_addr + k * 32);
+#pragma unroll
+            for (int h = 0; h < BN / UN; ++h) {
+              const uint64_t bd = umma_desc_k_sw128(b_addr + h * UN * GEMM_BK * 2 + k * 32);
+              umma_bf16(d_tmem + h * UN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == STAGES) stage = 0, phase ^= 1u;
+        }
+        if (++acc == ACC) acc = 0, acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0..7) =====================
+    const int lq = warp & 3, ch = warp >> 2;
+    const int row_in_tile = lq * 32 + lane;
+    constexpr int HALF = BN / 2;
+    constexpr int CHUNKS = HALF / 32;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * BN;
+      const int row = m0 + row_in_tile;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lq * 32) << 16) + ch * HALF;
+
+      if constexpr (EPI == EPI_RES_LN) {
+        // ---- pass 1: v = acc + bias + residual -> back to TMEM; row sum ----
+        float sum = 0.f;
+        const float* xrow = p.X + (size_t)(row_ok ? row : 0) * p.N;
+#pragma unroll 1
+        for (int ck = 0; ck < CHUNKS; ++ck) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ck * 32, v);
+          tc_wait_ld();
+          const int c0 = ch * HALF + ck * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(p.bias + c0 + j);
+            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok) r4 = *reinterpret_cast<const float4*>(xrow + c0 + j);
+            float y0 = __uint_as_float(v[j]) + b4.x + r4.x, y1 = __uint_as_float(v[j + 1]) + b4.y + r4.y;
+            float y2 = __uint_as_float(v[j + 2]) + b4.z + r4.z, y3 = __uint_as_float(v[j + 3]) + b4.w + r4.w;
+            sum += (y0 + y1) + (y2 + y3);
+            v[j] = __float_as_uint(y0), v[j + 1] = __float_as_uint(y1);
+            v[j + 2] = __float_as_uint(y2), v[j + 3] = __float_as_uint(y3);
+          }
+          tmem_st32(taddr + ck * 32, v);
+        }
+        tc_wait_st();
+        s_red[ch * 128 + row_in_tile] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mean = (s_red[row_in_tile] + s_red[128 + row_in_tile]) / (float)p.N;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // ---- pass 2: centred second moment ----
+        float sq = 0.f;
+#pragma unroll 1
+        for (int ck = 0; ck < CHUNKS; ++ck) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ck * 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = __uint_as_float(v[j]) - mean;
+            sq = fmaf(d, d, sq);
+          }
+        }
+        s_red[ch * 128 + row_in_tile] = sq;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float var = (s_red[row_in_tile] + s_red[128 + row_in_tile]) / (float)p.N;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        // ---- pass 3: normalise, affine, write fp32 residual stream + bf16 operand copy ----
+#pragma unroll 1
+        for (int ck = 0; ck < CHUNKS; ++ck) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ck * 32, v);
+          tc_wait_ld();
+          const int c0 = ch * HALF + ck * 32;
+          if (row_ok) {
+            float* xo = p.X + (size_t)row * p.N + c0;
+            __nv_bfloat16* xb = p.Xb + (size_t)row * p.N + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float y[8];
+#pragma unroll
+              for (int e = 0; e < 8; e += 4) {
+                const float4 g4 = *reinterpret_cast<const float4*>(p.gamma + c0 + j + e);
+                const float4 be4 = *reinterpret_cast<const float4*>(p.beta + c0 + j + e);
+                y[e + 0] = (__uint_as_float(v[j + e + 0]) - mean) * rstd * g4.x + be4.x;
+                y[e + 1] = (__uint_as_float(v[j + e + 1]) - mean) * rstd * g4.y + be4.y;
+                y[e + 2] = (__uint_as_float(v[j + e + 2]) - mean) * rstd * g4.z + be4.z;
+                y[e + 3] = (__uint_as_float(v[j + e + 3]) - mean) * rstd * g4.w + be4.w;
+                *reinterpret_cast<float4*>(xo + j + e) = make_float4(y[e], y[e + 1], y[e + 2], y[e + 3]);
+              }
+              *reinterpret_cast<uint4*>(xb + j) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                             pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int ck = 0; ck < CHUNKS; ++ck) {
+          uint32_t v[32];
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+          tmem_ld32(taddr + ck * 32, v);
+          tc_wait_ld();
+          const int c0 = n0 + ch * HALF + ck * 32;  // global column of v[0]
+          if constexpr (EPI == EPI_POSTERIOR) {
+            const int b = row / p.S, s = row % p.S;
+            if (row_ok && s >= p.P0 && c0 < p.nfeat) {
+            const int tau = s - p.P0;
+            const int t = p.t_ptr[b];
+            const float k1 = p.c1[t], k2 = p.c2[t], sg = p.sigma[t];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int f = c0 + j;
+              if (f < p.nfeat) {
+                const size_t e = ((size_t)b * p.nfeat + f) * p.T + tau;
+                const float x0 = nan_to_num(__uint_as_float(v[j]) + p.bias[f]);
+                if (p.x0_out) p.x0_out[e] = x0;
+                if (p.x_out) {
+                  const float eps = p.noise ? p.noise[e] : philox_normal(p.seed, (uint32_t)t, e);
+                  p.x_out[e] = (k1 * x0 + k2 * p.x_t[e]) + sg * eps;
+                }
+              }
+            }
+            }
+          } else if (row_ok && c0 < p.N) {
+            float y[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + c0 + j);
+              y[j] = __uint_as_float(v[j]) + b4.x, y[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+              y[j + 2] = __uint_as_float(v[j + 2]) + b4.z, y[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+            if constexpr (EPI == EPI_F32) {
+              float* o = p.out_f32 + (size_t)row * p.ld_f32 + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            } else if constexpr (EPI == EPI_TOKEN_OUT) {
+              const int b = row / p.T, tau = row % p.T;
+              const size_t orow = (size_t)b * p.S + p.P0 + tau;
+              const float* per = p.pe + (size_t)(p.P0 + tau) * p.N + c0;
+              float* xo = p.X + orow * p.N + c0;
+              __nv_bfloat16* xb = p.Xb + orow * p.N + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+#pragma unroll
+                for (int e = 0; e < 8; e += 4) {
+                  const float4 pe4 = *reinterpret_cast<const float4*>(per + j + e);
+                  y[j + e + 0] = nan_to_num(y[j + e + 0]) + pe4.x, y[j + e + 1] = nan_to_num(y[j + e + 1]) + pe4.y;
+                  y[j + e + 2] = nan_to_num(y[j + e + 2]) + pe4.z, y[j + e + 3] = nan_to_num(y[j + e + 3]) + pe4.w;
+                  *reinterpret_cast<float4*>(xo + j + e) = make_float4(y[j + e], y[j + e + 1], y[j + e + 2], y[j + e + 3]);
+                }
+                *reinterpret_cast<uint4*>(xb + j) =
+                    make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
+                               pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
+              }
+            } else {
+              if constexpr (EPI == EPI_ADD_SILU_BF16) {
+                const float* ar = p.addmat + (size_t)row * p.N + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 a4 = *reinterpret_cast<const float4*>(ar + j);
+                  y[j] = silu(y[j] + a4.x), y[j + 1] = silu(y[j + 1] + a4.y);
+                  y[j + 2] = silu(y[j + 2] + a4.z), y[j + 3] = silu(y[j + 3] + a4.w);
+                }
+              } else if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = gelu_erf(y[j]);
+              }
+              __nv_bfloat16* o = p.out_bf16 + (size_t)row * p.ld_bf16 + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(o + j) =
+                    make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
+                               pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
+            }
+          }
+        }
+      }
+      // accumulator stage drained -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == ACC) acc = 0, acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// host-side launcher ------------------------------------------------------------------------------
+int num_sms();
+
+template <int BN, int EPI>
+int configure_gemm() {  // once per process, outside any stream capture
+  TAMF_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GemmCfg<BN>::SMEM_BYTES));
+  return TAMF_OK;
+}
+
+template <int BN, int EPI>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}
+
+}  // namespace tamf

@@ -1,0 +1,262 @@
+// nn.cu -- exact brute-force chamfer nearest neighbour (K=1) and the fused hand->object distance.
+//
+// Replaces pytorch3d.ops.knn_points(K=1) behind ChamferDistance.forward
+// (thirdparty/chamfer_distance/chamfer_distance/chamfer_distance.py:147-162) and
+// SegmentRefineModel.multi_object_h2o_dist (src/oakink2_tamf/model/segment_refine_model.py:142-168).
+//
+// Layout: one CTA scans one (cloud n, candidate split s) pair for ALL queries of that cloud.  Candidates are
+// staged through shared memory as float4 (coalesced global reads, broadcast LDS.128 in the inner loop); each
+// thread keeps QPT queries in registers so one LDS feeds QPT distance evaluations.  Splits are merged with a
+// 64-bit atomicMin on (float_bits(d2) << 32 | idx): d2 >= 0 so the bit pattern orders like the value, and the
+// index in the low word makes the LOWEST index win exact ties -- the oracle's rule.  The int64 `idx` output
+// buffer itself is the packed scratch (memset to all-ones, finalised in place), so no workspace is needed.
+//
+// Arithmetic (bit-exact contract, oracle/nn_oracle.c): d = (dx*dx + dy*dy) + dz*dz with __fsub_rn/__fmul_rn/
+// __fadd_rn, which nvcc never contracts into FMA.
+#include "common.cuh"
+
+namespace tamf {
+
+constexpr int NN_QPT = 4;       // queries per thread
+constexpr int NN_CHUNK = 1024;  // candidates staged per shared-memory round (16 KB as float4)
+
+struct NNObj {  // one rigid object of a sequence (fused h2o mode)
+  int first;    // index of the sequence's first object in the packed cloud array
+  int count;    // number of objects of the sequence
+};
+
+__device__ __forceinline__ void nn_scan_chunk(const float4* __restrict__ sc, int n_c, int base_idx,
+                                              const float (&qx)[NN_QPT], const float (&qy)[NN_QPT],
+                                              const float (&qz)[NN_QPT], float (&best)[NN_QPT], int (&bidx)[NN_QPT]) {
+#pragma unroll 4
+  for (int j = 0; j < n_c; ++j) {
+    const float4 c = sc[j];
+#pragma unroll
+    for (int q = 0; q < NN_QPT; ++q) {
+      const float dx = __fsub_rn(qx[q], c.x), dy = __fsub_rn(qy[q], c.y), dz = __fsub_rn(qz[q], c.z);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (d < best[q]) {  // strict: ascending scan keeps the lowest index on ties
+        best[q] = d;
+        bidx[q] = base_idx + j;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void nn_publish(unsigned long long* packed, float best, int bidx) {
+  if (bidx >= 0) {
+    unsigned long long v = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)bidx;
+    atomicMin(packed, v);
+  }
+}
+
+// grid (N, splits); block = ceil(P1 / QPT) rounded up to a warp
+__global__ void __launch_bounds__(1024) nn_scan_kernel(const float* __restrict__ x, const float* __restrict__ y, int P1,
+                                                       int P2, int per_split, unsigned long long* __restrict__ packed) {
+  __shared__ float4 sc[NN_CHUNK];
+  const int n = blockIdx.x;
+  const int c_begin = blockIdx.y * per_split;
+  const int c_end = min(P2, c_begin + per_split);
+  const float* xn = x + (size_t)n * P1 * 3;
+  const float* yn = y + (size_t)n * P2 * 3;
+
+  float qx[NN_QPT], qy[NN_QPT], qz[NN_QPT], best[NN_QPT];
+  int bidx[NN_QPT];
+#pragma unroll
+  for (int q = 0; q < NN_QPT; ++q) {
+    const int i = threadIdx.x + q * blockDim.x;
+    const bool ok = i < P1;
+    qx[q] = ok ? xn[3 * i + 0] : 0.f;
+    qy[q] = ok ? xn[3 * i + 1] : 0.f;
+    qz[q] = ok ? xn[3 * i + 2] : 0.f;
+    best[q] = __int_as_float(0x7f800000);  // +inf
+    bidx[q] = -1;
+  }
+  for (int c0 = c_begin; c0 < c_end; c0 += NN_CHUNK) {
+    const int n_c = min(NN_CHUNK, c_end - c0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_c; j += blockDim.x) {
+      const float* p = yn + (size_t)(c0 + j) * 3;
+      sc[j] = make_float4(p[0], p[1], p[2], 0.f);
+    }
+    __syncthreads();
+    nn_scan_chunk(sc, n_c, c0, qx, qy, qz, best, bidx);
+  }
+#pragma unroll
+  for (int q = 0; q < NN_QPT; ++q) {
+    const int i = threadIdx.x + q * blockDim.x;
+    if (i < P1) nn_publish(packed + (size_t)n * P1 + i, best[q], bidx[q]);
+  }
+}
+
+// rot6d -> rotation matrix rows (src/dev_fn/transform/rotation.py:446-467; F.normalize eps 1e-12)
+__device__ __forceinline__ void rot6d_rows(const float* d6, float (&R)[9]) {
+  float a1x = d6[0], a1y = d6[1], a1z = d6[2], a2x = d6[3], a2y = d6[4], a2z = d6[5];
+  float n1 = fmaxf(sqrtf(a1x * a1x + a1y * a1y + a1z * a1z), 1e-12f);
+  float b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+  float dt = b1x * a2x + b1y * a2y + b1z * a2z;
+  float b2x = a2x - dt * b1x, b2y = a2y - dt * b1y, b2z = a2z - dt * b1z;
+  float n2 = fmaxf(sqrtf(b2x * b2x + b2y * b2y + b2z * b2z), 1e-12f);
+  b2x /= n2, b2y /= n2, b2z /= n2;
+  R[0] = b1x, R[1] = b1y, R[2] = b1z;
+  R[3] = b2x, R[4] = b2y, R[5] = b2z;
+  R[6] = b1y * b2z - b1z * b2y;
+  R[7] = b1z * b2x - b1x * b2z;
+  R[8] = b1x * b2y - b1y * b2x;
+}
+
+// Fused variant: grid (B*T, splits).  Candidate j of the sequence's concatenated cloud is object o = j / P,
+// point p = j % P, moved to the world by frame t's transform of object o while it is staged.
+__global__ void __launch_bounds__(1024)
+    h2o_scan_kernel(const float* __restrict__ verts, const float* __restrict__ obj_traj,
+                    const float* __restrict__ obj_points, const int* __restrict__ obj_first, int T, int V, int nobj_max,
+                    int P, int per_split, unsigned long long* __restrict__ packed) {
+  __shared__ float4 sc[NN_CHUNK];
+  __shared__ float sR[12];
+  const int f = blockIdx.x, b = f / T, t = f % T;
+  const int first = obj_first[b], nobj = obj_first[b + 1] - first;
+  const int P2 = nobj * P;
+  const int c_begin = blockIdx.y * per_split;
+  const int c_end = min(P2, c_begin + per_split);
+  const float* xn = verts + (size_t)f * V * 3;
+
+  float qx[NN_QPT], qy[NN_QPT], qz[NN_QPT], best[NN_QPT];
+  int bidx[NN_QPT];
+#pragma unroll
+  for (int q = 0; q < NN_QPT; ++q) {
+    const int i = threadIdx.x + q * blockDim.x;
+    const bool ok = i < V;
+    qx[q] = ok ? xn[3 * i + 0] : 0.f;
+    qy[q] = ok ? xn[3 * i + 1] : 0.f;
+    qz[q] = ok ? xn[3 * i + 2] : 0.f;
+    best[q] = __int_as_float(0x7f800000);
+    bidx[q] = -1;
+  }
+  int cur_obj = -1;
+  for (int c0 = c_begin; c0 < c_end;) {
+    const int o = c0 / P;
+    const int n_c = min(min(NN_CHUNK, c_end - c0), (o + 1) * P - c0);  // a chunk never straddles objects
+    __syncthreads();
+    if (o != cur_obj) {
+      if (threadIdx.x == 0) {
+        const float* tr = obj_traj + (((size_t)b * nobj_max + o) * T + t) * 9;
+        float R[9];
+        rot6d_rows(tr + 3, R);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sR[k] = R[k];
+        sR[9] = tr[0], sR[10] = tr[1], sR[11] = tr[2];
+      }
+      cur_obj = o;
+      __syncthreads();
+    }
+    const float* pts = obj_points + ((size_t)(first + o) * P + (c0 - o * P)) * 3;
+    for (int j = threadIdx.x; j < n_c; j += blockDim.x) {
+      const float px = pts[3 * j], py = pts[3 * j + 1], pz = pts[3 * j + 2];
+      // transf_point_array: R p + t   (src/dev_fn/transform/transform.py:36-53)
+      sc[j] = make_float4(fmaf(sR[2], pz, fmaf(sR[1], py, sR[0] * px)) + sR[9],
+                          fmaf(sR[5], pz, fmaf(sR[4], py, sR[3] * px)) + sR[10],
+                          fmaf(sR[8], pz, fmaf(sR[7], py, sR[6] * px)) + sR[11], 0.f);
+    }
+    __syncthreads();
+    nn_scan_chunk(sc, n_c, c0, qx, qy, qz, best, bidx);
+    c0 += n_c;
+  }
+#pragma unroll
+  for (int q = 0; q < NN_QPT; ++q) {
+    const int i = threadIdx.x + q * blockDim.x;
+    if (i < V) nn_publish(packed + (size_t)f * V + i, best[q], bidx[q]);
+  }
+}
+
+// packed -> (d2 | dist, idx) in place
+__global__ void nn_finalize_kernel(unsigned long long* __restrict__ packed, float* __restrict__ d_out, size_t n,
+                                   int take_sqrt) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long v = packed[i];
+  float d = __uint_as_float((unsigned int)(v >> 32));
+  d_out[i] = take_sqrt ? sqrtf(d) : d;
+  reinterpret_cast<long long*>(packed)[i] = (long long)(unsigned int)(v & 0xffffffffull);
+}
+
+static int pick_splits(int n_clouds, int P2) {
+  // enough CTAs for >= 2 waves of 148 SMs, but never split below one shared-memory chunk
+  int want = (2 * 148 + n_clouds - 1) / n_clouds;
+  int max_splits = (P2 + NN_CHUNK - 1) / NN_CHUNK;
+  int s = want < 1 ? 1 : want;
+  if (s > max_splits) s = max_splits;
+  if (s < 1) s = 1;
+  return s;
+}
+
+}  // namespace tamf
+
+using namespace tamf;
+
+extern "C" int tamf_nn_query(const float* x, const float* y, int N, int P1, int P2, float* d2, int64_t* idx,
+                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TAMF_REQUIRE(N >= 0 && P1 >= 0, TAMF_E_BADARG, "tamf_nn_query: negative size");
+  if (N == 0 || P1 == 0) return TAMF_OK;  // empty query set: nothing to write
+  TAMF_REQUIRE(P2 > 0, TAMF_E_BADARG, "tamf_nn_query: empty candidate cloud (P2 == 0) has no nearest neighbour");
+  TAMF_REQUIRE(x && y && d2 && idx, TAMF_E_BADARG, "tamf_nn_query: null pointer");
+  TAMF_REQUIRE(P1 <= 1024 * NN_QPT, TAMF_E_BADARG, "tamf_nn_query: P1 > 4096 queries per cloud unsupported");
+  TAMF_REQUIRE(N <= 2147483647 / 1 && (long long)P2 < 2147483647LL, TAMF_E_BADARG, "tamf_nn_query: size overflow");
+  TAMF_REQUIRE(aligned16(idx), TAMF_E_ALIGN, "tamf_nn_query: idx must be 16-byte aligned");
+  int rc = check_device();
+  if (rc) return rc;
+  const size_t total = (size_t)N * P1;
+  TAMF_CUDA_CHECK(cudaMemsetAsync(idx, 0xFF, total * sizeof(int64_t), stream));
+  int threads = ((P1 + NN_QPT - 1) / NN_QPT + 31) / 32 * 32;
+  int splits = pick_splits(N, P2);
+  int per_split = ((P2 + splits - 1) / splits + 3) / 4 * 4;
+  splits = (P2 + per_split - 1) / per_split;
+  // gridDim.x limit is 2^31-1; N beyond 65535 splits is fine on x
+  nn_scan_kernel<<<dim3(N, splits), threads, 0, stream>>>(x, y, P1, P2, per_split, (unsigned long long*)idx);
+  TAMF_LAUNCH_CHECK();
+  nn_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((unsigned long long*)idx, d2, total, 0);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}
+
+extern "C" int tamf_h2o_dist(const float* verts, const float* obj_traj, const float* obj_points,
+                             const int32_t* obj_first_host, int B, int T, int V, int nobj_max, int P, float* dist,
+                             int64_t* idx, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TAMF_REQUIRE(B > 0 && T > 0 && V > 0 && P > 0 && nobj_max > 0, TAMF_E_BADARG, "tamf_h2o_dist: bad size");
+  TAMF_REQUIRE(verts && obj_traj && obj_points && obj_first_host && dist && idx, TAMF_E_BADARG,
+               "tamf_h2o_dist: null pointer");
+  TAMF_REQUIRE(V <= 1024 * NN_QPT, TAMF_E_BADARG, "tamf_h2o_dist: V > 4096 unsupported");
+  TAMF_REQUIRE(B <= 4096, TAMF_E_BADARG, "tamf_h2o_dist: B > 4096 unsupported");
+  int rc = check_device();
+  if (rc) return rc;
+  int max_nobj = 0;
+  for (int b = 0; b < B; ++b) {
+    int n = obj_first_host[b + 1] - obj_first_host[b];
+    TAMF_REQUIRE(n >= 1 && n <= nobj_max, TAMF_E_BADARG,
+                 "tamf_h2o_dist: every sequence needs 1..nobj_max objects (empty cloud has no nearest neighbour)");
+    if (n > max_nobj) max_nobj = n;
+  }
+  // obj_first goes to the device through a small pinned-less async copy from a static staging buffer
+  static thread_local int* d_first = nullptr;
+  static thread_local int d_first_cap = 0;
+  if (d_first_cap < B + 1) {
+    if (d_first) cudaFree(d_first);
+    TAMF_CUDA_CHECK(cudaMalloc(&d_first, sizeof(int) * (size_t)(B + 1)));
+    d_first_cap = B + 1;
+  }
+  TAMF_CUDA_CHECK(cudaMemcpyAsync(d_first, obj_first_host, sizeof(int) * (size_t)(B + 1), cudaMemcpyHostToDevice, stream));
+  const size_t total = (size_t)B * T * V;
+  TAMF_CUDA_CHECK(cudaMemsetAsync(idx, 0xFF, total * sizeof(int64_t), stream));
+  int threads = ((V + NN_QPT - 1) / NN_QPT + 31) / 32 * 32;
+  int P2 = max_nobj * P;
+  int splits = pick_splits(B * T, P2);
+  int per_split = ((P2 + splits - 1) / splits + 3) / 4 * 4;
+  splits = (P2 + per_split - 1) / per_split;
+  h2o_scan_kernel<<<dim3(B * T, splits), threads, 0, stream>>>(verts, obj_traj, obj_points, d_first, T, V, nobj_max, P,
+                                                               per_split, (unsigned long long*)idx);
+  TAMF_LAUNCH_CHECK();
+  nn_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((unsigned long long*)idx, dist, total, 1);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}

@@ -1,0 +1,98 @@
+"""Drop-in for `chamfer_distance.ChamferDistance` and `point2point_signed`, backed by tamf_nn_query.
+
+Reference: thirdparty/chamfer_distance/chamfer_distance/chamfer_distance.py:65-162 (ChamferDistance.forward ->
+(cham_x, cham_y, idx_x, idx_y): squared distances and int64 indices, both directions) and
+src/oakink2_tamf/model/loss/chamfer_distance.py:4-64 (point2point_signed)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def nn_query(x: torch.Tensor, y: torch.Tensor):
+    """x [N,P1,3], y [N,P2,3] CUDA fp32 -> (d2 [N,P1] fp32, idx [N,P1] int64): pytorch3d knn_points(K=1)."""
+    if x.ndim != 3 or y.ndim != 3:
+        raise ValueError("Expected points to be of shape (N, P, D)")
+    if y.shape[0] != x.shape[0] or y.shape[2] != x.shape[2]:
+        raise ValueError("y does not have the correct shape.")
+    if x.shape[2] != 3:
+        raise ValueError("tamf_b200 nearest-neighbour query supports D == 3 only")
+    if not x.is_cuda:
+        raise RuntimeError("tamf_b200.chamfer needs CUDA tensors (no CPU fallback)")
+    x = x.detach().to(torch.float32).contiguous()
+    y = y.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    N, P1, _ = x.shape
+    P2 = y.shape[1]
+    d2 = torch.empty((N, P1), dtype=torch.float32, device=x.device)
+    idx = torch.empty((N, P1), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tamf_nn_query(_lib.ptr(x), _lib.ptr(y), N, P1, P2, _lib.ptr(d2), _lib.ptr(idx),
+                                            _lib.stream_ptr(x.device)), "tamf_nn_query")
+    return d2, idx
+
+
+class ChamferDistance(torch.nn.Module):
+    """`ChamferDistance()(x, y)` -> (d2_x [N,P1], d2_y [N,P2], idx_x [N,P1], idx_y [N,P2]) (chamfer_distance.py:147-162).
+    Only the homogeneous tensor form the reference's call sites use is supported (no lengths / normals / weights)."""
+
+    def forward(self, x, y, x_lengths=None, y_lengths=None, x_normals=None, y_normals=None, weights=None,
+                batch_reduction="mean", point_reduction="mean"):
+        if batch_reduction is not None and batch_reduction not in ["mean", "sum"]:
+            raise ValueError('batch_reduction must be one of ["mean", "sum"] or None')
+        if point_reduction not in ["mean", "sum"]:
+            raise ValueError('point_reduction must be one of ["mean", "sum"]')
+        if x_lengths is not None or y_lengths is not None or weights is not None:
+            raise NotImplementedError("heterogeneous clouds / weights are not on the TaMF path")
+        d2x, ix = nn_query(x, y)
+        d2y, iy = nn_query(y, x)
+        return d2x, d2y, ix, iy
+
+
+def point2point_signed(x, y, x_normals=None, y_normals=None):
+    """model/loss/chamfer_distance.py:4-64 -> (y2x_signed [N,P2], x2y_signed [N,P1], yidx_near [N,P2])."""
+    N, P1, D = x.shape
+    P2 = y.shape[1]
+    if y.shape[0] != N or y.shape[2] != D:
+        raise ValueError("y does not have the correct shape.")
+    _, _, xidx_near, yidx_near = ChamferDistance()(x, y)
+    xe = xidx_near.view(N, P1, 1).expand(N, P1, D)
+    ye = yidx_near.view(N, P2, 1).expand(N, P2, D)
+    x2y = x - y.gather(1, xe)
+    y2x = y - x.gather(1, ye)
+    if x_normals is not None:
+        y_nn = x_normals.gather(1, ye)
+        in_out = (y_nn * y2x).sum(-1).sign()
+        y2x_signed = y2x.norm(dim=2) * in_out
+    else:
+        y2x_signed = y2x.norm(dim=2)
+    if y_normals is not None:
+        x_nn = y_normals.gather(1, xe)
+        in_out_x = (x_nn * x2y).sum(-1).sign()
+        x2y_signed = x2y.norm(dim=2) * in_out_x
+    else:
+        x2y_signed = x2y.norm(dim=2)
+    return y2x_signed, x2y_signed, yidx_near
+
+
+def h2o_dist(verts: torch.Tensor, obj_traj: torch.Tensor, obj_points_list, return_idx: bool = False):
+    """Fused `SegmentRefineModel.multi_object_h2o_dist` (segment_refine_model.py:142-168).
+    verts [B,T,V,3] CUDA; obj_traj [B,nobj_max,T,9]; obj_points_list: list of B arrays [nobj_b,P,3] -> [B,T,V]."""
+    import numpy as np
+    dev = verts.device
+    B, T, V, _ = verts.shape
+    first = [0]
+    for o in obj_points_list:
+        first.append(first[-1] + int(o.shape[0]))
+    P = int(obj_points_list[0].shape[1])
+    pts = torch.from_numpy(np.concatenate([np.asarray(o, np.float32) for o in obj_points_list], 0)).to(dev).contiguous()
+    first_t = torch.tensor(first, dtype=torch.int32)
+    verts = verts.detach().to(torch.float32).contiguous()
+    obj_traj = obj_traj.detach().to(device=dev, dtype=torch.float32).contiguous()
+    dist = torch.empty((B, T, V), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, T, V), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tamf_h2o_dist(_lib.ptr(verts), _lib.ptr(obj_traj), _lib.ptr(pts),
+                                            _lib.C.c_void_p(first_t.data_ptr()), B, T, V, obj_traj.shape[1], P,
+                                            _lib.ptr(dist), _lib.ptr(idx), _lib.stream_ptr(dev)), "tamf_h2o_dist")
+    return (dist, idx) if return_idx else dist

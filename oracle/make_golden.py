@@ -1,0 +1,124 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the REFERENCE ITSELF (imported from
+/root/reference through oracle/ref_shims.py) on seeded synthetic inputs.  Run in the authoring container:
+
+    python -m oracle.make_golden
+
+The fixtures travel to the GPU box (which has no /root/reference); tests compare both the oracle restatement and
+the CUDA path against them.  Inputs are regenerated from the seeds recorded in each file by tamf_b200.synth, so
+only reference OUTPUTS (and the CLIP-stub text features, which need the reference's CLIP code) are stored.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oakink2-tamf_b200"))
+
+from oracle import ref_shims  # noqa: E402
+from tamf_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_g(ref, arch: str, B: int, T: int, nobj: int, ragged: bool, steps, tag: str):
+    cfg = synth.ARCH[arch]
+    model = ref.mdm.InterationSegmentMDM(**cfg)
+    model.eval()
+    sd = synth.g_state_dict(cfg, seed=0)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert all(k.startswith("clip_model.") for k in missing) and not unexpected, (missing, unexpected)
+    batch = synth.make_batch(B, T, nobj=nobj, seed=11, ragged=ragged)
+    x = torch.randn(B, 99, 1, T, generator=torch.Generator().manual_seed(5))
+    out = {"arch": arch, "B": B, "T": T, "nobj": nobj, "ragged": int(ragged), "batch_seed": 11, "x_seed": 5,
+           "weight_seed": 0, "steps": np.array(steps)}
+    with torch.no_grad():
+        out["text_feat"] = model.encode_text(batch["text"]).numpy()
+        for t in steps:
+            ts = torch.full((B,), t, dtype=torch.long)
+            out[f"x0_t{t}"] = model(x, ts, batch).numpy()
+    np.savez_compressed(os.path.join(OUT, f"g_{tag}.npz"), **out)
+    print("wrote g_", tag)
+    return model, sd, batch, out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_shims.install()
+
+    # ---- G forward: arch_mdm ragged objects (pins the padded-mean quirk), 4 timesteps ----
+    model, sd, batch, g = golden_g(ref, "arch_mdm", B=3, T=48, nobj=3, ragged=True, steps=[999, 500, 1, 0], tag="arch_mdm")
+    # ---- G forward: arch_mdm_l at the real T ----
+    golden_g(ref, "arch_mdm_l", B=2, T=160, nobj=2, ragged=False, steps=[999, 0], tag="arch_mdm_l")
+
+    # ---- diffusion tables + p_sample chain through the reference sampler ----
+    diffusion = ref.diffusion_util.create_gaussian_diffusion(1000, "cosine")
+    tabs = {k: getattr(diffusion, k) for k in (
+        "betas", "alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1",
+        "posterior_mean_coef2", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod")}
+    np.savez_compressed(os.path.join(OUT, "diffusion_tables.npz"), **tabs)
+    # p_sample at a few t with given noise (reference p_sample, gaussian_diffusion.py:412-460)
+    B, T = 3, 48
+    x = torch.randn(B, 99, 1, T, generator=torch.Generator().manual_seed(5))
+    ps = {}
+    gd = ref.gd
+    orig = gd.th.randn_like
+    for t in (999, 500, 1, 0):
+        gd.th.randn_like = lambda z, _t=t: synth.step_noise(77, _t, tuple(z.shape))
+        with torch.no_grad():
+            o = diffusion.p_sample(model, x, torch.full((B,), t, dtype=torch.long), clip_denoised=False,
+                                   model_kwargs={"batch": batch})
+        ps[f"sample_t{t}"] = o["sample"].numpy()
+    # free-running 4-step chain t = 3..0: the body of p_sample_loop_progressive (gaussian_diffusion.py:621-640)
+    img = x.clone()
+    for t in (3, 2, 1, 0):
+        gd.th.randn_like = lambda z, _t=t: synth.step_noise(77, _t, tuple(z.shape))
+        with torch.no_grad():
+            img = diffusion.p_sample(model, img, torch.full((B,), t, dtype=torch.long), clip_denoised=False,
+                                     model_kwargs={"batch": batch})["sample"]
+    ps["chain_3_0"] = img.numpy()
+    gd.th.randn_like = orig
+    np.savez_compressed(os.path.join(OUT, "p_sample_arch_mdm.npz"), noise_seed=77, **ps)
+    print("wrote p_sample")
+
+    # ---- rotation helpers + ManoLayer FK (quat mode) on synthetic assets ----
+    g0 = torch.Generator().manual_seed(3)
+    N = 24
+    pose_repr = torch.from_numpy(synth.random_pose_repr(np.random.default_rng(21), 1, N)[0])
+    betas = 0.5 * torch.randn(N, 10, generator=g0)
+    fk = {"N": N, "pose_seed": 21, "betas": betas.numpy(), "pose_repr": pose_repr.numpy()}
+    R = ref.rotation.rot6d_to_rotmat(pose_repr[:, 3:].reshape(N, 16, 6))
+    q = ref.rotation.rotmat_to_quat(R)
+    fk["rotmat"], fk["quat"] = R.numpy(), q.numpy()
+    for side in ("right", "left"):
+        layer = ref.manolayer.ManoLayer(mano_assets_root=ref.mano_root, rot_mode="quat", side=side, center_idx=0,
+                                        use_pca=False, flat_hand_mean=True)
+        o = layer(pose_coeffs=q, betas=betas)
+        fk[f"verts_{side}"], fk[f"joints_{side}"] = o.verts.numpy(), o.joints.numpy()
+    np.savez_compressed(os.path.join(OUT, "mano_fk.npz"), **fk)
+    print("wrote mano_fk")
+
+    # ---- R forward (SegmentRefineModel) ----
+    cfg = synth.ARCH["arch_refine"]
+    rmodel = ref.refine.SegmentRefineModel(ref.mano_root, **cfg, use_pc=True)
+    rmodel.eval()
+    rsd = synth.r_state_dict(cfg, 0)
+    missing, unexpected = rmodel.load_state_dict(rsd, strict=False)
+    assert all("mano_layer" in k for k in missing) and not unexpected, (missing, unexpected)
+    B, T, P = 2, 16, 256
+    rb = synth.make_batch(B, T, nobj=2, seed=2, ragged=True, npoints=P, with_pointcloud=True)
+    with torch.no_grad():
+        ro = rmodel(rb)
+    keep = ["refine_pose_repr", "sample_hand_verts", "sample_hand_joints", "sample_h2o_dist", "refine_h2o_dist",
+            "target_h2o_dist", "refine_hand_verts", "target_hand_joints"]
+    np.savez_compressed(os.path.join(OUT, "r_arch_refine.npz"), B=B, T=T, P=P, batch_seed=2, weight_seed=0,
+                        **{k: ro[k].numpy() for k in keep})
+    print("wrote r_arch_refine")
+
+
+if __name__ == "__main__":
+    main()
