@@ -162,6 +162,13 @@ int tamf_p_sample_loop_host(tamf_denoiser* h, const float* text_feat_host, const
                             const float* shape_host, const float* obj_traj_host, const float* obj_emb_host,
                             int nobj_max, const float* x_T_host, uint64_t seed, float* sample_out_host, void* stream);
 
+/* Measurement aid (bench.py roofline): runs ONE p_sample step at timestep t eagerly (no graph) with a CUDA event
+ * between consecutive kernels and returns the per-kernel device times in launch order:
+ *   prep, embed-a, embed-b, L x {in_proj, attention, out_proj+LN1, linear1+GELU, linear2+LN2}, final+posterior.
+ * ms_out [cap] HOST floats, *n_out = number of kernels (3 + 5 L + 1).  x_io is advanced one step.  Synchronous. */
+int tamf_denoiser_profile_step(tamf_denoiser* h, float* x_io, int t, uint64_t seed, float* ms_out_host, int cap,
+                               int* n_out_host, void* stream);
+
 /* Number of kernels this library launched since load (for bench.py's gpu_launches claim). */
 uint64_t tamf_kernel_launch_count(void);
 

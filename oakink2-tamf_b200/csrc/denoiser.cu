@@ -250,22 +250,34 @@ static int upload_bf16(tamf_denoiser* h, __nv_bfloat16** dst, const float* src, 
 }
 
 // One denoiser evaluation (+ optional posterior update) enqueued on `s`.
+// `marks` (profiling only): one event is recorded after every kernel of the step, in launch order.
 static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, float* x_out, float* x0_out,
-                        const float* noise, uint64_t seed, cudaStream_t s) {
+                        const float* noise, uint64_t seed, cudaStream_t s, std::vector<cudaEvent_t>* marks = nullptr) {
   const int d = h->d, ff = h->ff, B = h->B, T = h->T, S = h->S, M = h->M, Mf = h->Mf;
   int rc;
+  auto mark = [&]() {
+    if (!marks) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    marks->push_back(e);
+  };
+  mark();
   prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, h->ttab, h->pe, h->prefix, h->A0, h->X, h->Xb, T, S, d,
                                                      h->nfeat);
   TAMF_LAUNCH_CHECK();
+  mark();
   {  // embed-a
     GemmParams p{};
     p.M = Mf, p.N = d, p.K = KPAD, p.bias = nullptr, p.addmat = h->objhalf, p.out_bf16 = h->H0, p.ld_bf16 = d;
     if ((rc = launch_gemm<256, EPI_ADD_SILU_BF16>(h->tm_A0, h->tm_wfold, p, s))) return rc;
+    mark();
   }
   {  // embed-b
     GemmParams p{};
     p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = 5, p.X = h->X, p.Xb = h->Xb;
     if ((rc = launch_gemm<256, EPI_TOKEN_OUT>(h->tm_H0, h->tm_wm2, p, s))) return rc;
+    mark();
   }
   for (int l = 0; l < h->L; ++l) {
     LayerDev& w = h->layers[l];
@@ -273,23 +285,27 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, fl
       GemmParams p{};
       p.M = M, p.N = 3 * d, p.K = d, p.bias = w.b_in, p.out_bf16 = h->QKV, p.ld_bf16 = 3 * d;
       if ((rc = launch_gemm<256, EPI_BIAS_BF16>(h->tm_Xb, w.tm_in, p, s))) return rc;
+      mark();
     }
     if (d / h->H == 128)
       rc = launch_attn<128>(h->QKV, h->ATT, B, S, h->H, d, s);
     else
       rc = launch_attn<64>(h->QKV, h->ATT, B, S, h->H, d, s);
     if (rc) return rc;
+    mark();
     {
       GemmParams p{};
       p.M = M, p.N = d, p.K = d, p.bias = w.b_out, p.X = h->X, p.Xb = h->Xb, p.gamma = w.g1, p.beta = w.be1;
       rc = (d == 512) ? launch_gemm<512, EPI_RES_LN>(h->tm_ATT, w.tm_out, p, s)
                       : launch_gemm<256, EPI_RES_LN>(h->tm_ATT, w.tm_out, p, s);
       if (rc) return rc;
+      mark();
     }
     {
       GemmParams p{};
       p.M = M, p.N = ff, p.K = d, p.bias = w.b1, p.out_bf16 = h->Hb, p.ld_bf16 = ff;
       if ((rc = launch_gemm<256, EPI_BIAS_GELU_BF16>(h->tm_Xb, w.tm_w1, p, s))) return rc;
+      mark();
     }
     {
       GemmParams p{};
@@ -297,6 +313,7 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, fl
       rc = (d == 512) ? launch_gemm<512, EPI_RES_LN>(h->tm_H, w.tm_w2, p, s)
                       : launch_gemm<256, EPI_RES_LN>(h->tm_H, w.tm_w2, p, s);
       if (rc) return rc;
+      mark();
     }
   }
   {  // final projection + DDPM posterior
@@ -305,6 +322,7 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, fl
     p.x_t = x_t, p.x_out = x_out, p.x0_out = x0_out, p.noise = noise, p.t_ptr = t_ptr, p.c1 = h->c1, p.c2 = h->c2,
     p.sigma = h->sigma, p.seed = seed;
     if ((rc = launch_gemm<128, EPI_POSTERIOR>(h->tm_Xb, h->tm_wfin, p, s))) return rc;
+    mark();
   }
   return TAMF_OK;
 }
@@ -605,6 +623,28 @@ extern "C" int tamf_p_sample_step(tamf_denoiser* h, float* x_io, int t, const fl
   fill_int_kernel<<<(h->B + 255) / 256, 256, 0, s>>>(h->t_dev, h->B, t);
   TAMF_LAUNCH_CHECK();
   return enqueue_step(h, x_io, h->t_dev, x_io, x0_out, noise, seed, s);
+}
+
+extern "C" int tamf_denoiser_profile_step(tamf_denoiser* h, float* x_io, int t, uint64_t seed, float* ms_out, int cap,
+                                          int* n_out, void* stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_denoiser_profile_step: bind + set_cond first");
+  TAMF_REQUIRE(x_io && ms_out && n_out, TAMF_E_BADARG, "tamf_denoiser_profile_step: null pointer");
+  TAMF_REQUIRE(t >= 0 && t < h->cfg.num_steps, TAMF_E_BADARG, "tamf_denoiser_profile_step: t out of range");
+  fill_int_kernel<<<(h->B + 255) / 256, 256, 0, s>>>(h->t_dev, h->B, t);
+  TAMF_LAUNCH_CHECK();
+  std::vector<cudaEvent_t> marks;
+  int rc = enqueue_step(h, x_io, h->t_dev, x_io, nullptr, nullptr, seed, s, &marks);
+  cudaError_t e = cudaStreamSynchronize(s);
+  const int n = (int)marks.size() - 1;
+  if (rc == TAMF_OK && e == cudaSuccess) {
+    for (int i = 0; i < n && i < cap; ++i) cudaEventElapsedTime(&ms_out[i], marks[i], marks[i + 1]);
+    *n_out = n;
+  }
+  for (cudaEvent_t ev : marks) cudaEventDestroy(ev);
+  if (rc) return rc;
+  TAMF_CUDA_CHECK(e);
+  return TAMF_OK;
 }
 
 extern "C" int tamf_p_sample_chain(tamf_denoiser* h, float* x_io, int t_start, int t_end, uint64_t seed,

@@ -18,7 +18,7 @@ SYMBOLS = [
     "tamf_version", "tamf_last_error", "tamf_nn_query", "tamf_h2o_dist", "tamf_mano_create", "tamf_mano_destroy",
     "tamf_mano_fk", "tamf_denoiser_create", "tamf_denoiser_destroy", "tamf_denoiser_workspace_bytes",
     "tamf_denoiser_bind", "tamf_denoiser_set_cond", "tamf_denoiser_forward", "tamf_p_sample_step",
-    "tamf_p_sample_chain", "tamf_p_sample_loop_host", "tamf_kernel_launch_count", "tamf_philox_normal",
+    "tamf_p_sample_chain", "tamf_p_sample_loop_host", "tamf_denoiser_profile_step", "tamf_kernel_launch_count", "tamf_philox_normal",
     "tamf_gemm_selftest",
 ]
 
@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
     L.tamf_p_sample_step.argtypes = [vp, vp, i32, vp, u64, vp, vp]
     L.tamf_p_sample_chain.argtypes = [vp, vp, i32, i32, u64, vp]
     L.tamf_p_sample_loop_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, u64, vp, vp]
+    L.tamf_denoiser_profile_step.argtypes = [vp, vp, i32, u64, vp, i32, vp, vp]
     L.tamf_philox_normal.argtypes = [vp, sz, u64, C.c_uint32, vp]
     L.tamf_gemm_selftest.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     if hasattr(L, "tamf_refiner_create"):

@@ -1,0 +1,115 @@
+"""Host-side logic of the drop-in classes that needs no GPU: schedule tables, state_dict contract, argument checks,
+sharding, synthetic generators, bench bookkeeping."""
+import numpy as np
+import pytest
+import torch
+
+import tamf_b200
+from tamf_b200 import shard, synth
+
+
+def test_schedule_tables_match_reference_golden(golden):
+    g = golden("diffusion_tables.npz")
+    d = tamf_b200.create_gaussian_diffusion(1000, "cosine")
+    assert d.num_timesteps == 1000
+    for k in ("betas", "alphas_cumprod", "posterior_log_variance_clipped", "posterior_mean_coef1",
+              "posterior_mean_coef2", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod"):
+        np.testing.assert_allclose(getattr(d, k), g[k], rtol=1e-12, atol=0)
+    with pytest.raises(NotImplementedError):
+        tamf_b200.create_gaussian_diffusion(1000, "cosine", sigma_small=False)
+    with pytest.raises(NotImplementedError):
+        tamf_b200.create_gaussian_diffusion(1000, "sqrt")
+
+
+@pytest.mark.parametrize("arch,nparam", [("arch_mdm", 7031395), ("arch_mdm_l", 27300963)])
+def test_state_dict_contract(arch, nparam):
+    """Same parameter names / count as the reference without CLIP, strict=False load like
+    launch/sample.py:190-196."""
+    cfg = synth.ARCH[arch]
+    m = tamf_b200.InterationSegmentMDM(**cfg, text_encoder=synth.text_features)
+    sd = synth.g_state_dict(cfg, 0)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    assert sum(p.numel() for p in m.parameters_wo_clip()) == nparam
+    keys = set(m.state_dict().keys())
+    for k in ("seqTransEncoder.layers.7.self_attn.in_proj_weight", "input_merge.2.bias", "embed_text.weight",
+              "embed_timestep.time_embed.0.weight", "output_process.poseFinal.bias", "hand_side_process.lh_embed",
+              "sequence_pos_encoder.pe", "obj_input_process.poseEmbedding.weight"):
+        assert k in keys
+    extra = dict(sd)
+    extra["clip_model.positional_embedding"] = torch.zeros(3)
+    missing, unexpected = m.load_state_dict(extra, strict=False)
+    assert unexpected == ["clip_model.positional_embedding"]
+
+
+def test_hand_side_ids_and_errors():
+    M = tamf_b200.InterationSegmentMDM
+    assert M.hand_side_ids(["rh", "lh", "rh"]) == [0, 1, 0]
+    with pytest.raises(ValueError, match="unexpected hand_side"):
+        M.hand_side_ids(["rh", "both"])
+    with pytest.raises(NotImplementedError):
+        M(**{**synth.ARCH["arch_mdm"], "activation": "relu"})
+
+
+def test_sampler_rejects_unsupported_hooks():
+    d = tamf_b200.create_gaussian_diffusion(1000, "cosine")
+    with pytest.raises(NotImplementedError):
+        d.p_sample_loop(None, (1, 99, 1, 8), clip_denoised=True, model_kwargs={"batch": {}})
+    with pytest.raises(NotImplementedError):
+        d.p_sample_loop(None, (1, 99, 1, 8), clip_denoised=False, cond_fn=lambda *a: 0, model_kwargs={"batch": {}})
+
+
+def test_q_sample_matches_closed_form():
+    d = tamf_b200.create_gaussian_diffusion(1000, "cosine")
+    x0, n = torch.ones(2, 3), torch.full((2, 3), 2.0)
+    t = torch.tensor([0, 999])
+    out = d.q_sample(x0, t, n)
+    exp = d.sqrt_alphas_cumprod[[0, 999]][:, None] + 2 * d.sqrt_one_minus_alphas_cumprod[[0, 999]][:, None]
+    np.testing.assert_allclose(out.numpy(), np.broadcast_to(exp, (2, 3)).astype(np.float32), rtol=1e-6)
+
+
+def test_shard_ranges_cover_and_match_reference_rule():
+    for n in (0, 1, 7, 64, 8192, 8191):
+        for w in (1, 2, 3, 4, 8):
+            rs = [shard.shard_range(n, r, w) for r in range(w)]
+            assert rs[0].start == 0 and rs[-1].stop == n
+            assert all(a.stop == b.start for a, b in zip(rs, rs[1:]))
+            # launch/sample.py:198-199
+            assert all(r.start == n * i // w and r.stop == n * (i + 1) // w for i, r in enumerate(rs))
+    assert [len(b) for b in shard.batches(range(10, 150), 64)] == [64, 64, 12]
+    with pytest.raises(ValueError):
+        shard.shard_range(4, 2, 2)
+
+
+def test_synth_is_deterministic_and_ragged_padding_is_zero():
+    a, b = synth.make_batch(4, 16, nobj=3, seed=5, ragged=True), synth.make_batch(4, 16, nobj=3, seed=5, ragged=True)
+    assert torch.equal(a["obj_traj"], b["obj_traj"]) and a["hand_side"] == ["rh", "lh", "rh", "lh"]
+    for i in range(4):
+        n = int(a["obj_num"][i])
+        assert float(a["obj_traj"][i, n:].abs().sum()) == 0 and float(a["obj_embedding"][i, n:].abs().sum()) == 0
+        assert len(a["obj_list"][i]) == n
+    assert torch.equal(synth.text_features(["x", "y"]), synth.text_features(["x", "y"]))
+
+
+def test_manolayer_host_surface():
+    layer = tamf_b200.ManoLayer(side="left", assets=synth.mano_assets("left"))
+    assert layer.th_faces.shape == (1538, 3) and layer.get_mano_closed_faces().shape == (1552, 3)
+    assert layer.th_posedirs.shape == (778, 3, 135) and layer.th_J_regressor.shape == (16, 778)
+    with pytest.raises(NotImplementedError):
+        tamf_b200.ManoLayer(side="right", center_idx=9, assets=synth.mano_assets("right"))
+
+
+def test_chamfer_argument_checks():
+    with pytest.raises(ValueError):
+        tamf_b200.nn_query(torch.zeros(4, 3), torch.zeros(1, 4, 3))
+    with pytest.raises(ValueError):
+        tamf_b200.ChamferDistance()(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3), point_reduction="max")
+
+
+def test_bench_flop_model():
+    import bench
+    cfg = synth.ARCH["arch_mdm_l"]
+    assert abs(bench.flops_per_seq_step(cfg) - 8.951e9) < 2e6  # 8 951 M
+    cls = bench.kernel_classes(cfg, 64)
+    assert len(cls) == 3 + 5 * 8 + 1
+    assert abs(sum(f for _, f in cls) / 64 - bench.flops_per_seq_step(cfg)) / 8.95e9 < 0.01
