@@ -162,6 +162,51 @@ int tamf_p_sample_loop_host(tamf_denoiser* h, const float* text_feat_host, const
                             const float* shape_host, const float* obj_traj_host, const float* obj_emb_host,
                             int nobj_max, const float* x_T_host, uint64_t seed, float* sample_out_host, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * MF-MDM R (refine) transformer pass.
+ * Replaces the tensor part of SegmentRefineModel.forward
+ *   src/oakink2_tamf/model/segment_refine_model.py:170-217
+ * (prefix tokens :177-186, input / object / h2o-distance embeddings + input_merge :189-208, positional encoding,
+ * 8-layer encoder, output_process, x_in + output, nan_to_num :211-217).  FK and hand->object distances of the same
+ * forward (:193-201, :220-232) are tamf_mano_fk(_select) and tamf_h2o_dist; tamf_b200/refine.py sequences them.   */
+typedef struct tamf_refiner tamf_refiner;
+
+typedef struct tamf_r_weights {
+  const float *shape_w, *shape_b;     /* hand_shape_process.shape_embed          [d,10]   */
+  const float *objemb_w, *objemb_b;   /* obj_embed_process.embedding             [d,768]  */
+  const float *pose_w, *pose_b;       /* input_process.poseEmbedding             [d,99]   */
+  const float *objtraj_w, *objtraj_b; /* obj_input_process.poseEmbedding         [d,9]    */
+  const float *dist_w, *dist_b;       /* h2o_dist_input_process.poseEmbedding    [d,778]  */
+  const float *merge0_w, *merge0_b;   /* input_merge.0                           [d,3d]   */
+  const float *merge2_w, *merge2_b;   /* input_merge.2                           [d,d]    */
+  const float *final_w, *final_b;     /* output_process.poseFinal                [99,d]   */
+  const float *pe;                    /* sequence_pos_encoder.pe                 [>= 3+T, d] */
+  int32_t pe_rows;
+  const tamf_layer_weights* layers;   /* [num_layers] */
+} tamf_r_weights;
+
+/* cfg: clip_dim / num_steps are ignored. */
+int tamf_refiner_create(const tamf_cfg* cfg, const tamf_r_weights* w, tamf_refiner** out);
+int tamf_refiner_destroy(tamf_refiner* h);
+size_t tamf_refiner_workspace_bytes(const tamf_refiner* h, int B, int T);
+int tamf_refiner_bind(tamf_refiner* h, int B, int T, void* workspace, size_t workspace_bytes);
+/* sample_pose_repr [B,T,99]; h2o_dist [B,T,778] (of the sampled pose); hand_side [B] int32 (0 rh, 1 lh);
+ * shape [B,T,10]; obj_traj [B,nobj_max,T,9]; obj_emb [B,nobj_max,768] -> refine_out [B,T,99] = x_in + delta. */
+int tamf_refiner_forward(tamf_refiner* h, const float* sample_pose_repr, const float* h2o_dist,
+                         const int32_t* hand_side, const float* shape, const float* obj_traj, const float* obj_emb,
+                         int nobj_max, float* refine_out, void* stream);
+
+/* FK of the frames listed in frame_ids [n] (device int32) only, results written at those frame indices of the full
+ * verts [N,778,3] / joints [N,21,3] arrays: lets one batch mix right and left hands without gather/scatter copies
+ * (the reference loops over batch items, segment_refine_model.py:113-129).  pose/betas are the FULL [N,..] arrays. */
+int tamf_mano_fk_select(const tamf_mano* h, int pose_mode, const float* pose, const float* betas,
+                        const int32_t* frame_ids, int n, float* verts, float* joints, void* stream);
+
+/* Area-weighted vertex normals (pytorch3d Meshes.verts_normals_packed as used at segment_refine_model.py:132-133;
+ * semantics restated in oracle/tamf_oracle.py:vertex_normals -- parity unpinned, pytorch3d is absent).
+ * verts [N,V,3] fp32, faces [F,3] int32 -> normals [N,V,3]. */
+int tamf_vertex_normals(const float* verts, const int32_t* faces, int N, int V, int F, float* normals, void* stream);
+
 /* Measurement aid (bench.py roofline): runs ONE p_sample step at timestep t eagerly (no graph) with a CUDA event
  * between consecutive kernels and returns the per-kernel device times in launch order:
  *   prep, embed-a, embed-b, L x {in_proj, attention, out_proj+LN1, linear1+GELU, linear2+LN2}, final+posterior.

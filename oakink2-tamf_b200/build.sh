@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
        -Xcudafe --diag_suppress=177 --expt-relaxed-constexpr)
 if [[ "${1:-}" == "-v" ]]; then FLAGS+=(-Xptxas -v); fi
 pids=()
-for f in api nn mano denoiser; do
+for f in api encoder nn mano denoiser refiner; do
   src="$here/csrc/$f.cu"; obj="$here/build/$f.o"
   newest=$(ls -t "$here"/csrc/*.cu "$here"/csrc/*.cuh "$here"/../include/*.h | head -1)
   if [[ ! -f "$obj" || "$newest" -nt "$obj" || "${1:-}" == "-v" ]]; then
@@ -17,5 +17,5 @@ for f in api nn mano denoiser; do
   fi
 done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
-"$NVCC" -shared -o "$here/lib/libtamf_b200.so" "$here"/build/{api,nn,mano,denoiser}.o -lcudart_static -lpthread -ldl -lrt
+"$NVCC" -shared -o "$here/lib/libtamf_b200.so" "$here"/build/{api,encoder,nn,mano,denoiser,refiner}.o -lcudart_static -lpthread -ldl -lrt
 echo "built $here/lib/libtamf_b200.so"

@@ -1,5 +1,7 @@
 // api.cu -- library-wide state: version, thread-local error, device check, TMA descriptor encoding,
 // GEMM self-test and Philox test entry points.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "gemm.cuh"
@@ -42,6 +44,15 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TAMF_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "attn.cuh"
+#include "encoder.cuh"
 #include "gemm.cuh"
 
 namespace tamf {
@@ -33,79 +34,6 @@ constexpr int MAX_NOBJ = 8;    // staging capacity of tamf_p_sample_loop_host
 // small kernels
 // ------------------------------------------------------------------------------------------------
 
-// out[r, n] = post( sum_k in[r,k] W[n,k] + bias[n] )   fp32 SIMT, 64x64 tile, 16-wide k slab, 4x4 per thread.
-// post: 0 none, 1 silu, 2 nan_to_num(.) + add[r % add_rows, n]
-__global__ void __launch_bounds__(256)
-    linear_f32_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ W, int ld_w,
-                      const float* __restrict__ bias, float* __restrict__ out, int ld_out, int R, int N, int K, int post,
-                      const float* __restrict__ add, int ld_add) {
-  __shared__ float sI[16][65], sW[16][65];
-  const int r0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      const int rr = i / 16, kk = i % 16;
-      sI[kk][rr] = (r0 + rr < R && k0 + kk < K) ? in[(size_t)(r0 + rr) * ld_in + k0 + kk] : 0.f;
-      sW[kk][rr] = (n0 + rr < N && k0 + kk < K) ? W[(size_t)(n0 + rr) * ld_w + k0 + kk] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sI[kk][ty * 4 + i], b[i] = sW[kk][tx * 4 + i];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty * 4 + i;
-    if (r >= R) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n >= N) continue;
-      float v = acc[i][j] + (bias ? bias[n] : 0.f);
-      if (post == 1) v = v / (1.0f + expf(-v));
-      if (post == 2) v = nan_to_num(v) + add[(size_t)r * ld_add + n];
-      out[(size_t)r * ld_out + n] = v;
-    }
-  }
-}
-
-static int linear_f32(const float* in, int ld_in, const float* W, int ld_w, const float* bias, float* out, int ld_out,
-                      int R, int N, int K, int post, const float* add, int ld_add, cudaStream_t s) {
-  dim3 grid((N + 63) / 64, (R + 63) / 64);
-  linear_f32_kernel<<<grid, 256, 0, s>>>(in, ld_in, W, ld_w, bias, out, ld_out, R, N, K, post, add, ld_add);
-  TAMF_LAUNCH_CHECK();
-  return TAMF_OK;
-}
-
-// out[o, i] = mean_r in[o, r, i]   (in viewed as [outer, red, inner]; torch.mean(x, dim) in fp32)
-__global__ void mean_axis_kernel(const float* __restrict__ in, float* __restrict__ out, int outer, int red, int inner) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)outer * inner) return;
-  const int o = (int)(i / inner), c = (int)(i % inner);
-  float acc = 0.f;
-  for (int r = 0; r < red; ++r) acc += in[((size_t)o * red + r) * inner + c];
-  out[i] = acc / (float)red;
-}
-
-// obj_traj [B,nobj,T,9] -> mean over objects, frame-major [B*T, 9]
-__global__ void traj_mean_kernel(const float* __restrict__ traj, float* __restrict__ out, int B, int nobj, int T) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * T * 9) return;
-  const int c = (int)(i % 9), tau = (int)((i / 9) % T), b = (int)(i / (9 * (size_t)T));
-  float acc = 0.f;
-  for (int o = 0; o < nobj; ++o) acc += traj[(((size_t)b * nobj + o) * T + tau) * 9 + c];
-  out[i] = acc / (float)nobj;
-}
-
 // prefix[b,1,:] = hand-side token (rh -> 0, lh -> e0), then nan_to_num(prefix) + pe[1..4]
 __global__ void prefix_finish_kernel(float* __restrict__ prefix, const int* __restrict__ hand_side,
                                      const float* __restrict__ pe, int B, int d) {
@@ -117,19 +45,6 @@ __global__ void prefix_finish_kernel(float* __restrict__ prefix, const int* __re
   prefix[i] = nan_to_num(v) + pe[(size_t)(1 + s) * d + c];
 }
 
-// fp32 [rows, cols] -> bf16 [rows, ld_out] with zero padding of columns cols..ld_out-1
-__global__ void to_bf16_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows, int cols,
-                                   int ld_out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)rows * ld_out) return;
-  const int c = (int)(i % ld_out), r = (int)(i / ld_out);
-  out[i] = __float2bfloat16_rn(c < cols ? in[(size_t)r * cols + c] : 0.f);
-}
-
-__global__ void fill_int_kernel(int* p, int n, int v) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
-}
 __global__ void add_int_kernel(int* p, int n, int dv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] += dv;
@@ -177,12 +92,6 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------------
-struct LayerDev {
-  __nv_bfloat16 *w_in, *w_out, *w1, *w2;
-  float *b_in, *b_out, *b1, *b2, *g1, *be1, *g2, *be2;
-  CUtensorMap tm_in, tm_out, tm_w1, tm_w2;
-};
-
 }  // namespace tamf
 
 using namespace tamf;
@@ -190,8 +99,9 @@ using namespace tamf;
 struct tamf_denoiser {
   tamf_cfg cfg{};
   int d = 0, ff = 0, L = 0, H = 0, nfeat = 0;
-  std::vector<void*> owned;  // device allocations freed by destroy
-  std::vector<LayerDev> layers;
+  DevPool pool;      // device allocations freed by destroy
+  EncoderStack enc;  // the 8 post-norm layers (encoder.cuh)
+  EncoderBuffers buf;
   // fp32 conditioning weights (exact fp32 SIMT path, once per sample)
   float *shape_w, *shape_b, *objemb_w, *objemb_b, *objtraj_w, *objtraj_b, *merge0_w, *merge_bias /* b1 + W1a.bp */,
       *text_w, *text_b, *pe, *ttab;
@@ -204,11 +114,11 @@ struct tamf_denoiser {
   // bound workspace
   int B = 0, T = 0, S = 0, M = 0, Mf = 0;
   bool bound = false, cond_set = false;
-  float *X, *objhalf, *prefix, *objtok, *trajmean, *shapemean, *embmean, *xbuf;
+  float *objhalf, *prefix, *objtok, *trajmean, *shapemean, *embmean, *xbuf;
   float *st_text, *st_shape, *st_traj, *st_emb;  // host-API staging
   int *st_side, *t_dev;
-  __nv_bfloat16 *Xb, *QKV, *ATT, *Hb, *A0, *H0;
-  CUtensorMap tm_Xb, tm_ATT, tm_H, tm_A0, tm_H0;
+  __nv_bfloat16 *A0, *H0;
+  CUtensorMap tm_A0, tm_H0, tm_Xb_fin;
   // cached step graph
   cudaGraphExec_t graph_exec = nullptr;
   float* graph_x = nullptr;
@@ -218,111 +128,44 @@ struct tamf_denoiser {
 
 namespace tamf {
 
-static int dev_alloc(tamf_denoiser* h, void** p, size_t bytes) {
-  TAMF_CUDA_CHECK(cudaMalloc(p, bytes));
-  h->owned.push_back(*p);
-  return TAMF_OK;
-}
-static int upload_f32(tamf_denoiser* h, float** dst, const float* src, size_t n) {
-  TAMF_REQUIRE(src != nullptr, TAMF_E_BADARG, "tamf_denoiser_create: null weight pointer");
-  int rc = dev_alloc(h, (void**)dst, n * sizeof(float));
-  if (rc) return rc;
-  TAMF_CUDA_CHECK(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
-  return TAMF_OK;
-}
-// fp32 host [rows, cols] -> bf16 device [rows, ld] (zero padded), via a device conversion kernel
+static int dev_alloc(tamf_denoiser* h, void** p, size_t bytes) { return h->pool.alloc(p, bytes); }
+static int upload_f32(tamf_denoiser* h, float** dst, const float* src, size_t n) { return h->pool.upload_f32(dst, src, n); }
 static int upload_bf16(tamf_denoiser* h, __nv_bfloat16** dst, const float* src, int rows, int cols, int ld) {
-  TAMF_REQUIRE(src != nullptr, TAMF_E_BADARG, "tamf_denoiser_create: null weight pointer");
-  float* tmp = nullptr;
-  TAMF_CUDA_CHECK(cudaMalloc(&tmp, (size_t)rows * cols * sizeof(float)));
-  cudaError_t e = cudaMemcpy(tmp, src, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice);
-  int rc = (e == cudaSuccess) ? dev_alloc(h, (void**)dst, (size_t)rows * ld * sizeof(__nv_bfloat16)) : TAMF_E_CUDA;
-  if (rc == TAMF_OK) {
-    const size_t n = (size_t)rows * ld;
-    to_bf16_pad_kernel<<<(unsigned)((n + 255) / 256), 256>>>(tmp, *dst, rows, cols, ld);
-    count_launch();
-    e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) rc = TAMF_E_CUDA;
-  }
-  cudaFree(tmp);
-  if (rc == TAMF_E_CUDA) set_error(std::string("upload_bf16: ") + cudaGetErrorString(cudaGetLastError()));
-  return rc;
+  return h->pool.upload_bf16(dst, src, rows, cols, ld);
 }
 
 // One denoiser evaluation (+ optional posterior update) enqueued on `s`.
 // `marks` (profiling only): one event is recorded after every kernel of the step, in launch order.
 static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, float* x_out, float* x0_out,
                         const float* noise, uint64_t seed, cudaStream_t s, std::vector<cudaEvent_t>* marks = nullptr) {
-  const int d = h->d, ff = h->ff, B = h->B, T = h->T, S = h->S, M = h->M, Mf = h->Mf;
+  const int d = h->d, B = h->B, T = h->T, S = h->S, M = h->M, Mf = h->Mf;
   int rc;
-  auto mark = [&]() {
-    if (!marks) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, s);
-    marks->push_back(e);
-  };
-  mark();
-  prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, h->ttab, h->pe, h->prefix, h->A0, h->X, h->Xb, T, S, d,
-                                                     h->nfeat);
+  mark_event(marks, s);
+  prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, h->ttab, h->pe, h->prefix, h->A0, h->buf.X, h->buf.Xb, T,
+                                                     S, d, h->nfeat);
   TAMF_LAUNCH_CHECK();
-  mark();
+  mark_event(marks, s);
   {  // embed-a
     GemmParams p{};
     p.M = Mf, p.N = d, p.K = KPAD, p.bias = nullptr, p.addmat = h->objhalf, p.out_bf16 = h->H0, p.ld_bf16 = d;
     if ((rc = launch_gemm<256, EPI_ADD_SILU_BF16>(h->tm_A0, h->tm_wfold, p, s))) return rc;
-    mark();
+    mark_event(marks, s);
   }
   {  // embed-b
     GemmParams p{};
-    p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = 5, p.X = h->X, p.Xb = h->Xb;
+    p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = 5, p.X = h->buf.X,
+    p.Xb = h->buf.Xb;
     if ((rc = launch_gemm<256, EPI_TOKEN_OUT>(h->tm_H0, h->tm_wm2, p, s))) return rc;
-    mark();
+    mark_event(marks, s);
   }
-  for (int l = 0; l < h->L; ++l) {
-    LayerDev& w = h->layers[l];
-    {
-      GemmParams p{};
-      p.M = M, p.N = 3 * d, p.K = d, p.bias = w.b_in, p.out_bf16 = h->QKV, p.ld_bf16 = 3 * d;
-      if ((rc = launch_gemm<256, EPI_BIAS_BF16>(h->tm_Xb, w.tm_in, p, s))) return rc;
-      mark();
-    }
-    if (d / h->H == 128)
-      rc = launch_attn<128>(h->QKV, h->ATT, B, S, h->H, d, s);
-    else
-      rc = launch_attn<64>(h->QKV, h->ATT, B, S, h->H, d, s);
-    if (rc) return rc;
-    mark();
-    {
-      GemmParams p{};
-      p.M = M, p.N = d, p.K = d, p.bias = w.b_out, p.X = h->X, p.Xb = h->Xb, p.gamma = w.g1, p.beta = w.be1;
-      rc = (d == 512) ? launch_gemm<512, EPI_RES_LN>(h->tm_ATT, w.tm_out, p, s)
-                      : launch_gemm<256, EPI_RES_LN>(h->tm_ATT, w.tm_out, p, s);
-      if (rc) return rc;
-      mark();
-    }
-    {
-      GemmParams p{};
-      p.M = M, p.N = ff, p.K = d, p.bias = w.b1, p.out_bf16 = h->Hb, p.ld_bf16 = ff;
-      if ((rc = launch_gemm<256, EPI_BIAS_GELU_BF16>(h->tm_Xb, w.tm_w1, p, s))) return rc;
-      mark();
-    }
-    {
-      GemmParams p{};
-      p.M = M, p.N = d, p.K = ff, p.bias = w.b2, p.X = h->X, p.Xb = h->Xb, p.gamma = w.g2, p.beta = w.be2;
-      rc = (d == 512) ? launch_gemm<512, EPI_RES_LN>(h->tm_H, w.tm_w2, p, s)
-                      : launch_gemm<256, EPI_RES_LN>(h->tm_H, w.tm_w2, p, s);
-      if (rc) return rc;
-      mark();
-    }
-  }
+  if ((rc = enqueue_encoder(h->enc, h->buf, s, marks))) return rc;
   {  // final projection + DDPM posterior
     GemmParams p{};
     p.M = M, p.N = h->nfeat, p.K = d, p.bias = h->b_fin, p.T = T, p.S = S, p.P0 = 5, p.nfeat = h->nfeat;
     p.x_t = x_t, p.x_out = x_out, p.x0_out = x0_out, p.noise = noise, p.t_ptr = t_ptr, p.c1 = h->c1, p.c2 = h->c2,
     p.sigma = h->sigma, p.seed = seed;
-    if ((rc = launch_gemm<128, EPI_POSTERIOR>(h->tm_Xb, h->tm_wfin, p, s))) return rc;
-    mark();
+    if ((rc = launch_gemm<128, EPI_POSTERIOR>(h->tm_Xb_fin, h->tm_wfin, p, s))) return rc;
+    mark_event(marks, s);
   }
   return TAMF_OK;
 }
@@ -340,7 +183,7 @@ static void drop_graph(tamf_denoiser* h) {
 extern "C" int tamf_denoiser_destroy(tamf_denoiser* h) {
   if (!h) return TAMF_OK;
   drop_graph(h);
-  for (void* p : h->owned) cudaFree(p);
+  h->pool.free_all();
   delete h;
   return TAMF_OK;
 }
@@ -351,8 +194,6 @@ extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w
   if (rc) return rc;
   const int d = cfg->latent_dim, ff = cfg->ff_size, L = cfg->num_layers, H = cfg->num_heads, nf = cfg->input_dim;
   TAMF_REQUIRE(d == 256 || d == 512, TAMF_E_BADARG, "latent_dim must be 256 or 512 (arch_mdm / arch_mdm_l)");
-  TAMF_REQUIRE(H > 0 && d % H == 0 && (d / H == 64 || d / H == 128), TAMF_E_BADARG, "head_dim must be 64 or 128");
-  TAMF_REQUIRE(ff % 256 == 0 && ff >= 256, TAMF_E_BADARG, "ff_size must be a multiple of 256");
   TAMF_REQUIRE(nf > 0 && nf <= KPAD, TAMF_E_BADARG, "input_dim must be <= 128");
   TAMF_REQUIRE(L > 0 && L <= 64 && w->layers, TAMF_E_BADARG, "bad num_layers");
   TAMF_REQUIRE(cfg->num_steps > 0 && w->pe && w->pe_rows >= cfg->num_steps, TAMF_E_BADARG,
@@ -405,27 +246,7 @@ extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w
   TRY(make_tmap_2d_bf16(&h->tm_wfold, h->wfold, KPAD, d, (uint64_t)KPAD * 2, 64, 256));
   TRY(make_tmap_2d_bf16(&h->tm_wm2, h->wm2, d, d, (uint64_t)d * 2, 64, 256));
   TRY(make_tmap_2d_bf16(&h->tm_wfin, h->wfin, d, nf, (uint64_t)d * 2, 64, 128));
-  h->layers.resize(L);
-  for (int l = 0; l < L; ++l) {
-    const tamf_layer_weights& s = w->layers[l];
-    LayerDev& o = h->layers[l];
-    TRY(upload_bf16(h, &o.w_in, s.in_proj_w, 3 * d, d, d));
-    TRY(upload_bf16(h, &o.w_out, s.out_proj_w, d, d, d));
-    TRY(upload_bf16(h, &o.w1, s.lin1_w, ff, d, d));
-    TRY(upload_bf16(h, &o.w2, s.lin2_w, d, ff, ff));
-    TRY(upload_f32(h, &o.b_in, s.in_proj_b, 3 * d));
-    TRY(upload_f32(h, &o.b_out, s.out_proj_b, d));
-    TRY(upload_f32(h, &o.b1, s.lin1_b, ff));
-    TRY(upload_f32(h, &o.b2, s.lin2_b, d));
-    TRY(upload_f32(h, &o.g1, s.norm1_w, d));
-    TRY(upload_f32(h, &o.be1, s.norm1_b, d));
-    TRY(upload_f32(h, &o.g2, s.norm2_w, d));
-    TRY(upload_f32(h, &o.be2, s.norm2_b, d));
-    TRY(make_tmap_2d_bf16(&o.tm_in, o.w_in, d, 3 * d, (uint64_t)d * 2, 64, 256));
-    TRY(make_tmap_2d_bf16(&o.tm_out, o.w_out, d, d, (uint64_t)d * 2, 64, 256));
-    TRY(make_tmap_2d_bf16(&o.tm_w1, o.w1, d, ff, (uint64_t)d * 2, 64, 256));
-    TRY(make_tmap_2d_bf16(&o.tm_w2, o.w2, ff, d, (uint64_t)ff * 2, 64, 256));
-  }
+  TRY(h->enc.upload(h->pool, w->layers, d, ff, L, H));
   {
     // schedule: fp32 lookups exactly like _extract_into_tensor(...).float() (gaussian_diffusion.py:1275);
     // sigma[t] = 1[t != 0] * exp(0.5 * logvar[t]) evaluated in fp32 (:459)
@@ -450,8 +271,8 @@ extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w
     const int n = cfg->num_steps;
     TRY(dev_alloc(h, (void**)&tmp, (size_t)n * d * sizeof(float)));
     TRY(dev_alloc(h, (void**)&h->ttab, (size_t)n * d * sizeof(float)));
-    TRY(linear_f32(h->pe, d, t0w, d, t0b, tmp, d, n, d, d, 1, nullptr, 0, 0));
-    TRY(linear_f32(tmp, d, t2w, d, t2b, h->ttab, d, n, d, d, 0, nullptr, 0, 0));
+    TRY(linear_f32(h->pe, d, t0w, d, t0b, tmp, d, n, d, d, 1, nullptr, 0, nullptr));
+    TRY(linear_f32(tmp, d, t2w, d, t2b, h->ttab, d, n, d, d, 0, nullptr, 0, nullptr));
     if (cudaDeviceSynchronize() != cudaSuccess) {
       set_error("tamf_denoiser_create: timestep table kernels failed");
       tamf_denoiser_destroy(h);
@@ -460,13 +281,8 @@ extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w
   }
   TRY((configure_gemm<256, EPI_ADD_SILU_BF16>()));
   TRY((configure_gemm<256, EPI_TOKEN_OUT>()));
-  TRY((configure_gemm<256, EPI_BIAS_BF16>()));
-  TRY((configure_gemm<256, EPI_BIAS_GELU_BF16>()));
-  TRY((configure_gemm<256, EPI_RES_LN>()));
-  TRY((configure_gemm<512, EPI_RES_LN>()));
   TRY((configure_gemm<128, EPI_POSTERIOR>()));
-  TRY(configure_attn<64>());
-  TRY(configure_attn<128>());
+  TRY(configure_encoder_kernels());
 #undef TRY
   *out = h;
   return TAMF_OK;
@@ -529,11 +345,12 @@ extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size
   drop_graph(h);
   uint8_t* p = static_cast<uint8_t*>(ws);
   h->B = B, h->T = T, h->S = T + 5, h->M = B * (T + 5), h->Mf = B * T;
-  h->X = (float*)(p + L.off[0]);
-  h->Xb = (__nv_bfloat16*)(p + L.off[1]);
-  h->QKV = (__nv_bfloat16*)(p + L.off[2]);
-  h->ATT = (__nv_bfloat16*)(p + L.off[3]);
-  h->Hb = (__nv_bfloat16*)(p + L.off[4]);
+  h->buf.B = B, h->buf.S = T + 5, h->buf.M = h->M;
+  h->buf.X = (float*)(p + L.off[0]);
+  h->buf.Xb = (__nv_bfloat16*)(p + L.off[1]);
+  h->buf.QKV = (__nv_bfloat16*)(p + L.off[2]);
+  h->buf.ATT = (__nv_bfloat16*)(p + L.off[3]);
+  h->buf.Hb = (__nv_bfloat16*)(p + L.off[4]);
   h->A0 = (__nv_bfloat16*)(p + L.off[5]);
   h->H0 = (__nv_bfloat16*)(p + L.off[6]);
   h->objhalf = (float*)(p + L.off[7]);
@@ -551,9 +368,8 @@ extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size
   h->t_dev = (int*)(p + L.off[19]);
   const int d = h->d, ff = h->ff;
   int rc;
-  if ((rc = make_tmap_2d_bf16(&h->tm_Xb, h->Xb, d, h->M, (uint64_t)d * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(&h->tm_ATT, h->ATT, d, h->M, (uint64_t)d * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(&h->tm_H, h->Hb, ff, h->M, (uint64_t)ff * 2, 64, 128))) return rc;
+  if ((rc = h->buf.make_maps(d, ff))) return rc;
+  h->tm_Xb_fin = h->buf.tm_Xb;
   if ((rc = make_tmap_2d_bf16(&h->tm_A0, h->A0, KPAD, h->Mf, (uint64_t)KPAD * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_H0, h->H0, d, h->Mf, (uint64_t)d * 2, 64, 128))) return rc;
   h->bound = true;
@@ -573,16 +389,10 @@ extern "C" int tamf_denoiser_set_cond(tamf_denoiser* h, const float* text_feat, 
   int rc;
   // means over frames / (padded) objects: interaction_segment_mdm.py:300, :260, :245
   {
-    size_t n = (size_t)B * c.hand_shape_dim;
-    mean_axis_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(shape, h->shapemean, B, T, c.hand_shape_dim);
-    TAMF_LAUNCH_CHECK();
-    n = (size_t)B * c.obj_embed_dim;
-    mean_axis_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(obj_emb, h->embmean, B, nobj_max, c.obj_embed_dim);
-    TAMF_LAUNCH_CHECK();
-    n = (size_t)Mf * 9;
     TAMF_REQUIRE(c.obj_input_dim == 9, TAMF_E_BADARG, "obj_input_dim must be 9");
-    traj_mean_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(obj_traj, h->trajmean, B, nobj_max, T);
-    TAMF_LAUNCH_CHECK();
+    if ((rc = mean_axis(shape, h->shapemean, B, T, c.hand_shape_dim, s))) return rc;
+    if ((rc = mean_axis(obj_emb, h->embmean, B, nobj_max, c.obj_embed_dim, s))) return rc;
+    if ((rc = traj_mean(obj_traj, h->trajmean, B, nobj_max, T, s))) return rc;
   }
   // prefix tokens 1..4 -> prefix[b, 0..3, :]
   if ((rc = linear_f32(text_feat, c.clip_dim, h->text_w, c.clip_dim, h->text_b, h->prefix + 0 * d, 4 * d, B, d,
@@ -620,8 +430,10 @@ extern "C" int tamf_p_sample_step(tamf_denoiser* h, float* x_io, int t, const fl
   TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_p_sample_step: bind + set_cond first");
   TAMF_REQUIRE(x_io, TAMF_E_BADARG, "tamf_p_sample_step: null pointer");
   TAMF_REQUIRE(t >= 0 && t < h->cfg.num_steps, TAMF_E_BADARG, "tamf_p_sample_step: t out of range");
-  fill_int_kernel<<<(h->B + 255) / 256, 256, 0, s>>>(h->t_dev, h->B, t);
-  TAMF_LAUNCH_CHECK();
+  {
+    int rc0 = fill_int(h->t_dev, h->B, t, s);
+    if (rc0) return rc0;
+  }
   return enqueue_step(h, x_io, h->t_dev, x_io, x0_out, noise, seed, s);
 }
 
@@ -631,8 +443,10 @@ extern "C" int tamf_denoiser_profile_step(tamf_denoiser* h, float* x_io, int t, 
   TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_denoiser_profile_step: bind + set_cond first");
   TAMF_REQUIRE(x_io && ms_out && n_out, TAMF_E_BADARG, "tamf_denoiser_profile_step: null pointer");
   TAMF_REQUIRE(t >= 0 && t < h->cfg.num_steps, TAMF_E_BADARG, "tamf_denoiser_profile_step: t out of range");
-  fill_int_kernel<<<(h->B + 255) / 256, 256, 0, s>>>(h->t_dev, h->B, t);
-  TAMF_LAUNCH_CHECK();
+  {
+    int rc0 = fill_int(h->t_dev, h->B, t, s);
+    if (rc0) return rc0;
+  }
   std::vector<cudaEvent_t> marks;
   int rc = enqueue_step(h, x_io, h->t_dev, x_io, nullptr, nullptr, seed, s, &marks);
   cudaError_t e = cudaStreamSynchronize(s);
@@ -683,8 +497,10 @@ extern "C" int tamf_p_sample_chain(tamf_denoiser* h, float* x_io, int t_start, i
     TAMF_CUDA_CHECK(e);
     h->graph_x = x_io, h->graph_seed = seed, h->graph_stream = s;
   }
-  fill_int_kernel<<<(h->B + 255) / 256, 256, 0, s>>>(h->t_dev, h->B, t_start);
-  TAMF_LAUNCH_CHECK();
+  {
+    int rc0 = fill_int(h->t_dev, h->B, t_start, s);
+    if (rc0) return rc0;
+  }
   const int per_step = 2 + 5 * h->L + 2 + 1;
   for (int t = t_start; t >= t_end; --t) {
     TAMF_CUDA_CHECK(cudaGraphLaunch(h->graph_exec, s));

@@ -1,0 +1,256 @@
+// encoder.cu -- shared transformer encoder stack (see encoder.cuh) + fp32 conditioning helpers.
+#include "encoder.cuh"
+
+#include "attn.cuh"
+#include "gemm.cuh"
+
+namespace tamf {
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+
+// fp32 SIMT linear: 64x64 tile, 16-wide k slab, 4x4 outputs per thread.
+__global__ void __launch_bounds__(256)
+    linear_f32_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ W, int ld_w,
+                      const float* __restrict__ bias, float* __restrict__ out, int ld_out, int R, int N, int K, int post,
+                      const float* __restrict__ add, int ld_add) {
+  __shared__ float sI[16][65], sW[16][65];
+  const int r0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int rr = i / 16, kk = i % 16;
+      sI[kk][rr] = (r0 + rr < R && k0 + kk < K) ? in[(size_t)(r0 + rr) * ld_in + k0 + kk] : 0.f;
+      sW[kk][rr] = (n0 + rr < N && k0 + kk < K) ? W[(size_t)(n0 + rr) * ld_w + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sI[kk][ty * 4 + i], b[i] = sW[kk][tx * 4 + i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (post == 1) v = v / (1.0f + expf(-v));
+      if (post == 2) v = nan_to_num(v) + add[(size_t)r * ld_add + n];
+      out[(size_t)r * ld_out + n] = v;
+    }
+  }
+}
+
+int linear_f32(const float* in, int ld_in, const float* W, int ld_w, const float* bias, float* out, int ld_out, int R,
+               int N, int K, int post, const float* add, int ld_add, cudaStream_t s) {
+  dim3 grid((N + 63) / 64, (R + 63) / 64);
+  linear_f32_kernel<<<grid, 256, 0, s>>>(in, ld_in, W, ld_w, bias, out, ld_out, R, N, K, post, add, ld_add);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}
+
+__global__ void mean_axis_kernel(const float* __restrict__ in, float* __restrict__ out, int outer, int red, int inner) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)outer * inner) return;
+  const int o = (int)(i / inner), c = (int)(i % inner);
+  float acc = 0.f;
+  for (int r = 0; r < red; ++r) acc += in[((size_t)o * red + r) * inner + c];
+  out[i] = acc / (float)red;
+}
+
+int mean_axis(const float* in, float* out, int outer, int red, int inner, cudaStream_t s) {
+  const size_t n = (size_t)outer * inner;
+  mean_axis_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, outer, red, inner);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}
+
+__global__ void traj_mean_kernel(const float* __restrict__ traj, float* __restrict__ out, int B, int nobj, int T) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * T * 9) return;
+  const int c = (int)(i % 9), tau = (int)((i / 9) % T), b = (int)(i / (9 * (size_t)T));
+  float acc = 0.f;
+  for (int o = 0; o < nobj; ++o) acc += traj[(((size_t)b * nobj + o) * T + tau) * 9 + c];
+  out[i] = acc / (float)nobj;
+}
+
+int traj_mean(const float* traj, float* out, int B, int nobj, int T, cudaStream_t s) {
+  const size_t n = (size_t)B * T * 9;
+  traj_mean_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(traj, out, B, nobj, T);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}
+
+__global__ void to_bf16_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows, int cols,
+                                   int ld_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * ld_out) return;
+  const int c = (int)(i % ld_out), r = (int)(i / ld_out);
+  out[i] = __float2bfloat16_rn(c < cols ? in[(size_t)r * cols + c] : 0.f);
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int fill_int(int* p, int n, int v, cudaStream_t s) {
+  fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DevPool
+// ------------------------------------------------------------------------------------------------
+int DevPool::alloc(void** p, size_t bytes) {
+  TAMF_CUDA_CHECK(cudaMalloc(p, bytes));
+  owned.push_back(*p);
+  return TAMF_OK;
+}
+
+int DevPool::upload_f32(float** dst, const float* src, size_t n) {
+  TAMF_REQUIRE(src != nullptr, TAMF_E_BADARG, "create: null weight pointer");
+  int rc = alloc((void**)dst, n * sizeof(float));
+  if (rc) return rc;
+  TAMF_CUDA_CHECK(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return TAMF_OK;
+}
+
+int DevPool::upload_bf16(__nv_bfloat16** dst, const float* src, int rows, int cols, int ld) {
+  TAMF_REQUIRE(src != nullptr, TAMF_E_BADARG, "create: null weight pointer");
+  float* tmp = nullptr;
+  TAMF_CUDA_CHECK(cudaMalloc(&tmp, (size_t)rows * cols * sizeof(float)));
+  cudaError_t e = cudaMemcpy(tmp, src, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice);
+  int rc = (e == cudaSuccess) ? alloc((void**)dst, (size_t)rows * ld * sizeof(__nv_bfloat16)) : TAMF_E_CUDA;
+  if (rc == TAMF_OK) {
+    const size_t n = (size_t)rows * ld;
+    to_bf16_pad_kernel<<<(unsigned)((n + 255) / 256), 256>>>(tmp, *dst, rows, cols, ld);
+    count_launch();
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = TAMF_E_CUDA;
+  }
+  cudaFree(tmp);
+  if (rc == TAMF_E_CUDA) set_error(std::string("upload_bf16: ") + cudaGetErrorString(cudaGetLastError()));
+  return rc;
+}
+
+void DevPool::free_all() {
+  for (void* p : owned) cudaFree(p);
+  owned.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder stack
+// ------------------------------------------------------------------------------------------------
+int EncoderStack::upload(DevPool& pool, const tamf_layer_weights* w, int d_, int ff_, int L_, int H_) {
+  TAMF_REQUIRE(d_ == 256 || d_ == 512, TAMF_E_BADARG, "latent_dim must be 256 or 512 (arch_mdm / arch_mdm_l / arch_refine)");
+  TAMF_REQUIRE(H_ > 0 && d_ % H_ == 0 && (d_ / H_ == 64 || d_ / H_ == 128), TAMF_E_BADARG, "head_dim must be 64 or 128");
+  TAMF_REQUIRE(ff_ % 256 == 0 && ff_ >= 256, TAMF_E_BADARG, "ff_size must be a multiple of 256");
+  TAMF_REQUIRE(L_ > 0 && L_ <= 64 && w, TAMF_E_BADARG, "bad num_layers");
+  d = d_, ff = ff_, L = L_, H = H_;
+  layers.resize(L);
+  int rc;
+#define TRY(x) \
+  if ((rc = (x)) != TAMF_OK) return rc;
+  for (int l = 0; l < L; ++l) {
+    const tamf_layer_weights& s = w[l];
+    LayerDev& o = layers[l];
+    TRY(pool.upload_bf16(&o.w_in, s.in_proj_w, 3 * d, d, d));
+    TRY(pool.upload_bf16(&o.w_out, s.out_proj_w, d, d, d));
+    TRY(pool.upload_bf16(&o.w1, s.lin1_w, ff, d, d));
+    TRY(pool.upload_bf16(&o.w2, s.lin2_w, d, ff, ff));
+    TRY(pool.upload_f32(&o.b_in, s.in_proj_b, 3 * d));
+    TRY(pool.upload_f32(&o.b_out, s.out_proj_b, d));
+    TRY(pool.upload_f32(&o.b1, s.lin1_b, ff));
+    TRY(pool.upload_f32(&o.b2, s.lin2_b, d));
+    TRY(pool.upload_f32(&o.g1, s.norm1_w, d));
+    TRY(pool.upload_f32(&o.be1, s.norm1_b, d));
+    TRY(pool.upload_f32(&o.g2, s.norm2_w, d));
+    TRY(pool.upload_f32(&o.be2, s.norm2_b, d));
+    TRY(make_tmap_2d_bf16(&o.tm_in, o.w_in, d, 3 * d, (uint64_t)d * 2, 64, 256));
+    TRY(make_tmap_2d_bf16(&o.tm_out, o.w_out, d, d, (uint64_t)d * 2, 64, 256));
+    TRY(make_tmap_2d_bf16(&o.tm_w1, o.w1, d, ff, (uint64_t)d * 2, 64, 256));
+    TRY(make_tmap_2d_bf16(&o.tm_w2, o.w2, ff, d, (uint64_t)ff * 2, 64, 256));
+  }
+#undef TRY
+  return TAMF_OK;
+}
+
+int EncoderBuffers::make_maps(int d, int ff) {
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tm_Xb, Xb, d, M, (uint64_t)d * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_ATT, ATT, d, M, (uint64_t)d * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_H, Hb, ff, M, (uint64_t)ff * 2, 64, 128))) return rc;
+  return TAMF_OK;
+}
+
+int configure_encoder_kernels() {
+  int rc;
+  if ((rc = configure_gemm<256, EPI_BIAS_BF16>())) return rc;
+  if ((rc = configure_gemm<256, EPI_BIAS_GELU_BF16>())) return rc;
+  if ((rc = configure_gemm<256, EPI_RES_LN>())) return rc;
+  if ((rc = configure_gemm<512, EPI_RES_LN>())) return rc;
+  if ((rc = configure_attn<64>())) return rc;
+  if ((rc = configure_attn<128>())) return rc;
+  return TAMF_OK;
+}
+
+int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStream_t s,
+                    std::vector<cudaEvent_t>* marks) {
+  const int d = enc.d, ff = enc.ff, M = buf.M;
+  int rc;
+  for (int l = 0; l < enc.L; ++l) {
+    const LayerDev& w = enc.layers[l];
+    {
+      GemmParams p{};
+      p.M = M, p.N = 3 * d, p.K = d, p.bias = w.b_in, p.out_bf16 = buf.QKV, p.ld_bf16 = 3 * d;
+      if ((rc = launch_gemm<256, EPI_BIAS_BF16>(buf.tm_Xb, w.tm_in, p, s))) return rc;
+      mark_event(marks, s);
+    }
+    if (d / enc.H == 128)
+      rc = launch_attn<128>(buf.QKV, buf.ATT, buf.B, buf.S, enc.H, d, s);
+    else
+      rc = launch_attn<64>(buf.QKV, buf.ATT, buf.B, buf.S, enc.H, d, s);
+    if (rc) return rc;
+    mark_event(marks, s);
+    {
+      GemmParams p{};
+      p.M = M, p.N = d, p.K = d, p.bias = w.b_out, p.X = buf.X, p.Xb = buf.Xb, p.gamma = w.g1, p.beta = w.be1;
+      rc = (d == 512) ? launch_gemm<512, EPI_RES_LN>(buf.tm_ATT, w.tm_out, p, s)
+                      : launch_gemm<256, EPI_RES_LN>(buf.tm_ATT, w.tm_out, p, s);
+      if (rc) return rc;
+      mark_event(marks, s);
+    }
+    {
+      GemmParams p{};
+      p.M = M, p.N = ff, p.K = d, p.bias = w.b1, p.out_bf16 = buf.Hb, p.ld_bf16 = ff;
+      if ((rc = launch_gemm<256, EPI_BIAS_GELU_BF16>(buf.tm_Xb, w.tm_w1, p, s))) return rc;
+      mark_event(marks, s);
+    }
+    {
+      GemmParams p{};
+      p.M = M, p.N = d, p.K = ff, p.bias = w.b2, p.X = buf.X, p.Xb = buf.Xb, p.gamma = w.g2, p.beta = w.be2;
+      rc = (d == 512) ? launch_gemm<512, EPI_RES_LN>(buf.tm_H, w.tm_w2, p, s)
+                      : launch_gemm<256, EPI_RES_LN>(buf.tm_H, w.tm_w2, p, s);
+      if (rc) return rc;
+      mark_event(marks, s);
+    }
+  }
+  return TAMF_OK;
+}
+
+}  // namespace tamf

@@ -1,0 +1,78 @@
+// encoder.cuh -- the post-norm transformer encoder stack shared by MF-MDM G (denoiser.cu) and R (refiner.cu), plus the
+// small fp32 helpers of the once-per-sample conditioning path.
+//
+// Reference: nn.TransformerEncoder of 8 x nn.TransformerEncoderLayer(d, nhead, ff, activation="gelu"), post-norm,
+// batch_first=False, no mask -- constructed at src/oakink2_tamf/model/interaction_segment_mdm.py:63-70 (G) and
+// src/oakink2_tamf/model/segment_refine_model.py:88-95 (R).
+//
+// Per layer, 5 kernels over the token matrix (row = b*S + s):
+//   QKV = Xb . Win^T + b                    tcgen05 GEMM, bf16 out           [M,3d]
+//   ATT = softmax(Q K^T / sqrt(hd)) V       fused attention (attn.cuh)       [M,d]
+//   X   = LN1(X + ATT . Wo^T + b)           tcgen05 GEMM, residual+LayerNorm epilogue (fp32 X + bf16 Xb)
+//   H   = gelu(Xb . W1^T + b)               tcgen05 GEMM, exact-erf GELU epilogue, bf16 out  [M,ff]
+//   X   = LN2(X + H . W2^T + b)             tcgen05 GEMM, residual+LayerNorm epilogue
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace tamf {
+
+// Device allocations owned by a handle (weights converted at create time; nothing is allocated in the hot path).
+struct DevPool {
+  std::vector<void*> owned;
+  int alloc(void** p, size_t bytes);
+  int upload_f32(float** dst, const float* src_host, size_t n);
+  // fp32 host [rows, cols] -> bf16 device [rows, ld] (columns cols..ld-1 zero)
+  int upload_bf16(__nv_bfloat16** dst, const float* src_host, int rows, int cols, int ld);
+  void free_all();
+};
+
+struct LayerDev {
+  __nv_bfloat16 *w_in, *w_out, *w1, *w2;
+  float *b_in, *b_out, *b1, *b2, *g1, *be1, *g2, *be2;
+  CUtensorMap tm_in, tm_out, tm_w1, tm_w2;
+};
+
+struct EncoderStack {
+  int d = 0, ff = 0, L = 0, H = 0;
+  std::vector<LayerDev> layers;
+  int upload(DevPool& pool, const tamf_layer_weights* w, int d, int ff, int L, int H);
+};
+
+// Activation buffers of one bound (B, S) problem; all row-major, row = b*S + s.
+struct EncoderBuffers {
+  int B = 0, S = 0, M = 0;
+  float* X = nullptr;             // fp32 residual stream [M,d]
+  __nv_bfloat16* Xb = nullptr;    // bf16 copy of X (GEMM A operand)
+  __nv_bfloat16* QKV = nullptr;   // [M,3d]
+  __nv_bfloat16* ATT = nullptr;   // [M,d]
+  __nv_bfloat16* Hb = nullptr;    // [M,ff]
+  CUtensorMap tm_Xb, tm_ATT, tm_H;
+  int make_maps(int d, int ff);
+};
+
+// Enqueue all L layers on `s`.  `marks` (profiling only): an event is recorded after every kernel.
+int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStream_t s,
+                    std::vector<cudaEvent_t>* marks);
+int configure_encoder_kernels();  // cudaFuncSetAttribute for every instantiation used above (once per process)
+
+// ---- small fp32 helpers (conditioning path, once per sample) ----
+// out[r,n] = post(sum_k in[r,k] W[n,k] + bias[n]); post: 0 none, 1 silu, 2 nan_to_num(.) + add[r,n]
+int linear_f32(const float* in, int ld_in, const float* W, int ld_w, const float* bias, float* out, int ld_out, int R,
+               int N, int K, int post, const float* add, int ld_add, cudaStream_t s);
+// out[o,i] = mean_r in[o,r,i]
+int mean_axis(const float* in, float* out, int outer, int red, int inner, cudaStream_t s);
+// obj_traj [B,nobj,T,9] -> mean over the (padded) object axis, frame-major [B*T,9]
+int traj_mean(const float* traj, float* out, int B, int nobj, int T, cudaStream_t s);
+int fill_int(int* p, int n, int v, cudaStream_t s);
+
+inline void mark_event(std::vector<cudaEvent_t>* marks, cudaStream_t s) {
+  if (!marks) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  marks->push_back(e);
+}
+
+}  // namespace tamf

@@ -81,20 +81,27 @@ __device__ __forceinline__ int fk_parent(int k) { return (k == 0) ? -1 : ((k - 1
 __global__ void __launch_bounds__(FK_THREADS)
     mano_fk_kernel(const float* __restrict__ blendT, const float* __restrict__ vt, const float* __restrict__ J0,
                    const float* __restrict__ JS, const float* __restrict__ wT, int is_right, int pose_mode,
-                   const float* __restrict__ pose, const float* __restrict__ betas, int N, float* __restrict__ verts,
-                   float* __restrict__ joints) {
+                   const float* __restrict__ pose, const float* __restrict__ betas, const int* __restrict__ frame_ids,
+                   int N, float* __restrict__ verts, float* __restrict__ joints) {
   __shared__ __align__(16) float sFeat[NFEAT][FK_FT];      // [feature][frame]: one LDS.128 x2 feeds 8 frames
   __shared__ float sR[FK_FT][16][9];         // local rotations
   __shared__ float sJ[FK_FT][16][3];         // rest joints J
   __shared__ float sG[FK_FT][16][12];        // global transforms (3x4), then G' = G - [0 | G.J]
   __shared__ float sTsl[FK_FT][3];
   __shared__ float sCenter[FK_FT][3];
+  // N frames are processed; slot i of this launch is frame frame_ids[i] of the full arrays (identity when null)
+  __shared__ int sFrame[FK_FT];
   const int f0 = blockIdx.x * FK_FT;
   const int tid = threadIdx.x;
+  if (tid < FK_FT) {
+    const int i = min(f0 + tid, N - 1);
+    sFrame[tid] = frame_ids ? frame_ids[i] : i;
+  }
+  __syncthreads();
 
   // ---- stage 1: rotations (FK_FT x 16 threads), shape coefficients, translations ----
   if (tid < FK_FT * 16) {
-    const int fl = tid / 16, k = tid % 16, f = min(f0 + fl, N - 1);
+    const int fl = tid / 16, k = tid % 16, f = sFrame[fl];
     float R[9];
     if (pose_mode == TAMF_POSE_REPR)
       rot6d_to_R_via_quat(pose + (size_t)f * 99 + 3 + 6 * k, R);
@@ -151,7 +158,8 @@ __global__ void __launch_bounds__(FK_THREADS)
   __syncthreads();
   // ---- stage 4: joints out (16 chain joints; tips are written by the vertex owners), centre, G' ----
   if (tid < FK_FT * 16) {
-    const int fl = tid / 16, k = tid % 16, f = f0 + fl;
+    const int fl = tid / 16, k = tid % 16, f = sFrame[fl];
+    const bool f_ok = f0 + fl < N;
     // reorder map of manolayer.py:240 : output slot of MANO joint k
     const int slot_of[16] = {0, 5, 6, 7, 9, 10, 11, 17, 18, 19, 13, 14, 15, 1, 2, 3};
     float g3[3], gj[3];
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(FK_THREADS)
       for (int r = 0; r < 3; ++r) sCenter[fl][r] = g3[r];  // joints[:, center_idx=0]
     }
     __syncwarp();
-    if (f < N) {
+    if (f_ok) {
       // centre = root joint translation = sG[fl][0][.][3] (read directly: sCenter may not be visible yet)
 #pragma unroll
       for (int r = 0; r < 3; ++r)
@@ -215,8 +223,8 @@ __global__ void __launch_bounds__(FK_THREADS)
     }
 #pragma unroll
     for (int fl = 0; fl < FK_FT; ++fl) {
-      const int f = f0 + fl;
-      if (f >= N) break;
+      if (f0 + fl >= N) break;
+      const int f = sFrame[fl];
       float Tm[12];
 #pragma unroll
       for (int e = 0; e < 12; ++e) Tm[e] = 0.f;
@@ -311,17 +319,83 @@ extern "C" int tamf_mano_destroy(tamf_mano* h) {
   return TAMF_OK;
 }
 
+static int launch_fk(const tamf_mano* h, int pose_mode, const float* pose, const float* betas, const int32_t* frame_ids,
+                     int n, float* verts, float* joints, cudaStream_t stream, const char* who) {
+  TAMF_REQUIRE(h, TAMF_E_BADARG, std::string(who) + ": null handle");
+  TAMF_REQUIRE(pose_mode == TAMF_POSE_QUAT || pose_mode == TAMF_POSE_REPR, TAMF_E_BADARG, std::string(who) + ": bad pose_mode");
+  TAMF_REQUIRE(n >= 0, TAMF_E_BADARG, std::string(who) + ": negative frame count");
+  if (n == 0) return TAMF_OK;
+  TAMF_REQUIRE(pose && betas && verts && joints, TAMF_E_BADARG, std::string(who) + ": null pointer");
+  mano_fk_kernel<<<(n + FK_FT - 1) / FK_FT, FK_THREADS, 0, stream>>>(h->d.blendT, h->d.vt, h->d.J0, h->d.JS, h->d.wT,
+                                                                    h->d.is_right, pose_mode, pose, betas, frame_ids, n,
+                                                                    verts, joints);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}
+
 extern "C" int tamf_mano_fk(const tamf_mano* h, int pose_mode, const float* pose, const float* betas, int N,
-                            float* verts, float* joints, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  TAMF_REQUIRE(h, TAMF_E_BADARG, "tamf_mano_fk: null handle");
-  TAMF_REQUIRE(pose_mode == TAMF_POSE_QUAT || pose_mode == TAMF_POSE_REPR, TAMF_E_BADARG, "tamf_mano_fk: bad pose_mode");
-  TAMF_REQUIRE(N >= 0, TAMF_E_BADARG, "tamf_mano_fk: negative N");
+                            float* verts, float* joints, void* stream) {
+  return launch_fk(h, pose_mode, pose, betas, nullptr, N, verts, joints, (cudaStream_t)stream, "tamf_mano_fk");
+}
+
+extern "C" int tamf_mano_fk_select(const tamf_mano* h, int pose_mode, const float* pose, const float* betas,
+                                   const int32_t* frame_ids, int n, float* verts, float* joints, void* stream) {
+  TAMF_REQUIRE(frame_ids || n == 0, TAMF_E_BADARG, "tamf_mano_fk_select: null frame_ids");
+  return launch_fk(h, pose_mode, pose, betas, frame_ids, n, verts, joints, (cudaStream_t)stream, "tamf_mano_fk_select");
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertex normals: one CTA per mesh; face normals accumulated into shared memory, then normalised.
+// cross(v2-v1, v0-v1) -> v1, cross(v0-v2, v1-v2) -> v2, cross(v1-v0, v2-v0) -> v0 (all three equal the face's
+// area-weighted normal), normalize(eps 1e-6)  -- oracle/tamf_oracle.py:vertex_normals.
+// ------------------------------------------------------------------------------------------------
+namespace tamf {
+__global__ void __launch_bounds__(256)
+    vertex_normals_kernel(const float* __restrict__ verts, const int* __restrict__ faces, int V, int F,
+                          float* __restrict__ normals) {
+  extern __shared__ float sN[];  // [V*3] accumulators, then [V*3] vertex cache
+  float* sV = sN + V * 3;
+  const float* v = verts + (size_t)blockIdx.x * V * 3;
+  for (int i = threadIdx.x; i < V * 3; i += blockDim.x) {
+    sN[i] = 0.f;
+    sV[i] = v[i];
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    const float a[3] = {sV[3 * i0], sV[3 * i0 + 1], sV[3 * i0 + 2]};
+    const float b[3] = {sV[3 * i1], sV[3 * i1 + 1], sV[3 * i1 + 2]};
+    const float c[3] = {sV[3 * i2], sV[3 * i2 + 1], sV[3 * i2 + 2]};
+    auto cross_add = [&](const float* p, const float* q, const float* o, int dst) {  // cross(p-o, q-o) -> dst
+      const float ux = p[0] - o[0], uy = p[1] - o[1], uz = p[2] - o[2];
+      const float wx = q[0] - o[0], wy = q[1] - o[1], wz = q[2] - o[2];
+      atomicAdd(&sN[3 * dst + 0], uy * wz - uz * wy);
+      atomicAdd(&sN[3 * dst + 1], uz * wx - ux * wz);
+      atomicAdd(&sN[3 * dst + 2], ux * wy - uy * wx);
+    };
+    cross_add(c, a, b, i1);
+    cross_add(a, b, c, i2);
+    cross_add(b, c, a, i0);
+  }
+  __syncthreads();
+  float* out = normals + (size_t)blockIdx.x * V * 3;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float x = sN[3 * i], y = sN[3 * i + 1], z = sN[3 * i + 2];
+    const float inv = 1.0f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-6f);
+    out[3 * i] = x * inv, out[3 * i + 1] = y * inv, out[3 * i + 2] = z * inv;
+  }
+}
+}  // namespace tamf
+
+extern "C" int tamf_vertex_normals(const float* verts, const int32_t* faces, int N, int V, int F, float* normals,
+                                   void* stream) {
+  TAMF_REQUIRE(N >= 0 && V > 0 && F >= 0, TAMF_E_BADARG, "tamf_vertex_normals: bad size");
   if (N == 0) return TAMF_OK;
-  TAMF_REQUIRE(pose && betas && verts && joints, TAMF_E_BADARG, "tamf_mano_fk: null pointer");
-  mano_fk_kernel<<<(N + FK_FT - 1) / FK_FT, FK_THREADS, 0, stream>>>(h->d.blendT, h->d.vt, h->d.J0, h->d.JS, h->d.wT,
-                                                                    h->d.is_right, pose_mode, pose, betas, N, verts,
-                                                                    joints);
+  TAMF_REQUIRE(verts && faces && normals, TAMF_E_BADARG, "tamf_vertex_normals: null pointer");
+  TAMF_REQUIRE((size_t)V * 24 <= 48 * 1024, TAMF_E_BADARG, "tamf_vertex_normals: V too large for one CTA");
+  int rc = check_device();
+  if (rc) return rc;
+  vertex_normals_kernel<<<N, 256, (size_t)V * 24, (cudaStream_t)stream>>>(verts, faces, V, F, normals);
   TAMF_LAUNCH_CHECK();
   return TAMF_OK;
 }

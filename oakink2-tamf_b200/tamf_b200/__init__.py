@@ -1,8 +1,9 @@
 """tamf_b200 -- B200-native drop-in for the reverse-diffusion sampling hot path of OakInk2-TaMF.
 
 Same call signatures as the reference (InterationSegmentMDM.forward(x, timesteps, batch), p_sample_loop,
-ManoLayer(...)(pose_coeffs, betas), ChamferDistance()(x, y), point2point_signed), backed by libtamf_b200.so."""
+ManoLayer(...)(pose_coeffs, betas), ChamferDistance()(x, y), point2point_signed, SegmentRefineModel(mano_path, ...)(batch)), backed by libtamf_b200.so."""
 from .chamfer import ChamferDistance, h2o_dist, nn_query, point2point_signed  # noqa: F401
 from .diffusion import GaussianDiffusion, SpacedDiffusion, create_gaussian_diffusion  # noqa: F401
 from .manolayer import MANOOutput, ManoLayer  # noqa: F401
 from .mdm import InterationSegmentMDM  # noqa: F401
+from .refine import SegmentRefineModel, vertex_normals  # noqa: F401

@@ -19,7 +19,8 @@ SYMBOLS = [
     "tamf_mano_fk", "tamf_denoiser_create", "tamf_denoiser_destroy", "tamf_denoiser_workspace_bytes",
     "tamf_denoiser_bind", "tamf_denoiser_set_cond", "tamf_denoiser_forward", "tamf_p_sample_step",
     "tamf_p_sample_chain", "tamf_p_sample_loop_host", "tamf_denoiser_profile_step", "tamf_kernel_launch_count", "tamf_philox_normal",
-    "tamf_gemm_selftest",
+    "tamf_gemm_selftest", "tamf_refiner_create", "tamf_refiner_destroy", "tamf_refiner_workspace_bytes",
+    "tamf_refiner_bind", "tamf_refiner_forward", "tamf_mano_fk_select", "tamf_vertex_normals",
 ]
 
 
@@ -89,13 +90,14 @@ def lib() -> C.CDLL:
     L.tamf_denoiser_profile_step.argtypes = [vp, vp, i32, u64, vp, i32, vp, vp]
     L.tamf_philox_normal.argtypes = [vp, sz, u64, C.c_uint32, vp]
     L.tamf_gemm_selftest.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
-    if hasattr(L, "tamf_refiner_create"):
-        L.tamf_refiner_create.argtypes = [C.POINTER(TamfCfg), C.POINTER(TamfRWeights), vp, vp, C.POINTER(vp)]
-        L.tamf_refiner_destroy.argtypes = [vp]
-        L.tamf_refiner_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
-        L.tamf_refiner_workspace_bytes.restype = sz
-        L.tamf_refiner_bind.argtypes = [vp, i32, i32, i32, i32, vp, sz]
-        L.tamf_refiner_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp]
+    L.tamf_refiner_create.argtypes = [C.POINTER(TamfCfg), C.POINTER(TamfRWeights), C.POINTER(vp)]
+    L.tamf_refiner_destroy.argtypes = [vp]
+    L.tamf_refiner_workspace_bytes.argtypes = [vp, i32, i32]
+    L.tamf_refiner_workspace_bytes.restype = sz
+    L.tamf_refiner_bind.argtypes = [vp, i32, i32, vp, sz]
+    L.tamf_refiner_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    L.tamf_mano_fk_select.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp]
+    L.tamf_vertex_normals.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     _lib = L
     return L
 

@@ -39,6 +39,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.TamfCfg) == 10 * 4
     assert ctypes.sizeof(_lib.TamfLayerWeights) == 12 * 8
     assert ctypes.sizeof(_lib.TamfGWeights) == 21 * 8 + 8 + 8 + 3 * 8  # pe_rows padded to 8
+    assert ctypes.sizeof(_lib.TamfRWeights) == 17 * 8 + 8 + 8
 
 
 def test_no_gpu_fails_loudly():
