@@ -221,9 +221,16 @@ uint64_t tamf_kernel_launch_count(void);
 int tamf_philox_normal(float* out, size_t n, uint64_t seed, uint32_t t, void* stream);
 
 /* Self-test of the tcgen05 GEMM against caller-provided data: C[M,N] fp32 = A[M,K] bf16 . W[N,K]^T bf16 + bias.
- * a, w are device bf16 (uint16 bit patterns), bias device fp32 [N] or NULL, c device fp32. */
+ * a, w are device bf16 (uint16 bit patterns), bias device fp32 [N] or NULL, c device fp32.
+ * tile_n in {128,256,512}; cta_group 1 (one CTA per 128-row tile) or 2 (CTA pair, tcgen05.mma.cta_group::2). */
 int tamf_gemm_selftest(const uint16_t* a, const uint16_t* w, const float* bias, float* c, int M, int N, int K,
-                       int tile_n, void* stream);
+                       int tile_n, int cta_group, void* stream);
+
+/* Debug aid (tools/gemm_trace.py): one launch of a hot-path GEMM shape with per-CTA clock64 event timestamps.
+ * which: 0 = in_proj-like (bias -> bf16), 1 = linear1-like (bias + GELU -> bf16), 2 = LayerNorm GEMM (N = 512).
+ * a [M,K], w [N,K] bf16; bias [N]; out bf16 [M,N]; X fp32 [M,N] (which 2); trace int64 [148][64] (device). */
+int tamf_gemm_trace(int which, const uint16_t* a, const uint16_t* w, const float* bias, void* out, float* X, int M,
+                    int N, int K, long long* trace, void* stream);
 
 #ifdef __cplusplus
 }

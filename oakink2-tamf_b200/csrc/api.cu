@@ -72,19 +72,22 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2D bf16 row-major tensor [rows][inner], TMA box [box_rows][box_inner] with 128-byte swizzle (box_inner*2 == 128).
+// 2D bf16 row-major tensor [rows][inner], TMA box [box_rows][box_inner]: box_inner = 64 -> 128-byte swizzle,
+// box_inner = 32 -> 64-byte swizzle (the two K-major operand layouts gemm.cuh builds UMMA descriptors for).
 int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes,
                       uint32_t box_inner, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   TAMF_REQUIRE(enc != nullptr, TAMF_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   TAMF_REQUIRE(aligned16(gptr) && (row_pitch_bytes % 16) == 0, TAMF_E_ALIGN, "TMA tensor must be 16-byte aligned");
-  TAMF_REQUIRE(box_inner * 2 == 128 && box_rows <= 256, TAMF_E_BADARG, "TMA box must be 64 bf16 x <=256 rows");
+  TAMF_REQUIRE((box_inner == 64 || box_inner == 32) && box_rows <= 256, TAMF_E_BADARG,
+               "TMA box must be 64 or 32 bf16 x <=256 rows");
   cuuint64_t dims[2] = {inner, rows};
   cuuint64_t strides[1] = {row_pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
@@ -120,8 +123,21 @@ extern "C" int tamf_philox_normal(float* out, size_t n, uint64_t seed, uint32_t 
   return philox_fill(out, n, seed, t, (cudaStream_t)stream);
 }
 
+namespace tamf {
+template <int BN, int CG>
+static int selftest_run(const uint16_t* a, const uint16_t* w, const GemmParams& p, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d_bf16(&tmA, a, p.K, p.M, (uint64_t)p.K * 2, gemm_bk(BN, CG), 128);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, w, p.K, p.N, (uint64_t)p.K * 2, gemm_bk(BN, CG), gemm_b_box_rows(BN, CG));
+  if (rc) return rc;
+  if ((rc = configure_gemm<BN, EPI_F32, CG>())) return rc;
+  return launch_gemm<BN, EPI_F32, CG>(tmA, tmB, p, stream);
+}
+}  // namespace tamf
+
 extern "C" int tamf_gemm_selftest(const uint16_t* a, const uint16_t* w, const float* bias, float* c, int M, int N, int K,
-                                  int tile_n, void* stream_) {
+                                  int tile_n, int cta_group, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_device();
   if (rc) return rc;
@@ -129,21 +145,48 @@ extern "C" int tamf_gemm_selftest(const uint16_t* a, const uint16_t* w, const fl
   TAMF_REQUIRE(M > 0 && N > 0 && K > 0 && (K % 8) == 0 && (N % 32) == 0, TAMF_E_BADARG,
                "tamf_gemm_selftest: need K % 8 == 0 and N % 32 == 0");
   TAMF_REQUIRE(tile_n == 128 || tile_n == 256 || tile_n == 512, TAMF_E_BADARG, "tamf_gemm_selftest: tile_n");
-  CUtensorMap tmA, tmB;
-  rc = make_tmap_2d_bf16(&tmA, a, K, M, (uint64_t)K * 2, 64, 128);
-  if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tmB, w, K, N, (uint64_t)K * 2, 64, tile_n > 256 ? 256 : tile_n);
-  if (rc) return rc;
+  TAMF_REQUIRE(cta_group == 1 || cta_group == 2, TAMF_E_BADARG, "tamf_gemm_selftest: cta_group must be 1 or 2");
   GemmParams p{};
   p.M = M, p.N = N, p.K = K, p.bias = bias, p.out_f32 = c, p.ld_f32 = N;
-  if (tile_n == 128) {
-    if ((rc = configure_gemm<128, EPI_F32>())) return rc;
-    return launch_gemm<128, EPI_F32>(tmA, tmB, p, stream);
+  if (cta_group == 1) {
+    if (tile_n == 128) return selftest_run<128, 1>(a, w, p, stream);
+    if (tile_n == 256) return selftest_run<256, 1>(a, w, p, stream);
+    return selftest_run<512, 1>(a, w, p, stream);
   }
-  if (tile_n == 256) {
-    if ((rc = configure_gemm<256, EPI_F32>())) return rc;
-    return launch_gemm<256, EPI_F32>(tmA, tmB, p, stream);
+  if (tile_n == 128) return selftest_run<128, 2>(a, w, p, stream);
+  if (tile_n == 256) return selftest_run<256, 2>(a, w, p, stream);
+  return selftest_run<512, 2>(a, w, p, stream);
+}
+
+// Debug aid (tools/gemm_trace.py): one launch of the hot-path GEMM shape `which` on caller data with per-CTA
+// clock64 timestamps.  which: 0 in_proj-like <256,BIAS_BF16>, 1 linear1-like <256,GELU>, 2 LN <512,RES_LN>.
+// trace [148][64] int64 device.  out: bf16 [M,N] (which 0/1); X fp32 + Xb bf16 [M,N] (which 2).
+extern "C" int tamf_gemm_trace(int which, const uint16_t* a, const uint16_t* w, const float* bias, void* out, float* X,
+                               int M, int N, int K, long long* trace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_device();
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_2d_bf16(&tmA, a, K, M, (uint64_t)K * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmB, w, K, N, (uint64_t)K * 2, 64, gemm_b_box_rows(256, 2)))) return rc;
+  GemmParams p{};
+  p.M = M, p.N = N, p.K = K, p.bias = bias, p.trace = trace;
+  p.dbg = getenv("TAMF_GEMM_DBG") ? atoi(getenv("TAMF_GEMM_DBG")) : 0;
+  if (which == 2) {
+    p.X = X, p.Xb = (__nv_bfloat16*)out, p.gamma = bias, p.beta = bias;
+    if ((rc = configure_gemm<512, EPI_RES_LN, 2>())) return rc;
+    return launch_gemm<512, EPI_RES_LN, 2>(tmA, tmB, p, stream);
   }
-  if ((rc = configure_gemm<512, EPI_F32>())) return rc;
-  return launch_gemm<512, EPI_F32>(tmA, tmB, p, stream);
+  p.out_bf16 = (__nv_bfloat16*)out, p.ld_bf16 = N;
+  if (which == 10) {  // single-CTA form of the in_proj shape (comparison only)
+    if ((rc = make_tmap_2d_bf16(&tmB, w, K, N, (uint64_t)K * 2, 64, gemm_b_box_rows(256, 1)))) return rc;
+    if ((rc = configure_gemm<256, EPI_BIAS_BF16, 1>())) return rc;
+    return launch_gemm<256, EPI_BIAS_BF16, 1>(tmA, tmB, p, stream);
+  }
+  if (which == 1) {
+    if ((rc = configure_gemm<256, EPI_BIAS_GELU_BF16, 2>())) return rc;
+    return launch_gemm<256, EPI_BIAS_GELU_BF16, 2>(tmA, tmB, p, stream);
+  }
+  if ((rc = configure_gemm<256, EPI_BIAS_BF16, 2>())) return rc;
+  return launch_gemm<256, EPI_BIAS_BF16, 2>(tmA, tmB, p, stream);
 }

@@ -154,6 +154,62 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ---- 2-CTA (cta_group::2) variants: the CTA pair of a cluster issues one 256-row MMA from the leader CTA ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: data lands in the issuing CTA's shared memory, bytes are credited to `bar_cluster_addr`
+// (the leader CTA's mbarrier).
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c_inner,
+                                                int c_row) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c_inner), "r"(c_row)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows per CTA] * B[N/2 rows per CTA]^T, M = 256; issued by ONE thread of the leader.
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in BOTH CTAs once all prior MMAs of this thread completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 // Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major (cute/arch/mma_sm100_desc.hpp InstrDescriptor).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -225,6 +281,22 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t t, uint64
   float s, c;
   __sincosf(6.283185307179586f * u1, &s, &c);
   return (sel & 1u) ? rad * s : rad * c;
+}
+
+// Sampler noise inside the fused posterior epilogue: one Philox block = 4 standard normals for the 4 consecutive
+// features 4g..4g+3 of frame (b*T + tau) at diffusion step t.  Counter (frame.lo, frame.hi, t, g | 0x80000000),
+// key = seed (the high bit of the last word keeps this stream disjoint from philox_normal's).
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t t, uint64_t frame, uint32_t g, float (&n)[4]) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)frame, (uint32_t)(frame >> 32), t, g | 0x80000000u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float u0 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
+  const float u2 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f, u3 = ((float)r.w + 0.5f) * 2.3283064365386963e-10f;
+  const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+  float s, c;
+  __sincosf(6.283185307179586f * u1, &s, &c);
+  n[0] = ra * c, n[1] = ra * s;
+  __sincosf(6.283185307179586f * u3, &s, &c);
+  n[2] = rb * c, n[3] = rb * s;
 }
 
 #endif  // __CUDACC__

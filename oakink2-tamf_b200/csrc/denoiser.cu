@@ -5,9 +5,10 @@
 // GaussianDiffusion.p_sample / p_sample_loop_progressive (model/diffusion/gaussian_diffusion.py:412-460, 573-640).
 //
 // Per step (everything else is hoisted, SURVEY.md 8a'):
-//   prep        x_t [B,99,1,T] fp32 -> A0 [B*T,128] bf16 (frame-major, K zero-padded); token 0 = ttab[t]+pe[0];
-//               tokens 1..4 = cached prefix
-//   embed-a     H0 = silu(A0 . Wf^T + obj_half)          Wf = merge0[:, :d] . poseEmbedding (folded, [d,128])
+//   prep        x_t [B,99,1,T] fp32 -> A0[:, 0:100] bf16 (frame-major); token 0 = ttab[t]+pe[0]; tokens 1..4 = prefix
+//   embed-a     H0 = silu(A0 . Wf^T + bf)   A0 = [x_t (99) | 0 | mean_obj(obj_traj) (9) | 0..] (K = 128), Wf =
+//               [merge0[:, :d] . poseEmbedding | 0 | merge0[:, d:] . objPoseEmbedding | 0..]  (both linear maps of
+//               input_merge.0 folded; the trajectory columns of A0 are written once per sample)
 //   embed-b     tok[5+tau] = nan_to_num(H0 . merge2^T + b) + pe[5+tau]     -> X fp32 / Xb bf16, rows b*S+5+tau
 //   8 x layer   QKV = Xb . Win^T + b ; ATT = softmax(QK^T/sqrt(hd)) V ; X = LN1(X + ATT . Wo^T + b)
 //               H = gelu(Xb . W1^T + b) ; X = LN2(X + H . W2^T + b)
@@ -16,7 +17,7 @@
 //
 // HBM layout (row = token index b*S + s, S = 5 + T; all row-major):
 //   X  fp32 [M,d] residual stream | Xb bf16 [M,d] GEMM operand copy | QKV bf16 [M,3d] | ATT bf16 [M,d] | H bf16 [M,ff]
-//   A0 bf16 [B*T,128] | H0 bf16 [B*T,d] | obj_half fp32 [B*T,d] | prefix fp32 [B,4,d] | ttab fp32 [steps,d]
+//   A0 bf16 [B*T,128] | H0 bf16 [B*T,d] | prefix fp32 [B,4,d] | ttab fp32 [steps,d]
 #include <vector>
 
 #include "attn.cuh"
@@ -27,7 +28,8 @@ namespace tamf {
 
 int philox_fill(float* out, size_t n, uint64_t seed, uint32_t t, cudaStream_t stream);
 
-constexpr int KPAD = 128;      // input_dim 99 zero-padded to the GEMM K tile
+constexpr int KPAD = 128;      // K of embed-a: 99 pose features | 0 | 9 trajectory features at TRAJ_COL | 0...
+constexpr int TRAJ_COL = 100;  // first column of mean_obj(obj_traj) in A0 / Wfold (even: prep writes bf16 pairs)
 constexpr int MAX_NOBJ = 8;    // staging capacity of tamf_p_sample_loop_host
 
 // ------------------------------------------------------------------------------------------------
@@ -43,6 +45,14 @@ __global__ void prefix_finish_kernel(float* __restrict__ prefix, const int* __re
   float v = prefix[i];
   if (s == 1) v = (hand_side[b] == 1 && c == 0) ? 1.f : 0.f;
   prefix[i] = nan_to_num(v) + pe[(size_t)(1 + s) * d + c];
+}
+
+// A0[r, TRAJ_COL .. KPAD) = [mean_obj(obj_traj)[r, 0:9], 0 ...] (bf16), once per sample batch
+__global__ void a0_cond_kernel(const float* __restrict__ trajmean, __nv_bfloat16* __restrict__ A0, int rows) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * (KPAD - TRAJ_COL)) return;
+  const int r = (int)(i / (KPAD - TRAJ_COL)), c = (int)(i % (KPAD - TRAJ_COL));
+  A0[(size_t)r * KPAD + TRAJ_COL + c] = __float2bfloat16_rn(c < 9 ? trajmean[(size_t)r * 9 + c] : 0.f);
 }
 
 __global__ void add_int_kernel(int* p, int n, int dv) {
@@ -66,8 +76,8 @@ __global__ void __launch_bounds__(256)
     tile[k][lane] = (tau < T) ? x[((size_t)b * nfeat + k) * T + tau] : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * (KPAD / 2); i += 256) {
-    const int j = i / (KPAD / 2), kp = (i % (KPAD / 2)) * 2;
+  for (int i = threadIdx.x; i < 32 * (TRAJ_COL / 2); i += 256) {  // columns >= TRAJ_COL belong to set_cond
+    const int j = i / (TRAJ_COL / 2), kp = (i % (TRAJ_COL / 2)) * 2;
     const int tau = tau0 + j;
     if (tau < T) {
       const float v0 = kp < nfeat ? tile[kp][j] : 0.f, v1 = (kp + 1) < nfeat ? tile[kp + 1][j] : 0.f;
@@ -103,8 +113,7 @@ struct tamf_denoiser {
   EncoderStack enc;  // the 8 post-norm layers (encoder.cuh)
   EncoderBuffers buf;
   // fp32 conditioning weights (exact fp32 SIMT path, once per sample)
-  float *shape_w, *shape_b, *objemb_w, *objemb_b, *objtraj_w, *objtraj_b, *merge0_w, *merge_bias /* b1 + W1a.bp */,
-      *text_w, *text_b, *pe, *ttab;
+  float *shape_w, *shape_b, *objemb_w, *objemb_b, *merge_bias /* b1 + W1a.bp + W1b.bo */, *text_w, *text_b, *pe, *ttab;
   int pe_rows = 0;
   // bf16 hot-path weights
   __nv_bfloat16 *wfold /*[d,128]*/, *wm2 /*[d,d]*/, *wfin /*[99,d]*/;
@@ -114,7 +123,7 @@ struct tamf_denoiser {
   // bound workspace
   int B = 0, T = 0, S = 0, M = 0, Mf = 0;
   bool bound = false, cond_set = false;
-  float *objhalf, *prefix, *objtok, *trajmean, *shapemean, *embmean, *xbuf;
+  float *prefix, *trajmean, *shapemean, *embmean, *xbuf;
   float *st_text, *st_shape, *st_traj, *st_emb;  // host-API staging
   int *st_side, *t_dev;
   __nv_bfloat16 *A0, *H0;
@@ -147,15 +156,15 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, fl
   mark_event(marks, s);
   {  // embed-a
     GemmParams p{};
-    p.M = Mf, p.N = d, p.K = KPAD, p.bias = nullptr, p.addmat = h->objhalf, p.out_bf16 = h->H0, p.ld_bf16 = d;
-    if ((rc = launch_gemm<256, EPI_ADD_SILU_BF16>(h->tm_A0, h->tm_wfold, p, s))) return rc;
+    p.M = Mf, p.N = d, p.K = KPAD, p.bias = h->merge_bias, p.out_bf16 = h->H0, p.ld_bf16 = d;
+    if ((rc = launch_gemm<256, EPI_BIAS_SILU_BF16, 2>(h->tm_A0, h->tm_wfold, p, s))) return rc;
     mark_event(marks, s);
   }
   {  // embed-b
     GemmParams p{};
     p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = 5, p.X = h->buf.X,
     p.Xb = h->buf.Xb;
-    if ((rc = launch_gemm<256, EPI_TOKEN_OUT>(h->tm_H0, h->tm_wm2, p, s))) return rc;
+    if ((rc = launch_gemm<256, EPI_TOKEN_OUT, 2>(h->tm_H0, h->tm_wm2, p, s))) return rc;
     mark_event(marks, s);
   }
   if ((rc = enqueue_encoder(h->enc, h->buf, s, marks))) return rc;
@@ -164,7 +173,7 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, fl
     p.M = M, p.N = h->nfeat, p.K = d, p.bias = h->b_fin, p.T = T, p.S = S, p.P0 = 5, p.nfeat = h->nfeat;
     p.x_t = x_t, p.x_out = x_out, p.x0_out = x0_out, p.noise = noise, p.t_ptr = t_ptr, p.c1 = h->c1, p.c2 = h->c2,
     p.sigma = h->sigma, p.seed = seed;
-    if ((rc = launch_gemm<128, EPI_POSTERIOR>(h->tm_Xb_fin, h->tm_wfin, p, s))) return rc;
+    if ((rc = launch_gemm<128, EPI_POSTERIOR, 2>(h->tm_Xb_fin, h->tm_wfin, p, s))) return rc;
     mark_event(marks, s);
   }
   return TAMF_OK;
@@ -194,7 +203,8 @@ extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w
   if (rc) return rc;
   const int d = cfg->latent_dim, ff = cfg->ff_size, L = cfg->num_layers, H = cfg->num_heads, nf = cfg->input_dim;
   TAMF_REQUIRE(d == 256 || d == 512, TAMF_E_BADARG, "latent_dim must be 256 or 512 (arch_mdm / arch_mdm_l)");
-  TAMF_REQUIRE(nf > 0 && nf <= KPAD, TAMF_E_BADARG, "input_dim must be <= 128");
+  TAMF_REQUIRE(nf > 0 && nf < TRAJ_COL, TAMF_E_BADARG, "input_dim must be < 100");
+  TAMF_REQUIRE(cfg->obj_input_dim == 9, TAMF_E_BADARG, "obj_input_dim must be 9");
   TAMF_REQUIRE(L > 0 && L <= 64 && w->layers, TAMF_E_BADARG, "bad num_layers");
   TAMF_REQUIRE(cfg->num_steps > 0 && w->pe && w->pe_rows >= cfg->num_steps, TAMF_E_BADARG,
                "pe table must cover num_steps rows");
@@ -211,9 +221,6 @@ extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w
   TRY(upload_f32(h, &h->shape_b, w->shape_b, d));
   TRY(upload_f32(h, &h->objemb_w, w->objemb_w, (size_t)d * cfg->obj_embed_dim));
   TRY(upload_f32(h, &h->objemb_b, w->objemb_b, d));
-  TRY(upload_f32(h, &h->objtraj_w, w->objtraj_w, (size_t)d * cfg->obj_input_dim));
-  TRY(upload_f32(h, &h->objtraj_b, w->objtraj_b, d));
-  TRY(upload_f32(h, &h->merge0_w, w->merge0_w, (size_t)d * 2 * d));
   TRY(upload_f32(h, &h->text_w, w->text_w, (size_t)d * cfg->clip_dim));
   TRY(upload_f32(h, &h->text_b, w->text_b, d));
   h->pe_rows = w->pe_rows;
@@ -221,31 +228,37 @@ extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w
   TRY(upload_f32(h, &h->b_m2, w->merge2_b, d));
   TRY(upload_f32(h, &h->b_fin, w->final_b, nf));
   {
-    // fold input_process.poseEmbedding through the hand half of input_merge.0 (exact in real arithmetic):
-    //   W1a (Wp x + bp) = (W1a Wp) x + W1a bp ;  accumulated in double, rounded once.
-    TAMF_REQUIRE(w->pose_w && w->pose_b && w->merge0_w && w->merge0_b, TAMF_E_BADARG, "null weight pointer");
-    std::vector<float> wf((size_t)d * nf), mb(d);
-    std::vector<double> row(nf);
+    // fold both linear maps feeding input_merge.0 through it (exact in real arithmetic; double accumulation,
+    // rounded once):  W1 [Wp x + bp ; mean_o(Wo traj_o + bo)] + b1
+    //              = (W1a Wp) x + (W1b Wo) mean_o(traj_o) + (b1 + W1a bp + W1b bo)
+    // (the mean over the zero-padded object axis commutes with the linear map, interaction_segment_mdm.py:243-246)
+    TAMF_REQUIRE(w->pose_w && w->pose_b && w->objtraj_w && w->objtraj_b && w->merge0_w && w->merge0_b, TAMF_E_BADARG,
+                 "null weight pointer");
+    std::vector<float> wf((size_t)d * KPAD, 0.f), mb(d);
+    std::vector<double> row(KPAD);
     for (int n = 0; n < d; ++n) {
-      for (int k = 0; k < nf; ++k) row[k] = 0.0;
+      std::fill(row.begin(), row.end(), 0.0);
       double bacc = (double)w->merge0_b[n];
+      const float* w1 = w->merge0_w + (size_t)n * 2 * d;
       for (int j = 0; j < d; ++j) {
-        const double a = (double)w->merge0_w[(size_t)n * 2 * d + j];
+        const double a = (double)w1[j], c = (double)w1[d + j];
         const float* pr = w->pose_w + (size_t)j * nf;
+        const float* tr = w->objtraj_w + (size_t)j * 9;
         for (int k = 0; k < nf; ++k) row[k] += a * (double)pr[k];
-        bacc += a * (double)w->pose_b[j];
+        for (int k = 0; k < 9; ++k) row[TRAJ_COL + k] += c * (double)tr[k];
+        bacc += a * (double)w->pose_b[j] + c * (double)w->objtraj_b[j];
       }
-      for (int k = 0; k < nf; ++k) wf[(size_t)n * nf + k] = (float)row[k];
+      for (int k = 0; k < KPAD; ++k) wf[(size_t)n * KPAD + k] = (float)row[k];
       mb[n] = (float)bacc;
     }
-    TRY(upload_bf16(h, &h->wfold, wf.data(), d, nf, KPAD));
+    TRY(upload_bf16(h, &h->wfold, wf.data(), d, KPAD, KPAD));
     TRY(upload_f32(h, &h->merge_bias, mb.data(), d));
   }
   TRY(upload_bf16(h, &h->wm2, w->merge2_w, d, d, d));
   TRY(upload_bf16(h, &h->wfin, w->final_w, nf, d, d));
-  TRY(make_tmap_2d_bf16(&h->tm_wfold, h->wfold, KPAD, d, (uint64_t)KPAD * 2, 64, 256));
-  TRY(make_tmap_2d_bf16(&h->tm_wm2, h->wm2, d, d, (uint64_t)d * 2, 64, 256));
-  TRY(make_tmap_2d_bf16(&h->tm_wfin, h->wfin, d, nf, (uint64_t)d * 2, 64, 128));
+  TRY(make_tmap_2d_bf16(&h->tm_wfold, h->wfold, KPAD, d, (uint64_t)KPAD * 2, 64, gemm_b_box_rows(256, 2)));
+  TRY(make_tmap_2d_bf16(&h->tm_wm2, h->wm2, d, d, (uint64_t)d * 2, 64, gemm_b_box_rows(256, 2)));
+  TRY(make_tmap_2d_bf16(&h->tm_wfin, h->wfin, d, nf, (uint64_t)d * 2, 64, gemm_b_box_rows(128, 2)));
   TRY(h->enc.upload(h->pool, w->layers, d, ff, L, H));
   {
     // schedule: fp32 lookups exactly like _extract_into_tensor(...).float() (gaussian_diffusion.py:1275);
@@ -279,9 +292,9 @@ extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w
       return TAMF_E_CUDA;
     }
   }
-  TRY((configure_gemm<256, EPI_ADD_SILU_BF16>()));
-  TRY((configure_gemm<256, EPI_TOKEN_OUT>()));
-  TRY((configure_gemm<128, EPI_POSTERIOR>()));
+  TRY((configure_gemm<256, EPI_BIAS_SILU_BF16, 2>()));
+  TRY((configure_gemm<256, EPI_TOKEN_OUT, 2>()));
+  TRY((configure_gemm<128, EPI_POSTERIOR, 2>()));
   TRY(configure_encoder_kernels());
 #undef TRY
   *out = h;
@@ -304,9 +317,9 @@ static WsLayout ws_layout(const tamf_denoiser* h, int B, int T) {
       M * ff * 2,                                // 4 H
       Mf * KPAD * 2,                             // 5 A0
       Mf * d * 2,                                // 6 H0
-      Mf * d * 4,                                // 7 objhalf
+      256,                                       // 7 (unused)
       (size_t)B * 4 * d * 4,                     // 8 prefix
-      Mf * d * 4,                                // 9 objtok
+      256,                                       // 9 (unused)
       Mf * 9 * 4,                                // 10 trajmean
       (size_t)B * 16 * 4,                        // 11 shapemean
       (size_t)B * h->cfg.obj_embed_dim * 4,      // 12 embmean
@@ -353,9 +366,7 @@ extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size
   h->buf.Hb = (__nv_bfloat16*)(p + L.off[4]);
   h->A0 = (__nv_bfloat16*)(p + L.off[5]);
   h->H0 = (__nv_bfloat16*)(p + L.off[6]);
-  h->objhalf = (float*)(p + L.off[7]);
   h->prefix = (float*)(p + L.off[8]);
-  h->objtok = (float*)(p + L.off[9]);
   h->trajmean = (float*)(p + L.off[10]);
   h->shapemean = (float*)(p + L.off[11]);
   h->embmean = (float*)(p + L.off[12]);
@@ -409,11 +420,12 @@ extern "C" int tamf_denoiser_set_cond(tamf_denoiser* h, const float* text_feat, 
     prefix_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->prefix, hand_side, h->pe, B, d);
     TAMF_LAUNCH_CHECK();
   }
-  // object half of input_merge.0 (+ all constant biases): obj_half = obj_tok . W1b^T + (b1 + W1a bp)
-  if ((rc = linear_f32(h->trajmean, 9, h->objtraj_w, 9, h->objtraj_b, h->objtok, d, Mf, d, 9, 0, nullptr, 0, s)))
-    return rc;
-  if ((rc = linear_f32(h->objtok, d, h->merge0_w + d, 2 * d, h->merge_bias, h->objhalf, d, Mf, d, d, 0, nullptr, 0, s)))
-    return rc;
+  // trajectory columns of the embed-a operand (the object half of input_merge.0 is folded into Wfold)
+  {
+    const size_t n = (size_t)Mf * (KPAD - TRAJ_COL);
+    a0_cond_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->trajmean, h->A0, Mf);
+    TAMF_LAUNCH_CHECK();
+  }
   h->cond_set = true;
   return TAMF_OK;
 }

@@ -181,10 +181,12 @@ int EncoderStack::upload(DevPool& pool, const tamf_layer_weights* w, int d_, int
     TRY(pool.upload_f32(&o.be1, s.norm1_b, d));
     TRY(pool.upload_f32(&o.g2, s.norm2_w, d));
     TRY(pool.upload_f32(&o.be2, s.norm2_b, d));
-    TRY(make_tmap_2d_bf16(&o.tm_in, o.w_in, d, 3 * d, (uint64_t)d * 2, 64, 256));
-    TRY(make_tmap_2d_bf16(&o.tm_out, o.w_out, d, d, (uint64_t)d * 2, 64, 256));
-    TRY(make_tmap_2d_bf16(&o.tm_w1, o.w1, d, ff, (uint64_t)d * 2, 64, 256));
-    TRY(make_tmap_2d_bf16(&o.tm_w2, o.w2, ff, d, (uint64_t)ff * 2, 64, 256));
+    // every encoder GEMM runs as a CTA pair (CG = 2): BK = 64, each CTA stages UN/2 = 128 rows of W per box
+    const uint32_t wbox = (uint32_t)gemm_b_box_rows(256, 2);
+    TRY(make_tmap_2d_bf16(&o.tm_in, o.w_in, d, 3 * d, (uint64_t)d * 2, 64, wbox));
+    TRY(make_tmap_2d_bf16(&o.tm_out, o.w_out, d, d, (uint64_t)d * 2, 64, wbox));
+    TRY(make_tmap_2d_bf16(&o.tm_w1, o.w1, d, ff, (uint64_t)d * 2, 64, wbox));
+    TRY(make_tmap_2d_bf16(&o.tm_w2, o.w2, ff, d, (uint64_t)ff * 2, 64, wbox));
   }
 #undef TRY
   return TAMF_OK;
@@ -200,10 +202,10 @@ int EncoderBuffers::make_maps(int d, int ff) {
 
 int configure_encoder_kernels() {
   int rc;
-  if ((rc = configure_gemm<256, EPI_BIAS_BF16>())) return rc;
-  if ((rc = configure_gemm<256, EPI_BIAS_GELU_BF16>())) return rc;
-  if ((rc = configure_gemm<256, EPI_RES_LN>())) return rc;
-  if ((rc = configure_gemm<512, EPI_RES_LN>())) return rc;
+  if ((rc = configure_gemm<256, EPI_BIAS_BF16, 2>())) return rc;
+  if ((rc = configure_gemm<256, EPI_BIAS_GELU_BF16, 2>())) return rc;
+  if ((rc = configure_gemm<256, EPI_RES_LN, 2>())) return rc;
+  if ((rc = configure_gemm<512, EPI_RES_LN, 2>())) return rc;
   if ((rc = configure_attn<64>())) return rc;
   if ((rc = configure_attn<128>())) return rc;
   return TAMF_OK;
@@ -218,7 +220,7 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     {
       GemmParams p{};
       p.M = M, p.N = 3 * d, p.K = d, p.bias = w.b_in, p.out_bf16 = buf.QKV, p.ld_bf16 = 3 * d;
-      if ((rc = launch_gemm<256, EPI_BIAS_BF16>(buf.tm_Xb, w.tm_in, p, s))) return rc;
+      if ((rc = launch_gemm<256, EPI_BIAS_BF16, 2>(buf.tm_Xb, w.tm_in, p, s))) return rc;
       mark_event(marks, s);
     }
     if (d / enc.H == 128)
@@ -230,22 +232,22 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     {
       GemmParams p{};
       p.M = M, p.N = d, p.K = d, p.bias = w.b_out, p.X = buf.X, p.Xb = buf.Xb, p.gamma = w.g1, p.beta = w.be1;
-      rc = (d == 512) ? launch_gemm<512, EPI_RES_LN>(buf.tm_ATT, w.tm_out, p, s)
-                      : launch_gemm<256, EPI_RES_LN>(buf.tm_ATT, w.tm_out, p, s);
+      rc = (d == 512) ? launch_gemm<512, EPI_RES_LN, 2>(buf.tm_ATT, w.tm_out, p, s)
+                      : launch_gemm<256, EPI_RES_LN, 2>(buf.tm_ATT, w.tm_out, p, s);
       if (rc) return rc;
       mark_event(marks, s);
     }
     {
       GemmParams p{};
       p.M = M, p.N = ff, p.K = d, p.bias = w.b1, p.out_bf16 = buf.Hb, p.ld_bf16 = ff;
-      if ((rc = launch_gemm<256, EPI_BIAS_GELU_BF16>(buf.tm_Xb, w.tm_w1, p, s))) return rc;
+      if ((rc = launch_gemm<256, EPI_BIAS_GELU_BF16, 2>(buf.tm_Xb, w.tm_w1, p, s))) return rc;
       mark_event(marks, s);
     }
     {
       GemmParams p{};
       p.M = M, p.N = d, p.K = ff, p.bias = w.b2, p.X = buf.X, p.Xb = buf.Xb, p.gamma = w.g2, p.beta = w.be2;
-      rc = (d == 512) ? launch_gemm<512, EPI_RES_LN>(buf.tm_H, w.tm_w2, p, s)
-                      : launch_gemm<256, EPI_RES_LN>(buf.tm_H, w.tm_w2, p, s);
+      rc = (d == 512) ? launch_gemm<512, EPI_RES_LN, 2>(buf.tm_H, w.tm_w2, p, s)
+                      : launch_gemm<256, EPI_RES_LN, 2>(buf.tm_H, w.tm_w2, p, s);
       if (rc) return rc;
       mark_event(marks, s);
     }

@@ -2,15 +2,24 @@
 //
 //   C[M,N] = A[M,K] (bf16, K-major) . W[N,K]^T (bf16, K-major = nn.Linear layout), fp32 accumulation in TMEM.
 //
-// One CTA per SM, 320 threads:
-//   warps 0-7  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (warp w owns TMEM lanes 32*(w%4).., column half
-//              w/4) and apply the fused epilogue.  TMEM hands every thread one accumulator ROW, so results are
-//              transposed through a warp-private XOR-swizzled shared-memory tile and leave the SM as full sectors;
-//              the fp32 residual of the LayerNorm epilogue arrives the same way (cp.async, one chunk ahead).
-//   warp 8     TMA producer: cp.async.bulk.tensor 2D loads of the 128x64 A tile and BNx64 W tile (128B swizzle)
-//              into a STAGES-deep shared-memory ring, signalled through mbarriers (expect_tx / complete_tx).
-//   warp 9     MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256, K=16) on
-//              shared-memory descriptors; tcgen05.commit releases ring slots and publishes accumulators.
+// CG = 2 (the hot-path configuration): a cluster of two CTAs on the two SMs of a TPC computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 (M = 256).  Each CTA stages its own 128 rows of A and HALF of the W tile, so the
+// shared-memory traffic per MMA drops from 12 KB to 8 KB per CTA -- with one CTA per tile the mainloop is bound by
+// the 128 B/clk of shared memory (UMMA operand reads + TMA writes), not by the tensor pipe (measured).
+// CG = 1 is the single-CTA form (M = 128), kept for the self-test and small problems.
+//
+// One CTA per SM, 576 threads:
+//   warps 0-15 epilogue: tcgen05.ld the CTA's 128 x BN fp32 accumulator (warp w owns TMEM lanes 32*(w%4).., column
+//              quarter w/4) and apply the fused epilogue.  TMEM hands every thread one accumulator ROW, so results
+//              are transposed through a warp-private XOR-swizzled shared-memory tile and leave the SM as full
+//              sectors; the fp32 residual of the LayerNorm epilogue arrives the same way (cp.async, one chunk
+//              ahead).  16 warps (4 per scheduler): the epilogue is latency-, not issue-bound.
+//   warp 16    TMA producer: cp.async.bulk.tensor 2D loads of the 128 x BK A tile and (BN/CG) x BK W tile into a
+//              STAGES-deep shared-memory ring, signalled through mbarriers (expect_tx / complete_tx; with CG = 2 both
+//              CTAs credit the leader's barrier).
+//   warp 17    MMA issuer (leader CTA only when CG = 2): one thread issues tcgen05.mma.kind::f16 (N <= 256, K = 16) on
+//              shared-memory descriptors; tcgen05.commit (multicast to both CTAs) releases ring slots and publishes
+//              accumulators.
 // The accumulator is double-buffered in TMEM when 2*BN <= 512 columns, so the epilogue of tile i overlaps the
 // mainloop of tile i+1 (persistent static round-robin tile schedule).  Launched with programmatic dependent launch:
 // barrier init, TMEM allocation, descriptor prefetch and the staging of bias/gamma/beta overlap the previous
@@ -19,7 +28,7 @@
 // Epilogues (what the reference runs as separate ATen kernels, SURVEY.md 2.4 K1,K3-K6,K9):
 //   EPI_BIAS_BF16      y = acc + b                                   -> bf16            (QKV in_proj)
 //   EPI_BIAS_GELU_BF16 y = gelu_erf(acc + b)                         -> bf16            (linear1 + F.gelu)
-//   EPI_ADD_SILU_BF16  y = silu(acc + addmat[m,n])                   -> bf16            (input_merge.0, hand half)
+//   EPI_BIAS_SILU_BF16 y = silu(acc + b)                             -> bf16            (input_merge.0, folded)
 //   EPI_TOKEN_OUT      y = nan_to_num(acc + b) + pe[P0+tau]          -> fp32 + bf16 token rows (input_merge.2)
 //   EPI_RES_LN         x = LayerNorm(x + acc + b) (eps 1e-5, biased var) in place -> fp32 + bf16 (BN == N == d)
 //   EPI_POSTERIOR      x0 = nan_to_num(acc + b); x_{t-1} = c1 x0 + c2 x_t + sigma eps  -> [B,99,1,T] fp32
@@ -33,7 +42,7 @@ namespace tamf {
 enum GemmEpi {
   EPI_BIAS_BF16 = 0,
   EPI_BIAS_GELU_BF16 = 1,
-  EPI_ADD_SILU_BF16 = 2,
+  EPI_BIAS_SILU_BF16 = 2,
   EPI_TOKEN_OUT = 3,
   EPI_RES_LN = 4,
   EPI_POSTERIOR = 5,
@@ -49,12 +58,10 @@ struct GemmParams {
   int ld_bf16;
   float* out_f32;
   int ld_f32;
-  // EPI_ADD_SILU_BF16
-  const float* addmat;  // [M,N]
   // EPI_TOKEN_OUT: GEMM row m = b*T + tau  ->  token row b*S + P0 + tau
   const float* pe;  // [rows, N]
   int T, S, P0;
-  // EPI_RES_LN: X fp32 [M,N] residual in / normalised out; Xb bf16 copy
+  // EPI_RES_LN: X fp32 [M,N] residual in / normalised out; Xb bf16 copy.  EPI_TOKEN_OUT writes the same pair.
   float* X;
   __nv_bfloat16* Xb;
   const float* gamma;
@@ -68,44 +75,80 @@ struct GemmParams {
   const float *c1, *c2, *sigma;  // [num_steps] fp32
   unsigned long long seed;
   int nfeat;
+  // debug only (tools/gemm_trace.py): per-CTA event timestamps, [grid][GEMM_TRACE_SLOTS] clock64 values; null in product
+  long long* trace;
+  int dbg;  // debug only: 1 skip global stores, 2 skip staging, 4 skip the whole epilogue body (bf16 epilogues)
 };
 
-constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 320;
-constexpr int GEMM_EPI_THREADS = 256;
-constexpr int GEMM_CTRL_BYTES = 256;      // mbarriers + TMEM slot
-constexpr int GEMM_STG_WARP = 2048;       // bf16 epilogues: warp-private staging tile, 32 rows x 64 B
-constexpr int GEMM_LN_STG_WARP = 14336;   // LN epilogue, per warp: 2 x 4 KB residual in | 4 KB fp32 out | 2 KB bf16 out
+constexpr int GEMM_TRACE_SLOTS = 64;
+constexpr int GEMM_BM = 128;                           // accumulator rows per CTA (TMEM lanes)
+constexpr int GEMM_EPI_WARPS = 16;
+constexpr int GEMM_EPI_THREADS = GEMM_EPI_WARPS * 32;  // 512
+constexpr int GEMM_THREADS = GEMM_EPI_THREADS + 64;    // + TMA producer warp + MMA issuer warp
+constexpr int GEMM_CTRL_BYTES = 256;                   // mbarriers + TMEM slot
+constexpr int GEMM_STG_WARP = 2048;                    // warp-private staging tile, 32 rows x 64 B
+constexpr int GEMM_LN_STG_WARP = 8192;                 // LN: 2 x 4 KB residual in (pass 1) = 4 KB fp32 + 2 KB bf16 out (pass 2)
+constexpr int GEMM_SMEM_MAX = 232448;                  // 227 KB
 
 constexpr bool epi_is_ln(int e) { return e == EPI_RES_LN; }
-constexpr bool epi_staged_bf16(int e) { return e == EPI_BIAS_BF16 || e == EPI_BIAS_GELU_BF16 || e == EPI_ADD_SILU_BF16; }
+constexpr bool epi_staged(int e) {
+  return e == EPI_BIAS_BF16 || e == EPI_BIAS_GELU_BF16 || e == EPI_BIAS_SILU_BF16 || e == EPI_TOKEN_OUT;
+}
+// Tile geometry shared with the host code that encodes the tensor maps.
+constexpr int gemm_bk(int bn, int cg) { return (bn == 512 && cg == 1) ? 32 : 64; }  // K extent of a pipeline stage
+constexpr int gemm_un(int bn) { return bn > 256 ? 256 : bn; }                        // N of one MMA instruction
+constexpr int gemm_b_box_rows(int bn, int cg) { return gemm_un(bn) / cg; }           // W rows per TMA box (per CTA)
 
-template <int BN>
+template <int BN, int EPI, int CG>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 128) ? 6 : (BN == 256 ? 4 : 2);
+  static constexpr int BK = gemm_bk(BN, CG);
+  static constexpr int UN = gemm_un(BN);
+  static constexpr int NH = BN / UN;            // MMA instructions per k-step
+  static constexpr int BOX_B = UN / CG;         // W rows per box held by this CTA
+  static constexpr int A_BYTES = GEMM_BM * BK * 2;
+  static constexpr int B_BYTES = NH * BOX_B * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 256) ? 256 : 512;
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // LN: bias | gamma | beta | row statistics sum[4][128], sumsq[4][128];  otherwise: the tile's bias slice
+  static constexpr int PARAM_BYTES = epi_is_ln(EPI) ? (3 * BN * 4 + 2 * 4 * 128 * 4) : (BN * 4);
+  static constexpr int STG_BYTES = epi_staged(EPI) ? GEMM_EPI_WARPS * GEMM_STG_WARP : 0;
+  static constexpr int RING_BUDGET = GEMM_SMEM_MAX - 1024 - GEMM_CTRL_BYTES - PARAM_BYTES - STG_BYTES;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  static_assert(PIPE_BYTES >= 8 * GEMM_LN_STG_WARP, "LN staging must fit in the pipeline ring");
+  // Shared-memory map: [pipeline ring | control | parameters | staging].  LN epilogues stage through the drained
+  // ring (one tile in flight); the other staged epilogues own a staging area (they overlap the next mainloop).
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + PIPE_BYTES + GEMM_CTRL_BYTES + PARAM_BYTES + STG_BYTES;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(!epi_is_ln(EPI) || PIPE_BYTES >= GEMM_EPI_WARPS * GEMM_LN_STG_WARP, "LN staging must fit in the ring");
+  static_assert(SMEM_BYTES <= GEMM_SMEM_MAX, "shared memory budget (227 KB) exceeded");
+  static_assert((2 * STAGES + 3 * ACC_STAGES) * 8 + 8 <= GEMM_CTRL_BYTES, "control block too small");
 };
 
-// Shared-memory map: [pipeline ring | control | parameters | staging].  LN epilogues stage through the drained
-// ring (one tile in flight); the bf16 epilogues own a staging area because they overlap the next tile's mainloop.
-template <int BN, int EPI>
-struct GemmSmem {
-  using Cfg = GemmCfg<BN>;
-  static constexpr int PARAM_BYTES = epi_is_ln(EPI) ? (3 * BN * 4 + 1024) : (2 * BN * 4);  // LN: b|gamma|beta|stats
-  static constexpr int STG_BYTES = epi_staged_bf16(EPI) ? 8 * GEMM_STG_WARP : 0;
-  static constexpr int BYTES = 1024 /*align slack*/ + Cfg::PIPE_BYTES + GEMM_CTRL_BYTES + PARAM_BYTES + STG_BYTES;
-  static_assert(BYTES <= 232448, "shared memory budget (227 KB) exceeded");
-};
-
-// exact-erf GELU (F.gelu default, the reference's activation="gelu")
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// GELU with the exact (erf) form of F.gelu, the reference's activation="gelu":  0.5 x (1 + erf(x / sqrt 2)).
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32-exact for a bf16 result) in 15 instructions:
+//   t = 1 / (1 + p |x| / sqrt 2),  q = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-x^2 / 2)  ( = erfc(|x| / sqrt 2) )
+//   gelu = x - 0.5 x q  (x >= 0),   0.5 x q  (x < 0)
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float t = fast_rcp(fmaf(0.23164189f, fabsf(x), 1.0f));
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  q = q * t * fast_ex2(x * x * -0.72134752f);
+  const float h = 0.5f * x * q;
+  return x >= 0.f ? x - h : h;
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
 // Programmatic dependent launch (PDL) controls
@@ -133,158 +176,212 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 __device__ __forceinline__ uint32_t stg128_off(int r, int p) { return (uint32_t)(r * 128 + ((p ^ (r & 7)) << 4)); }
 __device__ __forceinline__ uint32_t stg64_off(int r, int p) { return (uint32_t)(r * 64 + ((p ^ ((r >> 1) & 3)) << 4)); }
 
-template <int BN, int EPI>
+// K-major operand tile written by TMA with 64-byte swizzle (rows of 32 bf16): 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+
+#define GEMM_TRACE(slot)                                                                                    \
+  do {                                                                                                      \
+    if (p.trace && (slot) < GEMM_TRACE_SLOTS) p.trace[(size_t)blockIdx.x * GEMM_TRACE_SLOTS + (slot)] = clock64(); \
+  } while (0)
+
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
-  using Sm = GemmSmem<BN, EPI>;
-  constexpr int STAGES = Cfg::STAGES, ACC = Cfg::ACC_STAGES;
+  using Cfg = GemmCfg<BN, EPI, CG>;
+  constexpr int STAGES = Cfg::STAGES, ACC = Cfg::ACC_STAGES, BK = Cfg::BK, UN = Cfg::UN, NH = Cfg::NH;
   constexpr bool LN = epi_is_ln(EPI);
+  constexpr int PW = GEMM_EPI_WARPS, PT = GEMM_EPI_THREADS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;  // identical in both CTAs of a pair (same kernel, same layout)
   uint8_t* smem = smem_raw + pad;
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
   uint8_t* ctrl = smem + Cfg::PIPE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);  // [STAGES]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);  // [STAGES]  (CG = 2: the leader's copy is the live one)
   uint64_t* empty_bar = full_bar + STAGES;                  // [STAGES]
   uint64_t* tfull_bar = empty_bar + STAGES;                 // [ACC]
-  uint64_t* tempty_bar = tfull_bar + ACC;                   // [ACC]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC);
-  float* s_par = reinterpret_cast<float*>(ctrl + GEMM_CTRL_BYTES);
-  // LN: bias | gamma | beta | row statistics [2][128];  otherwise: bias slices of two consecutive tiles
-  float* s_gamma = s_par + BN;
-  float* s_beta = s_par + 2 * BN;
-  float* s_red = s_par + 3 * BN;
-  uint8_t* s_stage = LN ? smem : (ctrl + GEMM_CTRL_BYTES + Sm::PARAM_BYTES);
+  uint64_t* tempty_bar = tfull_bar + ACC;                   // [ACC]     (CG = 2: the leader's copy is the live one)
+  uint64_t* ldone_bar = tempty_bar + ACC;                   // [ACC]     LN only: THIS CTA's epilogue has left the ring
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ldone_bar + ACC);
+  float* s_bias = reinterpret_cast<float*>(ctrl + GEMM_CTRL_BYTES);
+  float* s_gamma = s_bias + BN;     // LN only
+  float* s_beta = s_bias + 2 * BN;  // LN only
+  float* s_sum = s_bias + 3 * BN;   // LN only: [4][128] partial row sums, then [4][128] partial sums of squares
+  float* s_sq = s_sum + 4 * 128;
+  uint8_t* s_stage = LN ? smem : (ctrl + GEMM_CTRL_BYTES + Cfg::PARAM_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader
+  const int tiles_m = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
-  if (warp == 8 && lane == 0) {
+  if (threadIdx.x == 0) GEMM_TRACE(0);
+  if (warp == PW && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 1);  // CG = 2: the leader's arrive.expect_tx covers the bytes of BOTH CTAs' loads
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);  // one elected lane per epilogue warp
+      mbar_init(&tempty_bar[a], PW * CG);  // one elected lane per epilogue warp (of both CTAs)
+      mbar_init(&ldone_bar[a], PW);
     }
     fence_mbar_init();
   }
-  if (warp == 9) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+  if (warp == PW + 1) {
+    if constexpr (CG == 2) {
+      tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   if constexpr (LN) {
-    if (warp < 8) {  // weights only (constant over the chain): staged before the dependency wait
-      for (int i = threadIdx.x; i < BN; i += GEMM_EPI_THREADS) {
-        s_par[i] = p.bias ? p.bias[i] : 0.f;
+    if (warp < PW) {  // weights only (constant over the chain): staged before the dependency wait
+      for (int i = threadIdx.x; i < BN; i += PT) {
+        s_bias[i] = p.bias ? p.bias[i] : 0.f;
         s_gamma[i] = p.gamma[i];
         s_beta[i] = p.beta[i];
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) GEMM_TRACE(1);
   pdl_launch_dependents();  // the next kernel may run its own prologue on SMs this grid has already left
   pdl_wait();               // everything the previous kernel wrote is visible from here on
+  if (threadIdx.x == 0) GEMM_TRACE(2);
 
-  if (warp == 8) {
-    // ===================== TMA producer =====================
+  if (warp == PW) {
+    // ===================== TMA producer (both CTAs of a pair) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * BN;
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+        const int m0 = (tile / tiles_n) * (GEMM_BM * CG) + (int)rank * GEMM_BM, n0 = (tile % tiles_n) * BN;
+        GEMM_TRACE(8 + 2 * it);
         if constexpr (LN) {
-          // the LN epilogue stages through the pipeline ring: do not refill it before that epilogue has drained
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+          // the LN epilogue stages through this CTA's ring: do not refill it before that epilogue has drained
+          mbar_wait(&ldone_bar[acc], acc_phase ^ 1u);
           if (++acc == ACC) acc = 0, acc_phase ^= 1u;
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, m0);
+          uint8_t* a_dst = sA + stage * Cfg::A_BYTES;
+          uint8_t* b_dst = sB + stage * Cfg::B_BYTES;
+          if constexpr (CG == 2) {
+            const uint32_t bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_2sm(a_dst, &tmA, bar, kb * BK, m0);
 #pragma unroll
-          for (int h = 0; h < (BN + 255) / 256; ++h)  // TMA box rows <= 256
-            tma_load_2d(sB + stage * Cfg::B_BYTES + h * 256 * GEMM_BK * 2, &tmB, &full_bar[stage], kb * GEMM_BK,
-                        n0 + h * 256);
+            for (int h = 0; h < NH; ++h)
+              tma_load_2d_2sm(b_dst + h * Cfg::BOX_B * BK * 2, &tmB, bar, kb * BK, n0 + h * UN + (int)rank * Cfg::BOX_B);
+            // (no arrive from the peer: a remote release-arrive blocks ~1500 cycles per k-block; the peer's bytes are
+            //  already accounted for by the leader's expect_tx, and its loads for the next use of a slot cannot be
+            //  issued before the multicast commit that follows the completion of this phase)
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
+#pragma unroll
+            for (int h = 0; h < NH; ++h)
+              tma_load_2d(b_dst + h * Cfg::BOX_B * BK * 2, &tmB, &full_bar[stage], kb * BK, n0 + h * UN);
+          }
           if (++stage == STAGES) stage = 0, phase ^= 1u;
         }
+        GEMM_TRACE(9 + 2 * it);
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr int UN = (BN > 256) ? 256 : BN;  // N per instruction
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, UN);
+  } else if (warp == PW + 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, UN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == 0) GEMM_TRACE(24 + 2 * it);
+          if (it == 1 && kb < 8) GEMM_TRACE(56 + kb);
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t ad = umma_desc_k_sw128(a_addr + k * 32);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = (BK == 64) ? umma_desc_k_sw128(a_addr + k * 32) : umma_desc_k_sw64(a_addr + k * 32);
 #pragma unroll
-            for (int h = 0; h < BN / UN; ++h) {
-              const uint64_t bd = umma_desc_k_sw128(b_addr + h * UN * GEMM_BK * 2 + k * 32);
-              umma_bf16(d_tmem + h * UN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            for (int h = 0; h < NH; ++h) {
+              const uint32_t bh = b_addr + h * Cfg::BOX_B * BK * 2 + k * 32;
+              const uint64_t bd = (BK == 64) ? umma_desc_k_sw128(bh) : umma_desc_k_sw64(bh);
+              if constexpr (CG == 2)
+                umma_bf16_2sm(d_tmem + h * UN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+              else
+                umma_bf16(d_tmem + h * UN, ad, bd, idesc, (kb | k) ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          // ring slot reusable (in both CTAs) once these MMAs have read it; last k-block publishes the accumulator
+          if constexpr (CG == 2) {
+            umma_commit_2sm(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          }
           if (++stage == STAGES) stage = 0, phase ^= 1u;
         }
+        GEMM_TRACE(25 + 2 * it);
         if (++acc == ACC) acc = 0, acc_phase ^= 1u;
       }
     }
   } else {
-    // ===================== epilogue (warps 0..7) =====================
-    const int lq = warp & 3, ch = warp >> 2;
+    // ===================== epilogue (warps 0..15, both CTAs) =====================
+    const int lq = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter
     const int row_in_tile = lq * 32 + lane;
-    constexpr int HALF = BN / 2;
-    constexpr int CHUNKS = HALF / 32;
+    constexpr int QW = BN / 4;       // columns per warp
+    constexpr int CHUNKS = QW / 32;  // 32-column TMEM chunks per warp
+    const uint32_t tempty_leader = (CG == 2) ? mapa_cluster(smem_u32(&tempty_bar[0]), 0) : 0u;
     uint32_t acc = 0, acc_phase = 0;
+    int staged_n0 = -1;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * BN;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+      const int m0 = (tile / tiles_n) * (GEMM_BM * CG) + (int)rank * GEMM_BM, n0 = (tile % tiles_n) * BN;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < p.M;
       const int grow0 = m0 + lq * 32;  // first global row of this warp
-      const float* s_bias = s_par;
       if constexpr (!LN) {
-        // this tile's bias slice -> buffer (it & 1).  One barrier per tile is enough: a warp that reaches it has
-        // finished tile it-1, so nobody still reads the buffer being overwritten for tile it+1.
-        float* sb = s_par + (it & 1) * BN;
-        for (int i = threadIdx.x; i < BN; i += GEMM_EPI_THREADS) sb[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        s_bias = sb;
+        if (n0 != staged_n0) {  // (re)stage the tile's bias slice; all 16 warps walk the same tile sequence
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          for (int i = threadIdx.x; i < BN; i += PT) s_bias[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          staged_n0 = n0;
+        }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lq * 32) << 16) + ch * HALF;
+      if (threadIdx.x == 0) GEMM_TRACE(40 + 2 * it);
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lq * 32) << 16) + cq * QW;
 
       if constexpr (LN) {
+        // ---------------- x = LayerNorm(x + acc + b), two passes over TMEM ----------------
         const uint32_t wst = smem_u32(s_stage) + warp * GEMM_LN_STG_WARP;
-        const uint32_t s_in0 = wst, s_outf = wst + 8192, s_outb = wst + 12288;
         const int crow = lane >> 3, cpiece = lane & 7;  // global side of the fp32 tiles: 4 rows x 8 pieces per pass
-        const float* xin = p.X + (size_t)ch * HALF;     // this warp's column half
-        auto prefetch = [&](int ck) {                   // residual chunk ck -> s_in[ck & 1], full 128-byte lines
-          const uint32_t dst = s_in0 + (ck & 1) * 4096;
+        const float* xin = p.X + (size_t)cq * QW;       // this warp's column quarter
+        auto prefetch = [&](int ck) {                   // residual chunk ck -> buffer ck & 1, full 128-byte lines
+          const uint32_t dst = wst + (ck & 1) * 4096;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = i * 4 + crow;
@@ -293,11 +390,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
           cp_async_commit();
         };
-        // ---- pass 1: v = acc + bias + residual -> back to TMEM; row sum ----
+        // ---- pass 1: y = acc + bias + residual -> back to TMEM; row sum and sum of squares ----
         prefetch(0);
-        float sum = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll 1
         for (int ck = 0; ck < CHUNKS; ++ck) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ck * 32, v);
           if (ck + 1 < CHUNKS) {
             prefetch(ck + 1);
             cp_async_wait<1>();
@@ -305,11 +404,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             cp_async_wait<0>();
           }
           __syncwarp();
-          uint32_t v[32];
-          tmem_ld32(taddr + ck * 32, v);
           tc_wait_ld();
-          const int c0 = ch * HALF + ck * 32;
-          const uint32_t src = s_in0 + (ck & 1) * 4096;
+          const int c0 = cq * QW + ck * 32;
+          const uint32_t src = wst + (ck & 1) * 4096;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint4 r4 = lds128(src + stg128_off(lane, j));
@@ -318,7 +415,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const float y1 = __uint_as_float(v[4 * j + 1]) + b4.y + __uint_as_float(r4.y);
             const float y2 = __uint_as_float(v[4 * j + 2]) + b4.z + __uint_as_float(r4.z);
             const float y3 = __uint_as_float(v[4 * j + 3]) + b4.w + __uint_as_float(r4.w);
-            sum += (y0 + y1) + (y2 + y3);
+            s0 += y0, s1 += y1, s2 += y2, s3 += y3;
+            q0 = fmaf(y0, y0, q0), q1 = fmaf(y1, y1, q1), q2 = fmaf(y2, y2, q2), q3 = fmaf(y3, y3, q3);
             v[4 * j] = __float_as_uint(y0), v[4 * j + 1] = __float_as_uint(y1);
             v[4 * j + 2] = __float_as_uint(y2), v[4 * j + 3] = __float_as_uint(y3);
           }
@@ -326,37 +424,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           __syncwarp();  // the buffer just read is refilled by the next iteration's prefetch
         }
         tc_wait_st();
-        s_red[ch * 128 + row_in_tile] = sum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float mean = (s_red[row_in_tile] + s_red[128 + row_in_tile]) / (float)p.N;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        // ---- pass 2: centred second moment (TMEM only) ----
-        float sq = 0.f;
-#pragma unroll 1
-        for (int ck = 0; ck < CHUNKS; ++ck) {
-          uint32_t v[32];
-          tmem_ld32(taddr + ck * 32, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = __uint_as_float(v[j]) - mean;
-            sq = fmaf(d, d, sq);
-          }
-        }
-        s_red[ch * 128 + row_in_tile] = sq;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float var = (s_red[row_in_tile] + s_red[128 + row_in_tile]) / (float)p.N;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        s_sum[cq * 128 + row_in_tile] = (s0 + s1) + (s2 + s3);
+        s_sq[cq * 128 + row_in_tile] = (q0 + q1) + (q2 + q3);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float inv_n = 1.0f / (float)p.N;
+        const float mean = ((s_sum[row_in_tile] + s_sum[128 + row_in_tile]) +
+                            (s_sum[256 + row_in_tile] + s_sum[384 + row_in_tile])) * inv_n;
+        const float ex2 = ((s_sq[row_in_tile] + s_sq[128 + row_in_tile]) +
+                           (s_sq[256 + row_in_tile] + s_sq[384 + row_in_tile])) * inv_n;
+        const float var = fmaxf(ex2 - mean * mean, 0.f);  // biased variance (F.layer_norm), fp32
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
-        // ---- pass 3: normalise + affine; fp32 residual stream and bf16 operand copy leave as full sectors ----
-        float* xo = p.X + (size_t)ch * HALF;
-        __nv_bfloat16* xbo = p.Xb + (size_t)ch * HALF;
+        // ---- pass 2: normalise + affine; fp32 residual stream and bf16 operand copy leave as full sectors ----
+        const uint32_t s_outf = wst, s_outb = wst + 4096;
+        float* xo = p.X + (size_t)cq * QW;
+        __nv_bfloat16* xbo = p.Xb + (size_t)cq * QW;
 #pragma unroll 1
         for (int ck = 0; ck < CHUNKS; ++ck) {
           uint32_t v[32];
           tmem_ld32(taddr + ck * 32, v);
           tc_wait_ld();
-          const int c0 = ch * HALF + ck * 32;
+          const int c0 = cq * QW + ck * 32;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 g4 = *reinterpret_cast<const float4*>(s_gamma + c0 + j * 4);
@@ -387,47 +474,88 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
           __syncwarp();
         }
-      } else if constexpr (epi_staged_bf16(EPI)) {
-        // ---- bias (+ activation) -> bf16, transposed through the warp-private staging tile ----
+      } else if constexpr (EPI == EPI_TOKEN_OUT) {
+        // ---- y = nan_to_num(acc + b) + pe[P0+tau] -> fp32 X and bf16 Xb at token row b*S + P0 + tau ----
         const uint32_t wst = smem_u32(s_stage) + warp * GEMM_STG_WARP;
+        const int prow = lane >> 2, pc = lane & 3;  // global side: 8 rows x 4 pieces (16 fp32 columns) per pass
 #pragma unroll 1
         for (int ck = 0; ck < CHUNKS; ++ck) {
-          const int cl = ch * HALF + ck * 32;  // column within the tile
-          const int cg = n0 + cl;              // global column
-          if (cg >= p.N) break;                // warp-uniform (N is a multiple of 64)
+          const int cl = cq * QW + ck * 32, cg = n0 + cl;
+          if (cg >= p.N) break;  // warp-uniform
           uint32_t v[32];
           tmem_ld32(taddr + ck * 32, v);
           tc_wait_ld();
-          float y[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cl + j * 4);
-            y[4 * j] = __uint_as_float(v[4 * j]) + b4.x, y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-            y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z, y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-          }
-          if constexpr (EPI == EPI_ADD_SILU_BF16) {
-            const float* ar = p.addmat + (size_t)(row_ok ? row : 0) * p.N + cg;
+          for (int hh = 0; hh < 2; ++hh) {  // 16 columns (64 B per row) per staging round
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 a4 = *reinterpret_cast<const float4*>(ar + j);
-              y[j] = silu(y[j] + a4.x), y[j + 1] = silu(y[j + 1] + a4.y);
-              y[j + 2] = silu(y[j + 2] + a4.z), y[j + 3] = silu(y[j + 3] + a4.w);
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cl + hh * 16 + j * 4);
+              sts128(wst + stg64_off(lane, j),
+                     make_uint4(__float_as_uint(nan_to_num(__uint_as_float(v[hh * 16 + 4 * j]) + b4.x)),
+                                __float_as_uint(nan_to_num(__uint_as_float(v[hh * 16 + 4 * j + 1]) + b4.y)),
+                                __float_as_uint(nan_to_num(__uint_as_float(v[hh * 16 + 4 * j + 2]) + b4.z)),
+                                __float_as_uint(nan_to_num(__uint_as_float(v[hh * 16 + 4 * j + 3]) + b4.w))));
             }
-          } else if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = gelu_erf(y[j]);
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + prow, gr = grow0 + r;
+              if (gr < p.M) {
+                const uint4 o = lds128(wst + stg64_off(r, pc));
+                const int b = gr / p.T, tau = gr - b * p.T;
+                const int col = cg + hh * 16 + pc * 4;
+                const float4 pe4 = *reinterpret_cast<const float4*>(p.pe + (size_t)(p.P0 + tau) * p.N + col);
+                const float y0 = __uint_as_float(o.x) + pe4.x, y1 = __uint_as_float(o.y) + pe4.y;
+                const float y2 = __uint_as_float(o.z) + pe4.z, y3 = __uint_as_float(o.w) + pe4.w;
+                const size_t orow = (size_t)b * p.S + p.P0 + tau;
+                *reinterpret_cast<float4*>(p.X + orow * p.N + col) = make_float4(y0, y1, y2, y3);
+                *reinterpret_cast<uint2*>(p.Xb + orow * p.N + col) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+              }
+            }
+            __syncwarp();
           }
+        }
+      } else if constexpr (epi_staged(EPI)) {
+        // ---- bias (+ activation) -> bf16, transposed through the warp-private staging tile ----
+        const uint32_t wst = smem_u32(s_stage) + warp * GEMM_STG_WARP;
+        const int prow = lane >> 2, pc = lane & 3;  // global side: 8 rows x 4 pieces (32 bf16 columns) per pass
+#pragma unroll 1
+        for (int ck = 0; ck < CHUNKS; ++ck) {
+          const int cl = cq * QW + ck * 32, cg = n0 + cl;
+          if (cg >= p.N) break;  // warp-uniform (N is a multiple of 32)
+          uint32_t v[32];
+          if (p.dbg & 4) continue;
+          tmem_ld32(taddr + ck * 32, v);
+          tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            sts128(wst + stg64_off(lane, j),
-                   make_uint4(pack_bf16x2(y[8 * j], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
-                              pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7])));
+          for (int j = 0; j < 4; ++j) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; e += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cl + j * 8 + e);
+              y[e] = __uint_as_float(v[8 * j + e]) + b4.x, y[e + 1] = __uint_as_float(v[8 * j + e + 1]) + b4.y;
+              y[e + 2] = __uint_as_float(v[8 * j + e + 2]) + b4.z, y[e + 3] = __uint_as_float(v[8 * j + e + 3]) + b4.w;
+            }
+            if constexpr (EPI == EPI_BIAS_SILU_BF16) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = silu(y[e]);
+            } else if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = gelu_erf(y[e]);
+            }
+            if (!(p.dbg & 2))
+              sts128(wst + stg64_off(lane, j), make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                           pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+            else if (y[0] == 1.2345f) p.out_bf16[0] = __float2bfloat16_rn(y[1] + y[2] + y[3] + y[4] + y[5] + y[6] + y[7]);
+          }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {  // 8 rows x 64 B per pass
-            const int r = i * 8 + (lane >> 2), pc = lane & 3;
-            const uint4 o = lds128(wst + stg64_off(r, pc));
-            if (grow0 + r < p.M) *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)(grow0 + r) * p.ld_bf16 + cg + pc * 8) = o;
+            const int r = i * 8 + prow;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (!(p.dbg & 2)) o = lds128(wst + stg64_off(r, pc));
+            if (grow0 + r < p.M && !(p.dbg & 1))
+              *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)(grow0 + r) * p.ld_bf16 + cg + pc * 8) = o;
           }
           __syncwarp();
         }
@@ -439,24 +567,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
           tmem_ld32(taddr + ck * 32, v);
           tc_wait_ld();
-          const int cl = ch * HALF + ck * 32;  // column within the tile
-          const int c0 = n0 + cl;              // global column of v[0]
+          const int cl = cq * QW + ck * 32;  // column within the tile
+          const int c0 = n0 + cl;            // global column of v[0]
           if constexpr (EPI == EPI_POSTERIOR) {
             const int b = row / p.S, s = row % p.S;
             if (row_ok && s >= p.P0 && c0 < p.nfeat) {
               const int tau = s - p.P0;
               const int t = p.t_ptr[b];
               const float k1 = p.c1[t], k2 = p.c2[t], sg = p.sigma[t];
+              const unsigned long long frame = (unsigned long long)b * p.T + tau;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int f = c0 + j;
-                if (f < p.nfeat) {
-                  const size_t e = ((size_t)b * p.nfeat + f) * p.T + tau;
-                  const float x0 = nan_to_num(__uint_as_float(v[j]) + s_bias[cl + j]);
-                  if (p.x0_out) p.x0_out[e] = x0;
-                  if (p.x_out) {
-                    const float eps = p.noise ? p.noise[e] : philox_normal(p.seed, (uint32_t)t, e);
-                    p.x_out[e] = (k1 * x0 + k2 * p.x_t[e]) + sg * eps;
+              for (int j = 0; j < 32; j += 4) {
+                float eps[4] = {0.f, 0.f, 0.f, 0.f};
+                if (p.x_out && !p.noise && c0 + j < p.nfeat)
+                  philox_normal4(p.seed, (uint32_t)t, frame, (uint32_t)((c0 + j) >> 2), eps);
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                  const int f = c0 + j + e4;
+                  if (f < p.nfeat) {
+                    const size_t e = ((size_t)b * p.nfeat + f) * p.T + tau;
+                    const float x0 = nan_to_num(__uint_as_float(v[j + e4]) + s_bias[cl + j + e4]);
+                    if (p.x0_out) p.x0_out[e] = x0;
+                    if (p.x_out) {
+                      const float n = p.noise ? p.noise[e] : eps[e4];
+                      p.x_out[e] = (k1 * x0 + k2 * p.x_t[e]) + sg * n;
+                    }
                   }
                 }
               }
@@ -472,35 +607,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                   p.x_out[base + f] = nan_to_num(p.x_t[base + f] + (__uint_as_float(v[j]) + s_bias[cl + j]));
               }
             }
-          } else if (row_ok && c0 < p.N) {
-            float y[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]) + s_bias[cl + j];
-            if constexpr (EPI == EPI_F32) {
+          } else {
+            static_assert(EPI == EPI_F32 || EPI == EPI_POSTERIOR || EPI == EPI_RESIDUAL_OUT, "unhandled epilogue");
+            if (row_ok && c0 < p.N) {
               float* o = p.out_f32 + (size_t)row * p.ld_f32 + c0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-            } else {
-              static_assert(EPI == EPI_F32 || EPI == EPI_TOKEN_OUT || EPI == EPI_POSTERIOR || EPI == EPI_RESIDUAL_OUT,
-                            "unhandled epilogue");
-              const int b = row / p.T, tau = row % p.T;
-              const size_t orow = (size_t)b * p.S + p.P0 + tau;
-              const float* per = p.pe + (size_t)(p.P0 + tau) * p.N + c0;
-              float* xo = p.X + orow * p.N + c0;
-              __nv_bfloat16* xb = p.Xb + orow * p.N + c0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-#pragma unroll
-                for (int e = 0; e < 8; e += 4) {
-                  const float4 pe4 = *reinterpret_cast<const float4*>(per + j + e);
-                  y[j + e + 0] = nan_to_num(y[j + e + 0]) + pe4.x, y[j + e + 1] = nan_to_num(y[j + e + 1]) + pe4.y;
-                  y[j + e + 2] = nan_to_num(y[j + e + 2]) + pe4.z, y[j + e + 3] = nan_to_num(y[j + e + 3]) + pe4.w;
-                  *reinterpret_cast<float4*>(xo + j + e) = make_float4(y[j + e], y[j + e + 1], y[j + e + 2], y[j + e + 3]);
-                }
-                *reinterpret_cast<uint4*>(xb + j) =
-                    make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
-                               pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
-              }
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(
+                    __uint_as_float(v[j]) + s_bias[cl + j], __uint_as_float(v[j + 1]) + s_bias[cl + j + 1],
+                    __uint_as_float(v[j + 2]) + s_bias[cl + j + 2], __uint_as_float(v[j + 3]) + s_bias[cl + j + 3]);
             }
           }
         }
@@ -508,15 +623,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       // accumulator stage drained -> hand it back to the MMA warp (and, for LN, the ring to the producer)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2)
+          mbar_arrive_cluster(tempty_leader + acc * 8);
+        else
+          mbar_arrive(&tempty_bar[acc]);
+        if constexpr (LN) mbar_arrive(&ldone_bar[acc]);
+      }
+      if (threadIdx.x == 0) GEMM_TRACE(41 + 2 * it);
       if (++acc == ACC) acc = 0, acc_phase ^= 1u;
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer may still signal our barriers / TMEM
+  if (threadIdx.x == 0) GEMM_TRACE(3);
+  if (warp == PW + 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CG == 2)
+      tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -524,34 +650,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 int num_sms();
 bool pdl_enabled();  // TAMF_PDL=0 turns programmatic dependent launch off (debug aid)
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 int configure_gemm() {  // once per process, outside any stream capture
-  TAMF_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       GemmSmem<BN, EPI>::BYTES));
+  TAMF_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GemmCfg<BN, EPI, CG>::SMEM_BYTES));
   return TAMF_OK;
 }
 
-template <int BN, int EPI>
+// tmA: A [M,K] with box {gemm_bk(BN,CG), 128}; tmB: W [N,K] with box {gemm_bk(BN,CG), gemm_b_box_rows(BN,CG)}.
+template <int BN, int EPI, int CG>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (epi_staged_bf16(EPI)) {
-    TAMF_REQUIRE(p.N % 64 == 0, TAMF_E_BADARG, "gemm: N must be a multiple of 64 for the bf16 epilogues");
+  const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((p.N + BN - 1) / BN);
+  const int slots = num_sms() / CG;
+  const int grid = (tiles < slots ? tiles : slots) * CG;
+  if (epi_staged(EPI) || EPI == EPI_F32) {
+    TAMF_REQUIRE(p.N % 32 == 0, TAMF_E_BADARG, "gemm: N must be a multiple of 32 for this epilogue");
   }
   if (EPI == EPI_RES_LN) {
     TAMF_REQUIRE(p.N == BN, TAMF_E_BADARG, "gemm: the LayerNorm epilogue needs the whole row in one tile (N == BN)");
   }
+  TAMF_REQUIRE(p.K % 8 == 0, TAMF_E_BADARG, "gemm: K must be a multiple of 8 (16-byte TMA rows)");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = GemmSmem<BN, EPI>::BYTES;
+  cfg.dynamicSmemBytes = GemmCfg<BN, EPI, CG>::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI>, tmA, tmB, p);
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, CG>, tmA, tmB, p);
   count_launch();
   if (e != cudaSuccess) {
     set_error(std::string("gemm launch failed: ") + cudaGetErrorString(e));

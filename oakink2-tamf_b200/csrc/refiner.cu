@@ -9,9 +9,10 @@
 // drop-in (tamf_b200/refine.py) sequences the calls.
 //
 // Frame-token embedding, folded like G's (exact in real arithmetic; double accumulation, rounded once):
-//   h = W1a (Wp x + bp) + W1b obj_tok + W1c (Wd dist + bd) + b1
-//     = [W1a Wp | W1c Wd] . [x ; dist]  +  (obj_tok . W1b^T + b1 + W1a bp + W1c bd)
-//   A0 [B*T, 960] bf16 = [x (99 -> 128) | dist (778 -> 832)]     one tcgen05 GEMM with K = 960, SiLU epilogue
+//   h = W1a (Wp x + bp) + W1b mean_o(Wo traj_o + bo) + W1c (Wd dist + bd) + b1
+//     = [W1a Wp | W1b Wo | W1c Wd] . [x ; mean_o(traj_o) ; dist]  +  (b1 + W1a bp + W1b bo + W1c bd)
+//   A0 [B*T, 960] bf16 = [x (99) | 0 | traj mean (9) | 0.. (-> 128) | dist (778 -> 832)]
+//                                                                 one tcgen05 GEMM with K = 960, SiLU epilogue
 //   tok[3+tau] = nan_to_num(silu(h) . W2^T + b2) + pe[3+tau]     second GEMM, token epilogue
 #include "encoder.cuh"
 #include "gemm.cuh"
@@ -23,10 +24,11 @@ constexpr int R_KX = 128;         // 99 pose features, zero padded
 constexpr int R_KD = 832;         // 778 distances, zero padded to a multiple of 64
 constexpr int R_K = R_KX + R_KD;  // 960
 constexpr int R_PREFIX = 3;
+constexpr int R_TRAJ_COL = 100;   // first column of mean_obj(obj_traj) inside the pose block
 
-// A0[r, :] = [x_in[r, 0:99], 0.., dist[r, 0:778], 0..] as bf16; one thread per pair of columns.
-__global__ void r_prep_kernel(const float* __restrict__ x_in, const float* __restrict__ dist,
-                              __nv_bfloat16* __restrict__ A0, int rows, int nfeat) {
+// A0[r, :] = [x_in[r, 0:99], 0, trajmean[r, 0:9], 0.., dist[r, 0:778], 0..] as bf16; one thread per pair of columns.
+__global__ void r_prep_kernel(const float* __restrict__ x_in, const float* __restrict__ trajmean,
+                              const float* __restrict__ dist, __nv_bfloat16* __restrict__ A0, int rows, int nfeat) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * (R_K / 2)) return;
   const int r = (int)(i / (R_K / 2)), c = (int)(i % (R_K / 2)) * 2;
@@ -35,7 +37,8 @@ __global__ void r_prep_kernel(const float* __restrict__ x_in, const float* __res
   for (int e = 0; e < 2; ++e) {
     const int cc = c + e;
     if (cc < R_KX)
-      v[e] = cc < nfeat ? x_in[(size_t)r * nfeat + cc] : 0.f;
+      v[e] = cc < nfeat ? x_in[(size_t)r * nfeat + cc]
+                        : ((cc >= R_TRAJ_COL && cc < R_TRAJ_COL + 9) ? trajmean[(size_t)r * 9 + (cc - R_TRAJ_COL)] : 0.f);
     else
       v[e] = (cc - R_KX) < R_NV ? dist[(size_t)r * R_NV + (cc - R_KX)] : 0.f;
   }
@@ -67,13 +70,13 @@ struct tamf_refiner {
   DevPool pool;
   EncoderStack enc;
   EncoderBuffers buf;
-  float *shape_w, *shape_b, *objemb_w, *objemb_b, *objtraj_w, *objtraj_b, *merge0_w, *merge_bias, *pe, *b_m2, *b_fin;
+  float *shape_w, *shape_b, *objemb_w, *objemb_b, *merge_bias, *pe, *b_m2, *b_fin;
   int pe_rows = 0;
   __nv_bfloat16 *wfold /*[d,960]*/, *wm2, *wfin;
   CUtensorMap tm_wfold, tm_wm2, tm_wfin, tm_A0, tm_H0;
   int B = 0, T = 0, S = 0, M = 0, Mf = 0;
   bool bound = false;
-  float *objhalf, *prefix, *objtok, *trajmean, *shapemean, *embmean;
+  float *prefix, *trajmean, *shapemean, *embmean;
   __nv_bfloat16 *A0, *H0;
 };
 
@@ -90,11 +93,12 @@ extern "C" int tamf_refiner_create(const tamf_cfg* cfg, const tamf_r_weights* w,
   if (rc) return rc;
   const int d = cfg->latent_dim, ff = cfg->ff_size, nf = cfg->input_dim;
   TAMF_REQUIRE(d == 256 || d == 512, TAMF_E_BADARG, "latent_dim must be 256 or 512");
-  TAMF_REQUIRE(nf > 0 && nf <= R_KX, TAMF_E_BADARG, "input_dim must be <= 128");
+  TAMF_REQUIRE(nf > 0 && nf < R_TRAJ_COL, TAMF_E_BADARG, "input_dim must be < 100");
   TAMF_REQUIRE(cfg->obj_input_dim == 9, TAMF_E_BADARG, "obj_input_dim must be 9");
   TAMF_REQUIRE(w->pe && w->pe_rows >= R_PREFIX + 1, TAMF_E_BADARG, "pe table missing");
-  TAMF_REQUIRE(w->pose_w && w->pose_b && w->dist_w && w->dist_b && w->merge0_w && w->merge0_b, TAMF_E_BADARG,
-               "null weight pointer");
+  TAMF_REQUIRE(w->pose_w && w->pose_b && w->dist_w && w->dist_b && w->merge0_w && w->merge0_b && w->objtraj_w &&
+                   w->objtraj_b,
+               TAMF_E_BADARG, "null weight pointer");
   tamf_refiner* h = new tamf_refiner();
   h->cfg = *cfg, h->d = d, h->ff = ff, h->nfeat = nf;
 #define TRY(x)                 \
@@ -107,16 +111,14 @@ extern "C" int tamf_refiner_create(const tamf_cfg* cfg, const tamf_r_weights* w,
   TRY(P.upload_f32(&h->shape_b, w->shape_b, d));
   TRY(P.upload_f32(&h->objemb_w, w->objemb_w, (size_t)d * cfg->obj_embed_dim));
   TRY(P.upload_f32(&h->objemb_b, w->objemb_b, d));
-  TRY(P.upload_f32(&h->objtraj_w, w->objtraj_w, (size_t)d * 9));
-  TRY(P.upload_f32(&h->objtraj_b, w->objtraj_b, d));
-  TRY(P.upload_f32(&h->merge0_w, w->merge0_w, (size_t)d * 3 * d));
   h->pe_rows = w->pe_rows;
   TRY(P.upload_f32(&h->pe, w->pe, (size_t)w->pe_rows * d));
   TRY(P.upload_f32(&h->b_m2, w->merge2_b, d));
   TRY(P.upload_f32(&h->b_fin, w->final_b, nf));
   {
-    // fold: Wfold[n, 0:99] = sum_j W1[n, j] Wp[j, :], Wfold[n, 128:906] = sum_j W1[n, 2d + j] Wd[j, :]
-    //       bias[n] = b1[n] + sum_j W1[n, j] bp[j] + sum_j W1[n, 2d + j] bd[j]
+    // fold: Wfold[n, 0:99] = sum_j W1[n, j] Wp[j, :], Wfold[n, 100:109] = sum_j W1[n, d + j] Wo[j, :],
+    //       Wfold[n, 128:906] = sum_j W1[n, 2d + j] Wd[j, :]
+    //       bias[n] = b1[n] + sum_j (W1[n, j] bp[j] + W1[n, d + j] bo[j] + W1[n, 2d + j] bd[j])
     std::vector<float> wf((size_t)d * R_K, 0.f), mb(d);
     std::vector<double> row(R_K);
     for (int n = 0; n < d; ++n) {
@@ -124,12 +126,14 @@ extern "C" int tamf_refiner_create(const tamf_cfg* cfg, const tamf_r_weights* w,
       double bacc = (double)w->merge0_b[n];
       const float* w1 = w->merge0_w + (size_t)n * 3 * d;
       for (int j = 0; j < d; ++j) {
-        const double a = (double)w1[j], c = (double)w1[2 * d + j];
+        const double a = (double)w1[j], o = (double)w1[d + j], c = (double)w1[2 * d + j];
         const float* pr = w->pose_w + (size_t)j * nf;
+        const float* tr = w->objtraj_w + (size_t)j * 9;
         const float* dr = w->dist_w + (size_t)j * R_NV;
         for (int k = 0; k < nf; ++k) row[k] += a * (double)pr[k];
+        for (int k = 0; k < 9; ++k) row[R_TRAJ_COL + k] += o * (double)tr[k];
         for (int k = 0; k < R_NV; ++k) row[R_KX + k] += c * (double)dr[k];
-        bacc += a * (double)w->pose_b[j] + c * (double)w->dist_b[j];
+        bacc += a * (double)w->pose_b[j] + o * (double)w->objtraj_b[j] + c * (double)w->dist_b[j];
       }
       for (int k = 0; k < R_K; ++k) wf[(size_t)n * R_K + k] = (float)row[k];
       mb[n] = (float)bacc;
@@ -139,13 +143,13 @@ extern "C" int tamf_refiner_create(const tamf_cfg* cfg, const tamf_r_weights* w,
   }
   TRY(P.upload_bf16(&h->wm2, w->merge2_w, d, d, d));
   TRY(P.upload_bf16(&h->wfin, w->final_w, nf, d, d));
-  TRY(make_tmap_2d_bf16(&h->tm_wfold, h->wfold, R_K, d, (uint64_t)R_K * 2, 64, 256));
-  TRY(make_tmap_2d_bf16(&h->tm_wm2, h->wm2, d, d, (uint64_t)d * 2, 64, 256));
-  TRY(make_tmap_2d_bf16(&h->tm_wfin, h->wfin, d, nf, (uint64_t)d * 2, 64, 128));
+  TRY(make_tmap_2d_bf16(&h->tm_wfold, h->wfold, R_K, d, (uint64_t)R_K * 2, 64, gemm_b_box_rows(256, 2)));
+  TRY(make_tmap_2d_bf16(&h->tm_wm2, h->wm2, d, d, (uint64_t)d * 2, 64, gemm_b_box_rows(256, 2)));
+  TRY(make_tmap_2d_bf16(&h->tm_wfin, h->wfin, d, nf, (uint64_t)d * 2, 64, gemm_b_box_rows(128, 2)));
   TRY(h->enc.upload(P, w->layers, d, ff, cfg->num_layers, cfg->num_heads));
-  TRY((configure_gemm<256, EPI_ADD_SILU_BF16>()));
-  TRY((configure_gemm<256, EPI_TOKEN_OUT>()));
-  TRY((configure_gemm<128, EPI_RESIDUAL_OUT>()));
+  TRY((configure_gemm<256, EPI_BIAS_SILU_BF16, 2>()));
+  TRY((configure_gemm<256, EPI_TOKEN_OUT, 2>()));
+  TRY((configure_gemm<128, EPI_RESIDUAL_OUT, 2>()));
   TRY(configure_encoder_kernels());
 #undef TRY
   *out = h;
@@ -167,9 +171,9 @@ static RWs r_layout(const tamf_refiner* h, int B, int T) {
       M * ff * 2,                            // 4 H
       Mf * R_K * 2,                          // 5 A0
       Mf * d * 2,                            // 6 H0
-      Mf * d * 4,                            // 7 objhalf
+      256,                                   // 7 (unused)
       (size_t)B * R_PREFIX * d * 4,          // 8 prefix
-      Mf * d * 4,                            // 9 objtok
+      256,                                   // 9 (unused)
       Mf * 9 * 4,                            // 10 trajmean
       (size_t)B * 16 * 4,                    // 11 shapemean
       (size_t)B * h->cfg.obj_embed_dim * 4,  // 12 embmean
@@ -208,9 +212,7 @@ extern "C" int tamf_refiner_bind(tamf_refiner* h, int B, int T, void* ws, size_t
   h->buf.Hb = (__nv_bfloat16*)(p + L.off[4]);
   h->A0 = (__nv_bfloat16*)(p + L.off[5]);
   h->H0 = (__nv_bfloat16*)(p + L.off[6]);
-  h->objhalf = (float*)(p + L.off[7]);
   h->prefix = (float*)(p + L.off[8]);
-  h->objtok = (float*)(p + L.off[9]);
   h->trajmean = (float*)(p + L.off[10]);
   h->shapemean = (float*)(p + L.off[11]);
   h->embmean = (float*)(p + L.off[12]);
@@ -248,33 +250,30 @@ extern "C" int tamf_refiner_forward(tamf_refiner* h, const float* sample_pose_re
     r_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->prefix, hand_side, h->pe, h->buf.X, h->buf.Xb, B, S, d);
     TAMF_LAUNCH_CHECK();
   }
-  if ((rc = linear_f32(h->trajmean, 9, h->objtraj_w, 9, h->objtraj_b, h->objtok, d, Mf, d, 9, 0, nullptr, 0, s)))
-    return rc;
-  if ((rc = linear_f32(h->objtok, d, h->merge0_w + d, 3 * d, h->merge_bias, h->objhalf, d, Mf, d, d, 0, nullptr, 0, s)))
-    return rc;
   // ---- frame tokens ----
   {
     const size_t n = (size_t)Mf * (R_K / 2);
-    r_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sample_pose_repr, h2o_dist, h->A0, Mf, h->nfeat);
+    r_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sample_pose_repr, h->trajmean, h2o_dist, h->A0, Mf,
+                                                              h->nfeat);
     TAMF_LAUNCH_CHECK();
   }
   {
     GemmParams p{};
-    p.M = Mf, p.N = d, p.K = R_K, p.bias = nullptr, p.addmat = h->objhalf, p.out_bf16 = h->H0, p.ld_bf16 = d;
-    if ((rc = launch_gemm<256, EPI_ADD_SILU_BF16>(h->tm_A0, h->tm_wfold, p, s))) return rc;
+    p.M = Mf, p.N = d, p.K = R_K, p.bias = h->merge_bias, p.out_bf16 = h->H0, p.ld_bf16 = d;
+    if ((rc = launch_gemm<256, EPI_BIAS_SILU_BF16, 2>(h->tm_A0, h->tm_wfold, p, s))) return rc;
   }
   {
     GemmParams p{};
     p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = R_PREFIX, p.X = h->buf.X,
     p.Xb = h->buf.Xb;
-    if ((rc = launch_gemm<256, EPI_TOKEN_OUT>(h->tm_H0, h->tm_wm2, p, s))) return rc;
+    if ((rc = launch_gemm<256, EPI_TOKEN_OUT, 2>(h->tm_H0, h->tm_wm2, p, s))) return rc;
   }
   if ((rc = enqueue_encoder(h->enc, h->buf, s, nullptr))) return rc;
   {
     GemmParams p{};
     p.M = M, p.N = h->nfeat, p.K = d, p.bias = h->b_fin, p.T = T, p.S = S, p.P0 = R_PREFIX, p.nfeat = h->nfeat;
     p.x_t = sample_pose_repr, p.x_out = refine_out;
-    if ((rc = launch_gemm<128, EPI_RESIDUAL_OUT>(h->buf.tm_Xb, h->tm_wfin, p, s))) return rc;
+    if ((rc = launch_gemm<128, EPI_RESIDUAL_OUT, 2>(h->buf.tm_Xb, h->tm_wfin, p, s))) return rc;
   }
   return TAMF_OK;
 }

@@ -20,7 +20,7 @@ SYMBOLS = [
     "tamf_denoiser_bind", "tamf_denoiser_set_cond", "tamf_denoiser_forward", "tamf_p_sample_step",
     "tamf_p_sample_chain", "tamf_p_sample_loop_host", "tamf_denoiser_profile_step", "tamf_kernel_launch_count", "tamf_philox_normal",
     "tamf_gemm_selftest", "tamf_refiner_create", "tamf_refiner_destroy", "tamf_refiner_workspace_bytes",
-    "tamf_refiner_bind", "tamf_refiner_forward", "tamf_mano_fk_select", "tamf_vertex_normals",
+    "tamf_refiner_bind", "tamf_refiner_forward", "tamf_mano_fk_select", "tamf_vertex_normals", "tamf_gemm_trace",
 ]
 
 
@@ -89,7 +89,7 @@ def lib() -> C.CDLL:
     L.tamf_p_sample_loop_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, u64, vp, vp]
     L.tamf_denoiser_profile_step.argtypes = [vp, vp, i32, u64, vp, i32, vp, vp]
     L.tamf_philox_normal.argtypes = [vp, sz, u64, C.c_uint32, vp]
-    L.tamf_gemm_selftest.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.tamf_gemm_selftest.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.tamf_refiner_create.argtypes = [C.POINTER(TamfCfg), C.POINTER(TamfRWeights), C.POINTER(vp)]
     L.tamf_refiner_destroy.argtypes = [vp]
     L.tamf_refiner_workspace_bytes.argtypes = [vp, i32, i32]
@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
     L.tamf_refiner_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.tamf_mano_fk_select.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp]
     L.tamf_vertex_normals.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.tamf_gemm_trace.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     _lib = L
     return L
 

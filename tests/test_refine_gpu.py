@@ -79,7 +79,9 @@ def test_vertex_normals_vs_oracle():
     ref = orc.vertex_normals(v, A["faces"])
     # accumulation order differs (shared-memory atomics): compare by value
     assert np.abs(n.cpu().numpy() - ref).max() < 2e-4
-    assert np.abs(np.linalg.norm(n.cpu().numpy(), axis=-1) - 1.0).max() < 1e-5
+    used = np.zeros(778, bool)
+    used[np.unique(A["faces"])] = True  # vertices no face references keep a zero normal (eps clamp)
+    assert np.abs(np.linalg.norm(n.cpu().numpy(), axis=-1)[:, used] - 1.0).max() < 1e-5
 
 
 def test_fk_select_matches_full():
