@@ -96,6 +96,26 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64
   return TAMF_OK;
 }
 
+int make_tmap_2d_f32(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes,
+                     uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  TAMF_REQUIRE(enc != nullptr, TAMF_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  TAMF_REQUIRE(aligned16(gptr) && (row_pitch_bytes % 16) == 0, TAMF_E_ALIGN, "TMA tensor must be 16-byte aligned");
+  TAMF_REQUIRE(box_rows <= 256, TAMF_E_BADARG, "TMA box must be <= 256 rows");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult " + std::to_string((int)r));
+    return TAMF_E_CUDA;
+  }
+  return TAMF_OK;
+}
+
 __global__ void philox_fill_kernel(float* out, size_t n, unsigned long long seed, uint32_t t) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = philox_normal(seed, t, i);
@@ -172,12 +192,18 @@ extern "C" int tamf_gemm_trace(int which, const uint16_t* a, const uint16_t* w, 
   GemmParams p{};
   p.M = M, p.N = N, p.K = K, p.bias = bias, p.trace = trace;
   p.dbg = getenv("TAMF_GEMM_DBG") ? atoi(getenv("TAMF_GEMM_DBG")) : 0;
+  CUtensorMap tmC, tmX;
   if (which == 2) {
+    if ((rc = make_tmap_2d_bf16(&tmC, out, N, M, (uint64_t)N * 2, 32, 32))) return rc;
+    if ((rc = make_tmap_2d_f32(&tmX, X, N, M, (uint64_t)N * 4, 32))) return rc;
+    p.tmC = &tmC, p.tmX = &tmX;
     p.X = X, p.Xb = (__nv_bfloat16*)out, p.gamma = bias, p.beta = bias;
     if ((rc = configure_gemm<512, EPI_RES_LN, 2>())) return rc;
     return launch_gemm<512, EPI_RES_LN, 2>(tmA, tmB, p, stream);
   }
   p.out_bf16 = (__nv_bfloat16*)out, p.ld_bf16 = N;
+  if ((rc = make_tmap_2d_bf16(&tmC, out, N, M, (uint64_t)N * 2, 64, 32))) return rc;
+  p.tmC = &tmC;
   if (which == 10) {  // single-CTA form of the in_proj shape (comparison only)
     if ((rc = make_tmap_2d_bf16(&tmB, w, K, N, (uint64_t)K * 2, 64, gemm_b_box_rows(256, 1)))) return rc;
     if ((rc = configure_gemm<256, EPI_BIAS_BF16, 1>())) return rc;

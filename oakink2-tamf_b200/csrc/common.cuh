@@ -53,6 +53,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency)
 int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner /*elements*/, uint64_t rows,
                       uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows);
+// fp32 row-major tensor, box [box_rows][32 floats] (128-byte rows, 128-byte swizzle): residual-stream tiles
+int make_tmap_2d_f32(CUtensorMap* out, const void* gptr, uint64_t inner /*elements*/, uint64_t rows,
+                     uint64_t row_pitch_bytes, uint32_t box_rows);
 
 // ---------------------------------------------------------------------------------------------
 // device side
@@ -119,6 +122,31 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_row)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_u32(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c_inner, int c_row) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c_inner), "r"(c_row)
+      : "memory");
+}
+// TMA store of a shared-memory tile (bulk async-group completion); rows / columns outside the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c_inner, int c_row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c_inner), "r"(c_row)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// ... have completed (writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -170,7 +198,9 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t ra
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // relaxed: a release at cluster scope compiles to MEMBAR.ALL.GPU (waits for every outstanding global access of the
+  // thread).  The only hand-off through this barrier is TMEM (reads completed by tcgen05.wait::ld + tcgen05.fence).
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of a CTA pair: data lands in the issuing CTA's shared memory, bytes are credited to `bar_cluster_addr`
 // (the leader CTA's mbarrier).

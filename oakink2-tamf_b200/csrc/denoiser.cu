@@ -127,7 +127,7 @@ struct tamf_denoiser {
   float *st_text, *st_shape, *st_traj, *st_emb;  // host-API staging
   int *st_side, *t_dev;
   __nv_bfloat16 *A0, *H0;
-  CUtensorMap tm_A0, tm_H0, tm_Xb_fin;
+  CUtensorMap tm_A0, tm_H0, tm_H0_st, tm_Xb_fin;
   // cached step graph
   cudaGraphExec_t graph_exec = nullptr;
   float* graph_x = nullptr;
@@ -156,7 +156,7 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, fl
   mark_event(marks, s);
   {  // embed-a
     GemmParams p{};
-    p.M = Mf, p.N = d, p.K = KPAD, p.bias = h->merge_bias, p.out_bf16 = h->H0, p.ld_bf16 = d;
+    p.M = Mf, p.N = d, p.K = KPAD, p.bias = h->merge_bias, p.out_bf16 = h->H0, p.ld_bf16 = d, p.tmC = &h->tm_H0_st;
     if ((rc = launch_gemm<256, EPI_BIAS_SILU_BF16, 2>(h->tm_A0, h->tm_wfold, p, s))) return rc;
     mark_event(marks, s);
   }
@@ -383,6 +383,7 @@ extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size
   h->tm_Xb_fin = h->buf.tm_Xb;
   if ((rc = make_tmap_2d_bf16(&h->tm_A0, h->A0, KPAD, h->Mf, (uint64_t)KPAD * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_H0, h->H0, d, h->Mf, (uint64_t)d * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&h->tm_H0_st, h->H0, d, h->Mf, (uint64_t)d * 2, 64, 32))) return rc;
   h->bound = true;
   h->cond_set = false;
   return TAMF_OK;

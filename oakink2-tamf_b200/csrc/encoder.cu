@@ -197,6 +197,10 @@ int EncoderBuffers::make_maps(int d, int ff) {
   if ((rc = make_tmap_2d_bf16(&tm_Xb, Xb, d, M, (uint64_t)d * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_ATT, ATT, d, M, (uint64_t)d * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_H, Hb, ff, M, (uint64_t)ff * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_QKV_st, QKV, 3 * d, M, (uint64_t)3 * d * 2, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_H_st, Hb, ff, M, (uint64_t)ff * 2, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_Xb_st, Xb, d, M, (uint64_t)d * 2, 32, 32))) return rc;
+  if ((rc = make_tmap_2d_f32(&tm_X, X, d, M, (uint64_t)d * 4, 32))) return rc;
   return TAMF_OK;
 }
 
@@ -219,7 +223,7 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     const LayerDev& w = enc.layers[l];
     {
       GemmParams p{};
-      p.M = M, p.N = 3 * d, p.K = d, p.bias = w.b_in, p.out_bf16 = buf.QKV, p.ld_bf16 = 3 * d;
+      p.M = M, p.N = 3 * d, p.K = d, p.bias = w.b_in, p.out_bf16 = buf.QKV, p.ld_bf16 = 3 * d, p.tmC = &buf.tm_QKV_st;
       if ((rc = launch_gemm<256, EPI_BIAS_BF16, 2>(buf.tm_Xb, w.tm_in, p, s))) return rc;
       mark_event(marks, s);
     }
@@ -232,6 +236,7 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     {
       GemmParams p{};
       p.M = M, p.N = d, p.K = d, p.bias = w.b_out, p.X = buf.X, p.Xb = buf.Xb, p.gamma = w.g1, p.beta = w.be1;
+      p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_X;
       rc = (d == 512) ? launch_gemm<512, EPI_RES_LN, 2>(buf.tm_ATT, w.tm_out, p, s)
                       : launch_gemm<256, EPI_RES_LN, 2>(buf.tm_ATT, w.tm_out, p, s);
       if (rc) return rc;
@@ -239,13 +244,14 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     }
     {
       GemmParams p{};
-      p.M = M, p.N = ff, p.K = d, p.bias = w.b1, p.out_bf16 = buf.Hb, p.ld_bf16 = ff;
+      p.M = M, p.N = ff, p.K = d, p.bias = w.b1, p.out_bf16 = buf.Hb, p.ld_bf16 = ff, p.tmC = &buf.tm_H_st;
       if ((rc = launch_gemm<256, EPI_BIAS_GELU_BF16, 2>(buf.tm_Xb, w.tm_w1, p, s))) return rc;
       mark_event(marks, s);
     }
     {
       GemmParams p{};
       p.M = M, p.N = d, p.K = ff, p.bias = w.b2, p.X = buf.X, p.Xb = buf.Xb, p.gamma = w.g2, p.beta = w.be2;
+      p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_X;
       rc = (d == 512) ? launch_gemm<512, EPI_RES_LN, 2>(buf.tm_H, w.tm_w2, p, s)
                       : launch_gemm<256, EPI_RES_LN, 2>(buf.tm_H, w.tm_w2, p, s);
       if (rc) return rc;

@@ -48,7 +48,9 @@ struct EncoderBuffers {
   __nv_bfloat16* QKV = nullptr;   // [M,3d]
   __nv_bfloat16* ATT = nullptr;   // [M,d]
   __nv_bfloat16* Hb = nullptr;    // [M,ff]
-  CUtensorMap tm_Xb, tm_ATT, tm_H;
+  CUtensorMap tm_Xb, tm_ATT, tm_H;              // GEMM A-operand loads, box {64, 128}
+  CUtensorMap tm_QKV_st, tm_H_st;               // bf16 epilogue stores, box {64, 32}
+  CUtensorMap tm_Xb_st, tm_X;                   // LayerNorm epilogue: Xb store {32, 32} bf16; X load + store {32, 32} fp32
   int make_maps(int d, int ff);
 };
 

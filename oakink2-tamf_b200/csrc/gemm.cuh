@@ -75,6 +75,11 @@ struct GemmParams {
   const float *c1, *c2, *sigma;  // [num_steps] fp32
   unsigned long long seed;
   int nfeat;
+  // host pointers to the TMA-store maps (copied into kernel parameters by launch_gemm):
+  //   tmC: bf16 output [M,N], box {64 cols, 32 rows} (bias/GELU/SiLU epilogues) | Xb [M,N], box {32, 32} (LN)
+  //   tmX: fp32 residual stream X [M,N], box {32, 32}, loaded (residual) and stored (normalised) by the LN epilogue
+  const CUtensorMap* tmC;
+  const CUtensorMap* tmX;
   // debug only (tools/gemm_trace.py): per-CTA event timestamps, [grid][GEMM_TRACE_SLOTS] clock64 values; null in product
   long long* trace;
   int dbg;  // debug only: 1 skip global stores, 2 skip staging, 4 skip the whole epilogue body (bf16 epilogues)
@@ -85,12 +90,14 @@ constexpr int GEMM_BM = 128;                           // accumulator rows per C
 constexpr int GEMM_EPI_WARPS = 16;
 constexpr int GEMM_EPI_THREADS = GEMM_EPI_WARPS * 32;  // 512
 constexpr int GEMM_THREADS = GEMM_EPI_THREADS + 64;    // + TMA producer warp + MMA issuer warp
-constexpr int GEMM_CTRL_BYTES = 256;                   // mbarriers + TMEM slot
-constexpr int GEMM_STG_WARP = 2048;                    // warp-private staging tile, 32 rows x 64 B
-constexpr int GEMM_LN_STG_WARP = 8192;                 // LN: 2 x 4 KB residual in (pass 1) = 4 KB fp32 + 2 KB bf16 out (pass 2)
+constexpr int GEMM_CTRL_BYTES = 512;                   // mbarriers + TMEM slot | 16 x 2 residual-tile mbarriers (LN)
+constexpr int GEMM_STG_WARP = 4096;                    // warp-private staging tile, 32 rows x 128 B (TMA-store source)
+constexpr int GEMM_LN_STG_WARP = 12288;                // LN: 2 x 4 KB residual tiles in (pass 1) | 2 x (4 KB fp32 + 2 KB bf16) out (pass 2)
 constexpr int GEMM_SMEM_MAX = 232448;                  // 227 KB
 
 constexpr bool epi_is_ln(int e) { return e == EPI_RES_LN; }
+// bf16 [M,N] outputs that leave the SM as TMA stores of warp-private 32 x 64 staging tiles
+constexpr bool epi_tma_bf16(int e) { return e == EPI_BIAS_BF16 || e == EPI_BIAS_GELU_BF16 || e == EPI_BIAS_SILU_BF16; }
 constexpr bool epi_staged(int e) {
   return e == EPI_BIAS_BF16 || e == EPI_BIAS_GELU_BF16 || e == EPI_BIAS_SILU_BF16 || e == EPI_TOKEN_OUT;
 }
@@ -116,13 +123,14 @@ struct GemmCfg {
   static constexpr int RING_BUDGET = GEMM_SMEM_MAX - 1024 - GEMM_CTRL_BYTES - PARAM_BYTES - STG_BYTES;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  // Shared-memory map: [pipeline ring | control | parameters | staging].  LN epilogues stage through the drained
+  // Shared-memory map: [pipeline ring | staging | control | parameters].  LN epilogues stage through the drained
   // ring (one tile in flight); the other staged epilogues own a staging area (they overlap the next mainloop).
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + PIPE_BYTES + GEMM_CTRL_BYTES + PARAM_BYTES + STG_BYTES;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(PIPE_BYTES % 1024 == 0, "staging tiles behind the ring must stay 1024-byte aligned");
   static_assert(!epi_is_ln(EPI) || PIPE_BYTES >= GEMM_EPI_WARPS * GEMM_LN_STG_WARP, "LN staging must fit in the ring");
   static_assert(SMEM_BYTES <= GEMM_SMEM_MAX, "shared memory budget (227 KB) exceeded");
-  static_assert((2 * STAGES + 3 * ACC_STAGES) * 8 + 8 <= GEMM_CTRL_BYTES, "control block too small");
+  static_assert((2 * STAGES + 3 * ACC_STAGES) * 8 + 8 <= 256, "control block too small");
 };
 
 __device__ __forceinline__ float fast_rcp(float x) {
@@ -135,19 +143,24 @@ __device__ __forceinline__ float fast_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// GELU with the exact (erf) form of F.gelu, the reference's activation="gelu":  0.5 x (1 + erf(x / sqrt 2)).
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32-exact for a bf16 result) in 15 instructions:
-//   t = 1 / (1 + p |x| / sqrt 2),  q = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-x^2 / 2)  ( = erfc(|x| / sqrt 2) )
-//   gelu = x - 0.5 x q  (x >= 0),   0.5 x q  (x < 0)
+// GELU with the exact (erf) form of F.gelu, the reference's activation="gelu":  x Phi(x),  Phi(x) = 0.5 (1 + erf(x / sqrt 2)).
+// Phi(x) - 0.5 = x P(x^2) on |x| <= 4 (degree-8 weighted least-squares fit, |error of x Phi| <= 1.7e-5 in fp32 Horner form,
+// i.e. below half a bf16 ulp of any |y| >= 0.01); outside, Phi is held at Phi(+-4) (1 - 3.2e-5 / 3.2e-5).  13 FMA/ALU
+// instructions and no MUFU: the epilogue of linear1 must keep pace with a 128 x 256 x 512 MMA tile (4096 cycles for
+// 32768 elements per SM), which two MUFU operations per element (16/clk/SM) alone would already exceed.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float t = fast_rcp(fmaf(0.23164189f, fabsf(x), 1.0f));
-  float q = fmaf(1.061405429f, t, -1.453152027f);
-  q = fmaf(q, t, 1.421413741f);
-  q = fmaf(q, t, -0.284496736f);
-  q = fmaf(q, t, 0.254829592f);
-  q = q * t * fast_ex2(x * x * -0.72134752f);
-  const float h = 0.5f * x * q;
-  return x >= 0.f ? x - h : h;
+  const float xc = fminf(fmaxf(x, -4.0f), 4.0f);
+  const float s = xc * xc;
+  float p = 6.699732416e-11f;
+  p = fmaf(p, s, -6.040797371e-09f);
+  p = fmaf(p, s, 2.434135770e-07f);
+  p = fmaf(p, s, -5.851926342e-06f);
+  p = fmaf(p, s, 9.488355446e-05f);
+  p = fmaf(p, s, -1.112714840e-03f);
+  p = fmaf(p, s, 9.816041892e-03f);
+  p = fmaf(p, s, -6.632534796e-02f);
+  p = fmaf(p, s, 3.988829340e-01f);
+  return x * fmaf(xc, p, 0.5f);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
@@ -189,7 +202,8 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
 
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
   using Cfg = GemmCfg<BN, EPI, CG>;
   constexpr int STAGES = Cfg::STAGES, ACC = Cfg::ACC_STAGES, BK = Cfg::BK, UN = Cfg::UN, NH = Cfg::NH;
   constexpr bool LN = epi_is_ln(EPI);
@@ -200,19 +214,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint8_t* smem = smem_raw + pad;
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* ctrl = smem + Cfg::PIPE_BYTES;
+  uint8_t* ctrl = smem + Cfg::PIPE_BYTES + Cfg::STG_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);  // [STAGES]  (CG = 2: the leader's copy is the live one)
   uint64_t* empty_bar = full_bar + STAGES;                  // [STAGES]
   uint64_t* tfull_bar = empty_bar + STAGES;                 // [ACC]
   uint64_t* tempty_bar = tfull_bar + ACC;                   // [ACC]     (CG = 2: the leader's copy is the live one)
   uint64_t* ldone_bar = tempty_bar + ACC;                   // [ACC]     LN only: THIS CTA's epilogue has left the ring
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ldone_bar + ACC);
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(ctrl + 256);  // [16][2]  LN only: residual tile landed (per warp, per buffer)
   float* s_bias = reinterpret_cast<float*>(ctrl + GEMM_CTRL_BYTES);
   float* s_gamma = s_bias + BN;     // LN only
   float* s_beta = s_bias + 2 * BN;  // LN only
   float* s_sum = s_bias + 3 * BN;   // LN only: [4][128] partial row sums, then [4][128] partial sums of squares
   float* s_sq = s_sum + 4 * 128;
-  uint8_t* s_stage = LN ? smem : (ctrl + GEMM_CTRL_BYTES + Cfg::PARAM_BYTES);
+  uint8_t* s_stage = LN ? smem : (smem + Cfg::PIPE_BYTES);  // 1024-byte aligned (swizzled TMA tiles)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader
@@ -234,6 +249,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], PW * CG);  // one elected lane per epilogue warp (of both CTAs)
       mbar_init(&ldone_bar[a], PW);
+    }
+    if constexpr (LN) {
+      for (int i = 0; i < 2 * PW; ++i) mbar_init(&rbar[i], 1);
+    }
+    if constexpr (LN || epi_tma_bf16(EPI)) {
+      tma_prefetch_desc(&tmC);
+      if constexpr (LN) tma_prefetch_desc(&tmX);
     }
     fence_mbar_init();
   }
@@ -355,6 +377,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     constexpr int CHUNKS = QW / 32;  // 32-column TMEM chunks per warp
     const uint32_t tempty_leader = (CG == 2) ? mapa_cluster(smem_u32(&tempty_bar[0]), 0) : 0u;
     uint32_t acc = 0, acc_phase = 0;
+    uint32_t rpar = 0;  // LN: parity bits of the two residual-tile mbarriers of this warp
     int staged_n0 = -1;
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
@@ -375,37 +398,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (threadIdx.x == 0) GEMM_TRACE(40 + 2 * it);
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lq * 32) << 16) + cq * QW;
 
+      // hand the drained accumulator stage back to the MMA warp
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2)
+            mbar_arrive_cluster(tempty_leader + acc * 8);
+          else
+            mbar_arrive(&tempty_bar[acc]);
+        }
+      };
       if constexpr (LN) {
         // ---------------- x = LayerNorm(x + acc + b), two passes over TMEM ----------------
+        // Warp-private 12 KB region of the drained ring: pass 1 receives the fp32 residual as TMA tiles
+        // [32 rows x 32 cols] (two buffers, two tiles in flight); pass 2 stages the normalised fp32 / bf16 tiles
+        // (two sets) and hands them to TMA stores, so no LSU global access is left in the epilogue.
         const uint32_t wst = smem_u32(s_stage) + warp * GEMM_LN_STG_WARP;
-        const int crow = lane >> 3, cpiece = lane & 7;  // global side of the fp32 tiles: 4 rows x 8 pieces per pass
-        const float* xin = p.X + (size_t)cq * QW;       // this warp's column quarter
-        auto prefetch = [&](int ck) {                   // residual chunk ck -> buffer ck & 1, full 128-byte lines
-          const uint32_t dst = wst + (ck & 1) * 4096;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + crow;
-            const int gr = min(grow0 + r, p.M - 1);  // rows past M read a valid row; they are never stored
-            cp_async_16(dst + stg128_off(r, cpiece), xin + (size_t)gr * p.N + ck * 32 + cpiece * 4);
-          }
-          cp_async_commit();
+        uint64_t* rb = rbar + warp * 2;
+        const int ccol0 = cq * QW;  // first column of this warp's quarter
+        auto prefetch = [&](int ck) {  // lane 0: residual tile ck -> buffer ck & 1 (rows past M arrive as zeros)
+          mbar_arrive_expect_tx(&rb[ck & 1], 4096);
+          tma_load_2d_u32(wst + (ck & 1) * 4096, &tmX, smem_u32(&rb[ck & 1]), ccol0 + ck * 32, grow0);
         };
+        if (lane == 0) {
+          prefetch(0);
+          if (CHUNKS > 1) prefetch(1);
+        }
         // ---- pass 1: y = acc + bias + residual -> back to TMEM; row sum and sum of squares ----
-        prefetch(0);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll 1
         for (int ck = 0; ck < CHUNKS; ++ck) {
           uint32_t v[32];
           tmem_ld32(taddr + ck * 32, v);
-          if (ck + 1 < CHUNKS) {
-            prefetch(ck + 1);
-            cp_async_wait<1>();
-          } else {
-            cp_async_wait<0>();
-          }
-          __syncwarp();
+          mbar_wait(&rb[ck & 1], (rpar >> (ck & 1)) & 1u);
+          rpar ^= 1u << (ck & 1);
           tc_wait_ld();
-          const int c0 = cq * QW + ck * 32;
+          const int c0 = ccol0 + ck * 32;
           const uint32_t src = wst + (ck & 1) * 4096;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -421,12 +450,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             v[4 * j + 2] = __float_as_uint(y2), v[4 * j + 3] = __float_as_uint(y3);
           }
           tmem_st32(taddr + ck * 32, v);
-          __syncwarp();  // the buffer just read is refilled by the next iteration's prefetch
+          __syncwarp();  // every lane has read this residual buffer: it may be refilled
+          if (lane == 0 && ck + 2 < CHUNKS) prefetch(ck + 2);
         }
         tc_wait_st();
+        if (threadIdx.x == 0) GEMM_TRACE(4);
         s_sum[cq * 128 + row_in_tile] = (s0 + s1) + (s2 + s3);
         s_sq[cq * 128 + row_in_tile] = (q0 + q1) + (q2 + q3);
         asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (threadIdx.x == 0) GEMM_TRACE(5);
         const float inv_n = 1.0f / (float)p.N;
         const float mean = ((s_sum[row_in_tile] + s_sum[128 + row_in_tile]) +
                             (s_sum[256 + row_in_tile] + s_sum[384 + row_in_tile])) * inv_n;
@@ -434,24 +466,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                            (s_sq[256 + row_in_tile] + s_sq[384 + row_in_tile])) * inv_n;
         const float var = fmaxf(ex2 - mean * mean, 0.f);  // biased variance (F.layer_norm), fp32
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
-        // ---- pass 2: normalise + affine; fp32 residual stream and bf16 operand copy leave as full sectors ----
-        const uint32_t s_outf = wst, s_outb = wst + 4096;
-        float* xo = p.X + (size_t)cq * QW;
-        __nv_bfloat16* xbo = p.Xb + (size_t)cq * QW;
+        const float nmr = -mean * rstd;
+        // ---- pass 2: normalise + affine -> staging set ck & 1 -> TMA stores of the fp32 and bf16 tiles ----
 #pragma unroll 1
         for (int ck = 0; ck < CHUNKS; ++ck) {
           uint32_t v[32];
           tmem_ld32(taddr + ck * 32, v);
           tc_wait_ld();
-          const int c0 = cq * QW + ck * 32;
+          if (ck == CHUNKS - 1) release_acc();  // last TMEM read of this tile
+          if (ck >= 2) {  // the stores of chunk ck - 2 must have finished reading this staging set
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+          const int c0 = ccol0 + ck * 32;
+          const uint32_t s_outf = wst + (ck & 1) * 6144, s_outb = s_outf + 4096;
+          if (p.dbg & 2) continue;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 g4 = *reinterpret_cast<const float4*>(s_gamma + c0 + j * 4);
             const float4 be4 = *reinterpret_cast<const float4*>(s_beta + c0 + j * 4);
-            const float y0 = (__uint_as_float(v[4 * j]) - mean) * rstd * g4.x + be4.x;
-            const float y1 = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * g4.y + be4.y;
-            const float y2 = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * g4.z + be4.z;
-            const float y3 = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * g4.w + be4.w;
+            const float y0 = fmaf(fmaf(__uint_as_float(v[4 * j]), rstd, nmr), g4.x, be4.x);
+            const float y1 = fmaf(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmr), g4.y, be4.y);
+            const float y2 = fmaf(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmr), g4.z, be4.z);
+            const float y3 = fmaf(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmr), g4.w, be4.w);
             sts128(s_outf + stg128_off(lane, j),
                    make_uint4(__float_as_uint(y0), __float_as_uint(y1), __float_as_uint(y2), __float_as_uint(y3)));
             v[2 * j] = pack_bf16x2(y0, y1), v[2 * j + 1] = pack_bf16x2(y2, y3);
@@ -459,21 +496,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128(s_outb + stg64_off(lane, j), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          fence_proxy_async_smem();
           __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {  // fp32: 4 rows x 128 B per pass
-            const int r = i * 4 + crow;
-            const uint4 o = lds128(s_outf + stg128_off(r, cpiece));
-            if (grow0 + r < p.M) *reinterpret_cast<uint4*>(xo + (size_t)(grow0 + r) * p.N + ck * 32 + cpiece * 4) = o;
+          if (lane == 0 && !(p.dbg & 1)) {
+            if (!(p.dbg & 4)) tma_store_2d(&tmX, s_outf, c0, grow0);  // rows past M are clipped by the tensor map
+            if (!(p.dbg & 8)) tma_store_2d(&tmC, s_outb, c0, grow0);
+            bulk_commit();
           }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {  // bf16: 8 rows x 64 B per pass
-            const int r = i * 8 + (lane >> 2), pc = lane & 3;
-            const uint4 o = lds128(s_outb + stg64_off(r, pc));
-            if (grow0 + r < p.M) *reinterpret_cast<uint4*>(xbo + (size_t)(grow0 + r) * p.N + ck * 32 + pc * 8) = o;
-          }
-          __syncwarp();
         }
+        if (lane == 0) {
+          bulk_wait_read<0>();          // staging lives in the ring: the producer may refill it only now
+          mbar_arrive(&ldone_bar[acc]);
+        }
+        if (threadIdx.x == 0) GEMM_TRACE(6);
       } else if constexpr (EPI == EPI_TOKEN_OUT) {
         // ---- y = nan_to_num(acc + b) + pe[P0+tau] -> fp32 X and bf16 Xb at token row b*S + P0 + tau ----
         const uint32_t wst = smem_u32(s_stage) + warp * GEMM_STG_WARP;
@@ -515,26 +550,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             __syncwarp();
           }
         }
-      } else if constexpr (epi_staged(EPI)) {
-        // ---- bias (+ activation) -> bf16, transposed through the warp-private staging tile ----
+      } else if constexpr (epi_tma_bf16(EPI)) {
+        // ---- bias (+ activation) -> bf16: the warp's 32 x 64 slab is staged as one 128-byte-swizzled tile and
+        //      leaves the SM as a single TMA store; TMEM is released as soon as the accumulator is in registers ----
+        static_assert(BN == 256, "the TMA-store bf16 epilogue is written for 64-column warp slabs (BN = 256)");
         const uint32_t wst = smem_u32(s_stage) + warp * GEMM_STG_WARP;
-        const int prow = lane >> 2, pc = lane & 3;  // global side: 8 rows x 4 pieces (32 bf16 columns) per pass
-#pragma unroll 1
-        for (int ck = 0; ck < CHUNKS; ++ck) {
-          const int cl = cq * QW + ck * 32, cg = n0 + cl;
-          if (cg >= p.N) break;  // warp-uniform (N is a multiple of 32)
-          uint32_t v[32];
-          if (p.dbg & 4) continue;
-          tmem_ld32(taddr + ck * 32, v);
-          tc_wait_ld();
+        const int cl = cq * QW;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32, v1);
+        tc_wait_ld();
+        release_acc();
+        if (lane == 0) bulk_wait_read<0>();  // the previous tile's store has finished reading the staging tile
+        __syncwarp();
+        if (n0 + cl < p.N) {  // warp-uniform (N is a multiple of 64)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 8; ++j) {
             float y[8];
 #pragma unroll
             for (int e = 0; e < 8; e += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cl + j * 8 + e);
-              y[e] = __uint_as_float(v[8 * j + e]) + b4.x, y[e + 1] = __uint_as_float(v[8 * j + e + 1]) + b4.y;
-              y[e + 2] = __uint_as_float(v[8 * j + e + 2]) + b4.z, y[e + 3] = __uint_as_float(v[8 * j + e + 3]) + b4.w;
+              const uint32_t* v = (j < 4) ? (v0 + j * 8 + e) : (v1 + (j - 4) * 8 + e);
+              y[e] = __uint_as_float(v[0]) + b4.x, y[e + 1] = __uint_as_float(v[1]) + b4.y;
+              y[e + 2] = __uint_as_float(v[2]) + b4.z, y[e + 3] = __uint_as_float(v[3]) + b4.w;
             }
             if constexpr (EPI == EPI_BIAS_SILU_BF16) {
 #pragma unroll
@@ -543,21 +581,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
               for (int e = 0; e < 8; ++e) y[e] = gelu_erf(y[e]);
             }
-            if (!(p.dbg & 2))
-              sts128(wst + stg64_off(lane, j), make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                           pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
-            else if (y[0] == 1.2345f) p.out_bf16[0] = __float2bfloat16_rn(y[1] + y[2] + y[3] + y[4] + y[5] + y[6] + y[7]);
+            sts128(wst + stg128_off(lane, j), make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                         pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
           }
+          fence_proxy_async_smem();
           __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {  // 8 rows x 64 B per pass
-            const int r = i * 8 + prow;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (!(p.dbg & 2)) o = lds128(wst + stg64_off(r, pc));
-            if (grow0 + r < p.M && !(p.dbg & 1))
-              *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)(grow0 + r) * p.ld_bf16 + cg + pc * 8) = o;
+          if (lane == 0) {
+            tma_store_2d(&tmC, wst, n0 + cl, grow0);  // rows past M / columns past N are clipped
+            bulk_commit();
           }
-          __syncwarp();
         }
       } else {
         // ---- small-N / remapped epilogues: row-per-thread stores ----
@@ -620,19 +652,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
         }
       }
-      // accumulator stage drained -> hand it back to the MMA warp (and, for LN, the ring to the producer)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2)
-          mbar_arrive_cluster(tempty_leader + acc * 8);
-        else
-          mbar_arrive(&tempty_bar[acc]);
-        if constexpr (LN) mbar_arrive(&ldone_bar[acc]);
-      }
+      // accumulator stage drained -> hand it back to the MMA warp (LN and the TMA-store epilogues did so already)
+      if constexpr (!LN && !epi_tma_bf16(EPI)) release_acc();
       if (threadIdx.x == 0) GEMM_TRACE(41 + 2 * it);
       if (++acc == ACC) acc = 0, acc_phase ^= 1u;
     }
+    if constexpr (LN || epi_tma_bf16(EPI)) {
+      if (lane == 0) bulk_wait<0>();  // this thread's TMA stores have been performed before the CTA retires
+    }
+    (void)rpar;
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer may still signal our barriers / TMEM
@@ -689,7 +717,15 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, CG>, tmA, tmB, p);
+  if (epi_is_ln(EPI)) {
+    TAMF_REQUIRE(p.tmC && p.tmX, TAMF_E_BADARG, "gemm: the LayerNorm epilogue needs the Xb / X tensor maps");
+  } else if (epi_tma_bf16(EPI)) {
+    TAMF_REQUIRE(p.tmC, TAMF_E_BADARG, "gemm: the bf16 epilogues need the output tensor map");
+    TAMF_REQUIRE(p.N % 64 == 0, TAMF_E_BADARG, "gemm: N must be a multiple of 64 for the TMA-store epilogue");
+  }
+  const CUtensorMap& tmC = p.tmC ? *p.tmC : tmA;  // unused maps are passed as copies of tmA
+  const CUtensorMap& tmX = p.tmX ? *p.tmX : tmA;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, CG>, tmA, tmB, tmC, tmX, p);
   count_launch();
   if (e != cudaSuccess) {
     set_error(std::string("gemm launch failed: ") + cudaGetErrorString(e));

@@ -73,7 +73,7 @@ struct tamf_refiner {
   float *shape_w, *shape_b, *objemb_w, *objemb_b, *merge_bias, *pe, *b_m2, *b_fin;
   int pe_rows = 0;
   __nv_bfloat16 *wfold /*[d,960]*/, *wm2, *wfin;
-  CUtensorMap tm_wfold, tm_wm2, tm_wfin, tm_A0, tm_H0;
+  CUtensorMap tm_wfold, tm_wm2, tm_wfin, tm_A0, tm_H0, tm_H0_st;
   int B = 0, T = 0, S = 0, M = 0, Mf = 0;
   bool bound = false;
   float *prefix, *trajmean, *shapemean, *embmean;
@@ -220,6 +220,7 @@ extern "C" int tamf_refiner_bind(tamf_refiner* h, int B, int T, void* ws, size_t
   if ((rc = h->buf.make_maps(h->d, h->ff))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_A0, h->A0, R_K, h->Mf, (uint64_t)R_K * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_H0, h->H0, h->d, h->Mf, (uint64_t)h->d * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&h->tm_H0_st, h->H0, h->d, h->Mf, (uint64_t)h->d * 2, 64, 32))) return rc;
   h->bound = true;
   return TAMF_OK;
 }
@@ -259,7 +260,7 @@ extern "C" int tamf_refiner_forward(tamf_refiner* h, const float* sample_pose_re
   }
   {
     GemmParams p{};
-    p.M = Mf, p.N = d, p.K = R_K, p.bias = h->merge_bias, p.out_bf16 = h->H0, p.ld_bf16 = d;
+    p.M = Mf, p.N = d, p.K = R_K, p.bias = h->merge_bias, p.out_bf16 = h->H0, p.ld_bf16 = d, p.tmC = &h->tm_H0_st;
     if ((rc = launch_gemm<256, EPI_BIAS_SILU_BF16, 2>(h->tm_A0, h->tm_wfold, p, s))) return rc;
   }
   {

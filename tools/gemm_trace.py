@@ -34,7 +34,7 @@ for cta in (0, 1, 73, 147):
         continue
     z = r[0]
     f = lambda v: "   -  " if v == 0 else f"{(v - z):6d}"
-    print(f"CTA {cta}: setup_done {f(r[1])} pdl_wait_done {f(r[2])} end {f(r[3])}")
+    print(f"CTA {cta}: setup_done {f(r[1])} pdl_wait_done {f(r[2])} end {f(r[3])}  ln: pass1_done {f(r[4])} stats_bar {f(r[5])} pass2_done {f(r[6])}")
     for it in range(8):
         if r[8 + 2 * it] == 0:
             break
