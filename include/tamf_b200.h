@@ -226,6 +226,12 @@ int tamf_philox_normal(float* out, size_t n, uint64_t seed, uint32_t t, void* st
 int tamf_gemm_selftest(const uint16_t* a, const uint16_t* w, const float* bias, float* c, int M, int N, int K,
                        int tile_n, int cta_group, void* stream);
 
+/* Self-test of the fused attention kernel: qkv device bf16 [B*S, 3d] (rows = tokens, columns q | k | v, head h owns
+ * columns h*hd .. of each, the layout F.multi_head_attention_forward derives from in_proj; torch
+ * nn/functional.py), out device bf16 [B*S, d] = softmax(q k^T / sqrt(hd)) v per (sequence, head), no mask
+ * (interaction_segment_mdm.py:63-70,171).  S <= 176, hd = d/H in {64, 128}. */
+int tamf_attn_selftest(const uint16_t* qkv, uint16_t* out, int B, int S, int H, int d, void* stream);
+
 /* Debug aid (tools/gemm_trace.py): one launch of a hot-path GEMM shape with per-CTA clock64 event timestamps.
  * which: 0 = in_proj-like (bias -> bf16), 1 = linear1-like (bias + GELU -> bf16), 2 = LayerNorm GEMM (N = 512).
  * a [M,K], w [N,K] bf16; bias [N]; out bf16 [M,N]; X fp32 [M,N] (which 2); trace int64 [148][64] (device). */

@@ -4,6 +4,7 @@
 
 #include <mutex>
 
+#include "attn.cuh"
 #include "gemm.cuh"
 
 namespace tamf {
@@ -96,6 +97,27 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64
   return TAMF_OK;
 }
 
+int make_tmap_3d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t mid, uint64_t outer,
+                      uint64_t mid_pitch_bytes, uint64_t outer_pitch_bytes, uint32_t box_mid) {
+  EncodeTiledFn enc = get_encode();
+  TAMF_REQUIRE(enc != nullptr, TAMF_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  TAMF_REQUIRE(aligned16(gptr) && (mid_pitch_bytes % 16) == 0 && (outer_pitch_bytes % 16) == 0, TAMF_E_ALIGN,
+               "TMA tensor must be 16-byte aligned");
+  TAMF_REQUIRE(box_mid >= 1 && box_mid <= 256, TAMF_E_BADARG, "TMA box must be <= 256 rows");
+  cuuint64_t dims[3] = {inner, mid, outer};
+  cuuint64_t strides[2] = {mid_pitch_bytes, outer_pitch_bytes};
+  cuuint32_t box[3] = {64, box_mid, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3d) failed with CUresult " + std::to_string((int)r));
+    return TAMF_E_CUDA;
+  }
+  return TAMF_OK;
+}
+
 int make_tmap_2d_f32(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes,
                      uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
@@ -176,6 +198,23 @@ extern "C" int tamf_gemm_selftest(const uint16_t* a, const uint16_t* w, const fl
   if (tile_n == 128) return selftest_run<128, 2>(a, w, p, stream);
   if (tile_n == 256) return selftest_run<256, 2>(a, w, p, stream);
   return selftest_run<512, 2>(a, w, p, stream);
+}
+
+extern "C" int tamf_attn_selftest(const uint16_t* qkv, uint16_t* out, int B, int S, int H, int d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_device();
+  if (rc) return rc;
+  TAMF_REQUIRE(qkv && out, TAMF_E_BADARG, "tamf_attn_selftest: null pointer");
+  TAMF_REQUIRE(B > 0 && S > 0 && S <= ATT_KP && H > 0 && d % H == 0 && (d / H == 64 || d / H == 128), TAMF_E_BADARG,
+               "tamf_attn_selftest: need 0 < S <= 176 and head_dim 64 or 128");
+  AttnMaps am;
+  if ((rc = make_attn_maps(&am, qkv, out, B, S, d))) return rc;
+  if (d / H == 128) {
+    if ((rc = configure_attn<128>())) return rc;
+    return launch_attn<128>(am, B, S, H, d, stream);
+  }
+  if ((rc = configure_attn<64>())) return rc;
+  return launch_attn<64>(am, B, S, H, d, stream);
 }
 
 // Debug aid (tools/gemm_trace.py): one launch of the hot-path GEMM shape `which` on caller data with per-CTA

@@ -57,6 +57,11 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner /*eleme
 int make_tmap_2d_f32(CUtensorMap* out, const void* gptr, uint64_t inner /*elements*/, uint64_t rows,
                      uint64_t row_pitch_bytes, uint32_t box_rows);
 
+// bf16 [outer][mid][inner] tensor (strides in bytes), box {64, box_mid, 1}, 128-byte swizzle
+int make_tmap_3d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t mid, uint64_t outer,
+                      uint64_t mid_pitch_bytes, uint64_t outer_pitch_bytes, uint32_t box_mid);
+bool pdl_enabled();  // TAMF_PDL=0 turns programmatic dependent launch off (debug aid)
+
 // ---------------------------------------------------------------------------------------------
 // device side
 // ---------------------------------------------------------------------------------------------
@@ -149,6 +154,25 @@ __device__ __forceinline__ void bulk_wait() {
 }
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 3D variants (attention: [batch][token][feature] views; tokens past S are zero-filled on load, clipped on store)
+__device__ __forceinline__ void tma_load_3d_u32(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// Programmatic dependent launch (PDL) controls
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {

@@ -201,6 +201,9 @@ int EncoderBuffers::make_maps(int d, int ff) {
   if ((rc = make_tmap_2d_bf16(&tm_H_st, Hb, ff, M, (uint64_t)ff * 2, 64, 32))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_Xb_st, Xb, d, M, (uint64_t)d * 2, 32, 32))) return rc;
   if ((rc = make_tmap_2d_f32(&tm_X, X, d, M, (uint64_t)d * 4, 32))) return rc;
+  AttnMaps am;
+  if ((rc = make_attn_maps(&am, QKV, ATT, B, S, d))) return rc;
+  tm_att_kv = am.kv, tm_att_q = am.q, tm_att_o = am.o;
   return TAMF_OK;
 }
 
@@ -227,11 +230,12 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
       if ((rc = launch_gemm<256, EPI_BIAS_BF16, 2>(buf.tm_Xb, w.tm_in, p, s))) return rc;
       mark_event(marks, s);
     }
-    if (d / enc.H == 128)
-      rc = launch_attn<128>(buf.QKV, buf.ATT, buf.B, buf.S, enc.H, d, s);
-    else
-      rc = launch_attn<64>(buf.QKV, buf.ATT, buf.B, buf.S, enc.H, d, s);
-    if (rc) return rc;
+    {
+      AttnMaps am;
+      am.kv = buf.tm_att_kv, am.q = buf.tm_att_q, am.o = buf.tm_att_o;
+      rc = (d / enc.H == 128) ? launch_attn<128>(am, buf.B, buf.S, enc.H, d, s) : launch_attn<64>(am, buf.B, buf.S, enc.H, d, s);
+      if (rc) return rc;
+    }
     mark_event(marks, s);
     {
       GemmParams p{};

@@ -164,10 +164,6 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
-// Programmatic dependent launch (PDL) controls
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
