@@ -19,4 +19,4 @@ if [[ "${1:-}" != "quick" ]]; then
       -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 1 --chain-steps 4 --no-cpu-baseline \
       --profile-reps 1 > gpurun_out/ncu_full.log 2>&1
 fi
-tail -5 gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/bench.json gpurun_out/bench.err gpurun_out/bench_ref.json
+tail -n 5 gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/bench.json gpurun_out/bench.err gpurun_out/bench_ref.json
