@@ -234,9 +234,9 @@ extern "C" int tamf_gemm_trace(int which, const uint16_t* a, const uint16_t* w, 
   CUtensorMap tmC, tmX;
   if (which == 2) {
     if ((rc = make_tmap_2d_bf16(&tmC, out, N, M, (uint64_t)N * 2, 32, 32))) return rc;
-    if ((rc = make_tmap_2d_f32(&tmX, X, N, M, (uint64_t)N * 4, 32))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tmX, X, N, M, (uint64_t)N * 2, 32, 32))) return rc;  // low plane (bf16 view of the buffer)
     p.tmC = &tmC, p.tmX = &tmX;
-    p.X = X, p.Xb = (__nv_bfloat16*)out, p.gamma = bias, p.beta = bias;
+    p.Xlo = (__nv_bfloat16*)X, p.Xb = (__nv_bfloat16*)out, p.gamma = bias, p.beta = bias;
     if ((rc = configure_gemm<512, EPI_RES_LN, 2>())) return rc;
     return launch_gemm<512, EPI_RES_LN, 2>(tmA, tmB, p, stream);
   }

@@ -309,6 +309,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Residual-stream element -> its two bf16 planes: hi = bf16(v), lo = bf16(v - hi)  (see gemm.cuh, EPI_RES_LN)
+__device__ __forceinline__ void store_hilo(__nv_bfloat16* hi_plane, __nv_bfloat16* lo_plane, size_t i, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi_plane[i] = h;
+  lo_plane[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 // Philox4x32-10 (Salmon et al. 2011) -- counter-based, used for the sampler's eps.
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 #pragma unroll

@@ -9,14 +9,15 @@
 //   embed-a     H0 = silu(A0 . Wf^T + bf)   A0 = [x_t (99) | 0 | mean_obj(obj_traj) (9) | 0..] (K = 128), Wf =
 //               [merge0[:, :d] . poseEmbedding | 0 | merge0[:, d:] . objPoseEmbedding | 0..]  (both linear maps of
 //               input_merge.0 folded; the trajectory columns of A0 are written once per sample)
-//   embed-b     tok[5+tau] = nan_to_num(H0 . merge2^T + b) + pe[5+tau]     -> X fp32 / Xb bf16, rows b*S+5+tau
+//   embed-b     tok[5+tau] = nan_to_num(H0 . merge2^T + b) + pe[5+tau]     -> Xb / Xlo, rows b*S+5+tau
 //   8 x layer   QKV = Xb . Win^T + b ; ATT = softmax(QK^T/sqrt(hd)) V ; X = LN1(X + ATT . Wo^T + b)
 //               H = gelu(Xb . W1^T + b) ; X = LN2(X + H . W2^T + b)
 //   final       x0 = nan_to_num(Xb . Wf^T + b) ; x_{t-1} = c1[t] x0 + c2[t] x_t + sigma[t] eps   (fused epilogue)
 // = 2 + 5*L + 2 = 44 kernel launches for L = 8, captured once in a CUDA graph and replayed per step.
 //
 // HBM layout (row = token index b*S + s, S = 5 + T; all row-major):
-//   X  fp32 [M,d] residual stream | Xb bf16 [M,d] GEMM operand copy | QKV bf16 [M,3d] | ATT bf16 [M,d] | H bf16 [M,ff]
+//   Xb bf16 [M,d] + Xlo bf16 [M,d] residual stream x = Xb + Xlo (Xb doubles as the GEMM operand) | QKV bf16 [M,3d] |
+//   ATT bf16 [M,d] | H bf16 [M,ff]
 //   A0 bf16 [B*T,128] | H0 bf16 [B*T,d] | prefix fp32 [B,4,d] | ttab fp32 [steps,d]
 #include <vector>
 
@@ -63,11 +64,11 @@ __global__ void add_int_kernel(int* p, int n, int dv) {
 // prep: grid (ceil(T/32), B), 256 threads.
 //  (a) A0[b*T+tau, k] = bf16(x[b,k,0,tau]) (k < nfeat), 0 for the K padding -- transposed through shared memory so
 //      both the read (along tau) and the write (along k) are coalesced.
-//  (b) blockIdx.x == 0 also writes the 5 prefix token rows of sequence b into X / Xb.
+//  (b) blockIdx.x == 0 also writes the 5 prefix token rows of sequence b into the residual planes Xb / Xlo.
 __global__ void __launch_bounds__(256)
     prep_kernel(const float* __restrict__ x, const int* __restrict__ t_ptr, const float* __restrict__ ttab,
                 const float* __restrict__ pe, const float* __restrict__ prefix, __nv_bfloat16* __restrict__ A0,
-                float* __restrict__ X, __nv_bfloat16* __restrict__ Xb, int T, int S, int d, int nfeat) {
+                __nv_bfloat16* __restrict__ Xlo, __nv_bfloat16* __restrict__ Xb, int T, int S, int d, int nfeat) {
   __shared__ float tile[KPAD][33];
   const int b = blockIdx.y, tau0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -93,8 +94,7 @@ __global__ void __launch_bounds__(256)
         v = nan_to_num(ttab[(size_t)t * d + c]) + pe[c];  // interaction_segment_mdm.py:142,158,170
       else
         v = prefix[((size_t)b * 4 + (s - 1)) * d + c];
-      X[((size_t)b * S + s) * d + c] = v;
-      Xb[((size_t)b * S + s) * d + c] = __float2bfloat16_rn(v);
+      store_hilo(Xb, Xlo, ((size_t)b * S + s) * d + c, v);
     }
   }
 }
@@ -150,7 +150,7 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, fl
   const int d = h->d, B = h->B, T = h->T, S = h->S, M = h->M, Mf = h->Mf;
   int rc;
   mark_event(marks, s);
-  prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, h->ttab, h->pe, h->prefix, h->A0, h->buf.X, h->buf.Xb, T,
+  prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, h->ttab, h->pe, h->prefix, h->A0, h->buf.Xlo, h->buf.Xb, T,
                                                      S, d, h->nfeat);
   TAMF_LAUNCH_CHECK();
   mark_event(marks, s);
@@ -162,7 +162,7 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, fl
   }
   {  // embed-b
     GemmParams p{};
-    p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = 5, p.X = h->buf.X,
+    p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = 5, p.Xlo = h->buf.Xlo,
     p.Xb = h->buf.Xb;
     if ((rc = launch_gemm<256, EPI_TOKEN_OUT, 2>(h->tm_H0, h->tm_wm2, p, s))) return rc;
     mark_event(marks, s);
@@ -310,7 +310,7 @@ static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static WsLayout ws_layout(const tamf_denoiser* h, int B, int T) {
   const size_t d = h->d, ff = h->ff, S = T + 5, M = (size_t)B * S, Mf = (size_t)B * T;
   const size_t sz[] = {
-      M * d * 4,                                 // 0 X
+      M * d * 2,                                 // 0 Xlo
       M * d * 2,                                 // 1 Xb
       M * 3 * d * 2,                             // 2 QKV
       M * d * 2,                                 // 3 ATT
@@ -359,7 +359,7 @@ extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size
   uint8_t* p = static_cast<uint8_t*>(ws);
   h->B = B, h->T = T, h->S = T + 5, h->M = B * (T + 5), h->Mf = B * T;
   h->buf.B = B, h->buf.S = T + 5, h->buf.M = h->M;
-  h->buf.X = (float*)(p + L.off[0]);
+  h->buf.Xlo = (__nv_bfloat16*)(p + L.off[0]);
   h->buf.Xb = (__nv_bfloat16*)(p + L.off[1]);
   h->buf.QKV = (__nv_bfloat16*)(p + L.off[2]);
   h->buf.ATT = (__nv_bfloat16*)(p + L.off[3]);

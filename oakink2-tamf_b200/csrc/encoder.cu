@@ -200,7 +200,7 @@ int EncoderBuffers::make_maps(int d, int ff) {
   if ((rc = make_tmap_2d_bf16(&tm_QKV_st, QKV, 3 * d, M, (uint64_t)3 * d * 2, 64, 32))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_H_st, Hb, ff, M, (uint64_t)ff * 2, 64, 32))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_Xb_st, Xb, d, M, (uint64_t)d * 2, 32, 32))) return rc;
-  if ((rc = make_tmap_2d_f32(&tm_X, X, d, M, (uint64_t)d * 4, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_Xlo, Xlo, d, M, (uint64_t)d * 2, 32, 32))) return rc;
   AttnMaps am;
   if ((rc = make_attn_maps(&am, QKV, ATT, B, S, d))) return rc;
   tm_att_kv = am.kv, tm_att_q = am.q, tm_att_o = am.o;
@@ -239,8 +239,8 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     mark_event(marks, s);
     {
       GemmParams p{};
-      p.M = M, p.N = d, p.K = d, p.bias = w.b_out, p.X = buf.X, p.Xb = buf.Xb, p.gamma = w.g1, p.beta = w.be1;
-      p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_X;
+      p.M = M, p.N = d, p.K = d, p.bias = w.b_out, p.Xlo = buf.Xlo, p.Xb = buf.Xb, p.gamma = w.g1, p.beta = w.be1;
+      p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_Xlo;
       rc = (d == 512) ? launch_gemm<512, EPI_RES_LN, 2>(buf.tm_ATT, w.tm_out, p, s)
                       : launch_gemm<256, EPI_RES_LN, 2>(buf.tm_ATT, w.tm_out, p, s);
       if (rc) return rc;
@@ -254,8 +254,8 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     }
     {
       GemmParams p{};
-      p.M = M, p.N = d, p.K = ff, p.bias = w.b2, p.X = buf.X, p.Xb = buf.Xb, p.gamma = w.g2, p.beta = w.be2;
-      p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_X;
+      p.M = M, p.N = d, p.K = ff, p.bias = w.b2, p.Xlo = buf.Xlo, p.Xb = buf.Xb, p.gamma = w.g2, p.beta = w.be2;
+      p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_Xlo;
       rc = (d == 512) ? launch_gemm<512, EPI_RES_LN, 2>(buf.tm_H, w.tm_w2, p, s)
                       : launch_gemm<256, EPI_RES_LN, 2>(buf.tm_H, w.tm_w2, p, s);
       if (rc) return rc;

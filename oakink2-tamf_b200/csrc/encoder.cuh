@@ -8,7 +8,7 @@
 // Per layer, 5 kernels over the token matrix (row = b*S + s):
 //   QKV = Xb . Win^T + b                    tcgen05 GEMM, bf16 out           [M,3d]
 //   ATT = softmax(Q K^T / sqrt(hd)) V       fused attention (attn.cuh)       [M,d]
-//   X   = LN1(X + ATT . Wo^T + b)           tcgen05 GEMM, residual+LayerNorm epilogue (fp32 X + bf16 Xb)
+//   X   = LN1(X + ATT . Wo^T + b)           tcgen05 GEMM, residual+LayerNorm epilogue (X = Xb + Xlo, two bf16 planes)
 //   H   = gelu(Xb . W1^T + b)               tcgen05 GEMM, exact-erf GELU epilogue, bf16 out  [M,ff]
 //   X   = LN2(X + H . W2^T + b)             tcgen05 GEMM, residual+LayerNorm epilogue
 #pragma once
@@ -43,14 +43,14 @@ struct EncoderStack {
 // Activation buffers of one bound (B, S) problem; all row-major, row = b*S + s.
 struct EncoderBuffers {
   int B = 0, S = 0, M = 0;
-  float* X = nullptr;             // fp32 residual stream [M,d]
-  __nv_bfloat16* Xb = nullptr;    // bf16 copy of X (GEMM A operand)
+  __nv_bfloat16* Xb = nullptr;    // residual stream, high plane bf16(x) [M,d] = the GEMM A operand
+  __nv_bfloat16* Xlo = nullptr;   // residual stream, low plane bf16(x - Xb) [M,d]
   __nv_bfloat16* QKV = nullptr;   // [M,3d]
   __nv_bfloat16* ATT = nullptr;   // [M,d]
   __nv_bfloat16* Hb = nullptr;    // [M,ff]
   CUtensorMap tm_Xb, tm_ATT, tm_H;              // GEMM A-operand loads, box {64, 128}
   CUtensorMap tm_QKV_st, tm_H_st;               // bf16 epilogue stores, box {64, 32}
-  CUtensorMap tm_Xb_st, tm_X;                   // LayerNorm epilogue: Xb store {32, 32} bf16; X load + store {32, 32} fp32
+  CUtensorMap tm_Xb_st, tm_Xlo;                 // LayerNorm epilogue: Xb / Xlo residual load + store, box {32, 32} bf16
   CUtensorMap tm_att_kv, tm_att_q, tm_att_o;    // attention: [B][S][3d] views of QKV (K/V box, Q box), [B][S][d] view of ATT
   int make_maps(int d, int ff);
 };

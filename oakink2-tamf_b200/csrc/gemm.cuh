@@ -29,8 +29,11 @@
 //   EPI_BIAS_BF16      y = acc + b                                   -> bf16            (QKV in_proj)
 //   EPI_BIAS_GELU_BF16 y = gelu_erf(acc + b)                         -> bf16            (linear1 + F.gelu)
 //   EPI_BIAS_SILU_BF16 y = silu(acc + b)                             -> bf16            (input_merge.0, folded)
-//   EPI_TOKEN_OUT      y = nan_to_num(acc + b) + pe[P0+tau]          -> fp32 + bf16 token rows (input_merge.2)
-//   EPI_RES_LN         x = LayerNorm(x + acc + b) (eps 1e-5, biased var) in place -> fp32 + bf16 (BN == N == d)
+//   EPI_TOKEN_OUT      y = nan_to_num(acc + b) + pe[P0+tau]          -> token rows as a bf16 hi/lo pair (input_merge.2)
+//   EPI_RES_LN         x = LayerNorm(x + acc + b) (eps 1e-5, biased var) in place -> bf16 hi/lo pair (BN == N == d)
+// The residual stream lives in HBM as TWO bf16 planes, Xb = bf16(x) (which is also the next GEMM's A operand) and
+// Xlo = bf16(x - Xb): x is recovered as Xb + Xlo to 2^-17 relative (fp32-grade for a LayerNorm input), but an LN
+// epilogue stores 4 instead of 6 bytes per element -- its second pass is bound by the ~32 B/clk/SM store path.
 //   EPI_POSTERIOR      x0 = nan_to_num(acc + b); x_{t-1} = c1 x0 + c2 x_t + sigma eps  -> [B,99,1,T] fp32
 //   EPI_RESIDUAL_OUT   y = nan_to_num(x_in + acc + b) -> [B,T,99] fp32 (MF-MDM R: segment_refine_model.py:215-217)
 //   EPI_F32            y = acc + b -> fp32 (self-test)
@@ -61,8 +64,9 @@ struct GemmParams {
   // EPI_TOKEN_OUT: GEMM row m = b*T + tau  ->  token row b*S + P0 + tau
   const float* pe;  // [rows, N]
   int T, S, P0;
-  // EPI_RES_LN: X fp32 [M,N] residual in / normalised out; Xb bf16 copy.  EPI_TOKEN_OUT writes the same pair.
-  float* X;
+  // EPI_RES_LN: residual in / normalised out as the bf16 pair Xb (hi) + Xlo (lo), both [M,N].  EPI_TOKEN_OUT writes
+  // the same pair.
+  __nv_bfloat16* Xlo;
   __nv_bfloat16* Xb;
   const float* gamma;
   const float* beta;
@@ -77,7 +81,7 @@ struct GemmParams {
   int nfeat;
   // host pointers to the TMA-store maps (copied into kernel parameters by launch_gemm):
   //   tmC: bf16 output [M,N], box {64 cols, 32 rows} (bias/GELU/SiLU epilogues) | Xb [M,N], box {32, 32} (LN)
-  //   tmX: fp32 residual stream X [M,N], box {32, 32}, loaded (residual) and stored (normalised) by the LN epilogue
+  //   tmX: Xlo [M,N] bf16, box {32, 32}; the LN epilogue loads (residual) and stores (normalised) through tmC + tmX
   const CUtensorMap* tmC;
   const CUtensorMap* tmX;
   // debug only (tools/gemm_trace.py): per-CTA event timestamps, [grid][GEMM_TRACE_SLOTS] clock64 values; null in product
@@ -92,7 +96,7 @@ constexpr int GEMM_EPI_THREADS = GEMM_EPI_WARPS * 32;  // 512
 constexpr int GEMM_THREADS = GEMM_EPI_THREADS + 64;    // + TMA producer warp + MMA issuer warp
 constexpr int GEMM_CTRL_BYTES = 512;                   // mbarriers + TMEM slot | 16 x 2 residual-tile mbarriers (LN)
 constexpr int GEMM_STG_WARP = 4096;                    // warp-private staging tile, 32 rows x 128 B (TMA-store source)
-constexpr int GEMM_LN_STG_WARP = 12288;                // LN: 2 x 4 KB residual tiles in (pass 1) | 2 x (4 KB fp32 + 2 KB bf16) out (pass 2)
+constexpr int GEMM_LN_STG_WARP = 8192;                 // LN: 2 x (2 KB hi + 2 KB lo) residual tiles in (pass 1) | the same out (pass 2)
 constexpr int GEMM_SMEM_MAX = 232448;                  // 227 KB
 
 constexpr bool epi_is_ln(int e) { return e == EPI_RES_LN; }
@@ -184,6 +188,14 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 // lanes = one row segment, full sectors).  16-byte piece p of row r is XOR-swizzled so both sides are conflict-free.
 __device__ __forceinline__ uint32_t stg128_off(int r, int p) { return (uint32_t)(r * 128 + ((p ^ (r & 7)) << 4)); }
 __device__ __forceinline__ uint32_t stg64_off(int r, int p) { return (uint32_t)(r * 64 + ((p ^ ((r >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ float bf16lo_f32(uint32_t w) { return __uint_as_float(w << 16); }          // element 0 of a pair
+__device__ __forceinline__ float bf16hi_f32(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }  // element 1
+// x -> (hi, lo) bf16 planes for a pair of values: hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  lo = pack_bf16x2(a - bf16lo_f32(hi), b - bf16hi_f32(hi));
+}
 
 // K-major operand tile written by TMA with 64-byte swizzle (rows of 32 bf16): 8-row groups 512 B apart.
 __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
@@ -407,15 +419,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       };
       if constexpr (LN) {
         // ---------------- x = LayerNorm(x + acc + b), two passes over TMEM ----------------
-        // Warp-private 12 KB region of the drained ring: pass 1 receives the fp32 residual as TMA tiles
-        // [32 rows x 32 cols] (two buffers, two tiles in flight); pass 2 stages the normalised fp32 / bf16 tiles
+        // Warp-private 8 KB region of the drained ring: pass 1 receives the residual as TMA tiles [32 rows x 32 cols]
+        // of the two bf16 planes (two buffers, two chunks in flight); pass 2 stages the normalised hi / lo tiles
         // (two sets) and hands them to TMA stores, so no LSU global access is left in the epilogue.
         const uint32_t wst = smem_u32(s_stage) + warp * GEMM_LN_STG_WARP;
         uint64_t* rb = rbar + warp * 2;
         const int ccol0 = cq * QW;  // first column of this warp's quarter
-        auto prefetch = [&](int ck) {  // lane 0: residual tile ck -> buffer ck & 1 (rows past M arrive as zeros)
+        auto prefetch = [&](int ck) {  // lane 0: residual tiles of chunk ck -> buffer ck & 1 (rows past M arrive as zeros)
           mbar_arrive_expect_tx(&rb[ck & 1], 4096);
-          tma_load_2d_u32(wst + (ck & 1) * 4096, &tmX, smem_u32(&rb[ck & 1]), ccol0 + ck * 32, grow0);
+          tma_load_2d_u32(wst + (ck & 1) * 4096, &tmC, smem_u32(&rb[ck & 1]), ccol0 + ck * 32, grow0);
+          tma_load_2d_u32(wst + (ck & 1) * 4096 + 2048, &tmX, smem_u32(&rb[ck & 1]), ccol0 + ck * 32, grow0);
         };
         if (lane == 0) {
           prefetch(0);
@@ -433,17 +446,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const int c0 = ccol0 + ck * 32;
           const uint32_t src = wst + (ck & 1) * 4096;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 r4 = lds128(src + stg128_off(lane, j));
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j * 4);
-            const float y0 = __uint_as_float(v[4 * j]) + b4.x + __uint_as_float(r4.x);
-            const float y1 = __uint_as_float(v[4 * j + 1]) + b4.y + __uint_as_float(r4.y);
-            const float y2 = __uint_as_float(v[4 * j + 2]) + b4.z + __uint_as_float(r4.z);
-            const float y3 = __uint_as_float(v[4 * j + 3]) + b4.w + __uint_as_float(r4.w);
-            s0 += y0, s1 += y1, s2 += y2, s3 += y3;
+          for (int j = 0; j < 4; ++j) {  // 8 columns per 16-byte piece of each plane
+            const uint4 h4 = lds128(src + stg64_off(lane, j));
+            const uint4 l4 = lds128(src + 2048 + stg64_off(lane, j));
+            const float4 ba = *reinterpret_cast<const float4*>(s_bias + c0 + j * 8);
+            const float4 bb = *reinterpret_cast<const float4*>(s_bias + c0 + j * 8 + 4);
+            const float y0 = __uint_as_float(v[8 * j]) + ba.x + (bf16lo_f32(h4.x) + bf16lo_f32(l4.x));
+            const float y1 = __uint_as_float(v[8 * j + 1]) + ba.y + (bf16hi_f32(h4.x) + bf16hi_f32(l4.x));
+            const float y2 = __uint_as_float(v[8 * j + 2]) + ba.z + (bf16lo_f32(h4.y) + bf16lo_f32(l4.y));
+            const float y3 = __uint_as_float(v[8 * j + 3]) + ba.w + (bf16hi_f32(h4.y) + bf16hi_f32(l4.y));
+            const float y4 = __uint_as_float(v[8 * j + 4]) + bb.x + (bf16lo_f32(h4.z) + bf16lo_f32(l4.z));
+            const float y5 = __uint_as_float(v[8 * j + 5]) + bb.y + (bf16hi_f32(h4.z) + bf16hi_f32(l4.z));
+            const float y6 = __uint_as_float(v[8 * j + 6]) + bb.z + (bf16lo_f32(h4.w) + bf16lo_f32(l4.w));
+            const float y7 = __uint_as_float(v[8 * j + 7]) + bb.w + (bf16hi_f32(h4.w) + bf16hi_f32(l4.w));
+            s0 += y0 + y4, s1 += y1 + y5, s2 += y2 + y6, s3 += y3 + y7;
             q0 = fmaf(y0, y0, q0), q1 = fmaf(y1, y1, q1), q2 = fmaf(y2, y2, q2), q3 = fmaf(y3, y3, q3);
-            v[4 * j] = __float_as_uint(y0), v[4 * j + 1] = __float_as_uint(y1);
-            v[4 * j + 2] = __float_as_uint(y2), v[4 * j + 3] = __float_as_uint(y3);
+            q0 = fmaf(y4, y4, q0), q1 = fmaf(y5, y5, q1), q2 = fmaf(y6, y6, q2), q3 = fmaf(y7, y7, q3);
+            v[8 * j] = __float_as_uint(y0), v[8 * j + 1] = __float_as_uint(y1);
+            v[8 * j + 2] = __float_as_uint(y2), v[8 * j + 3] = __float_as_uint(y3);
+            v[8 * j + 4] = __float_as_uint(y4), v[8 * j + 5] = __float_as_uint(y5);
+            v[8 * j + 6] = __float_as_uint(y6), v[8 * j + 7] = __float_as_uint(y7);
           }
           tmem_st32(taddr + ck * 32, v);
           __syncwarp();  // every lane has read this residual buffer: it may be refilled
@@ -463,7 +485,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const float var = fmaxf(ex2 - mean * mean, 0.f);  // biased variance (F.layer_norm), fp32
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         const float nmr = -mean * rstd;
-        // ---- pass 2: normalise + affine -> staging set ck & 1 -> TMA stores of the fp32 and bf16 tiles ----
+        // ---- pass 2: normalise + affine -> staging set ck & 1 -> TMA stores of the hi / lo bf16 tiles ----
 #pragma unroll 1
         for (int ck = 0; ck < CHUNKS; ++ck) {
           uint32_t v[32];
@@ -475,28 +497,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             __syncwarp();
           }
           const int c0 = ccol0 + ck * 32;
-          const uint32_t s_outf = wst + (ck & 1) * 6144, s_outb = s_outf + 4096;
+          const uint32_t s_outh = wst + (ck & 1) * 4096, s_outl = s_outh + 2048;
           if (p.dbg & 2) continue;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 g4 = *reinterpret_cast<const float4*>(s_gamma + c0 + j * 4);
-            const float4 be4 = *reinterpret_cast<const float4*>(s_beta + c0 + j * 4);
-            const float y0 = fmaf(fmaf(__uint_as_float(v[4 * j]), rstd, nmr), g4.x, be4.x);
-            const float y1 = fmaf(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmr), g4.y, be4.y);
-            const float y2 = fmaf(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmr), g4.z, be4.z);
-            const float y3 = fmaf(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmr), g4.w, be4.w);
-            sts128(s_outf + stg128_off(lane, j),
-                   make_uint4(__float_as_uint(y0), __float_as_uint(y1), __float_as_uint(y2), __float_as_uint(y3)));
-            v[2 * j] = pack_bf16x2(y0, y1), v[2 * j + 1] = pack_bf16x2(y2, y3);
-          }
+          for (int j = 0; j < 4; ++j) {
+            uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            sts128(s_outb + stg64_off(lane, j), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            for (int e = 0; e < 4; ++e) {
+              const int c = j * 8 + e * 2;
+              const float2 g2 = *reinterpret_cast<const float2*>(s_gamma + c0 + c);
+              const float2 be2 = *reinterpret_cast<const float2*>(s_beta + c0 + c);
+              const float y0 = fmaf(fmaf(__uint_as_float(v[c]), rstd, nmr), g2.x, be2.x);
+              const float y1 = fmaf(fmaf(__uint_as_float(v[c + 1]), rstd, nmr), g2.y, be2.y);
+              split_bf16x2(y0, y1, hi[e], lo[e]);
+            }
+            sts128(s_outh + stg64_off(lane, j), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            sts128(s_outl + stg64_off(lane, j), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && !(p.dbg & 1)) {
-            if (!(p.dbg & 4)) tma_store_2d(&tmX, s_outf, c0, grow0);  // rows past M are clipped by the tensor map
-            if (!(p.dbg & 8)) tma_store_2d(&tmC, s_outb, c0, grow0);
+            if (!(p.dbg & 8)) tma_store_2d(&tmC, s_outh, c0, grow0);  // rows past M are clipped by the tensor map
+            if (!(p.dbg & 4)) tma_store_2d(&tmX, s_outl, c0, grow0);
             bulk_commit();
           }
         }
@@ -506,7 +528,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
         if (threadIdx.x == 0) GEMM_TRACE(6);
       } else if constexpr (EPI == EPI_TOKEN_OUT) {
-        // ---- y = nan_to_num(acc + b) + pe[P0+tau] -> fp32 X and bf16 Xb at token row b*S + P0 + tau ----
+        // ---- y = nan_to_num(acc + b) + pe[P0+tau] -> the bf16 pair Xb / Xlo at token row b*S + P0 + tau ----
         const uint32_t wst = smem_u32(s_stage) + warp * GEMM_STG_WARP;
         const int prow = lane >> 2, pc = lane & 3;  // global side: 8 rows x 4 pieces (16 fp32 columns) per pass
 #pragma unroll 1
@@ -539,8 +561,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 const float y0 = __uint_as_float(o.x) + pe4.x, y1 = __uint_as_float(o.y) + pe4.y;
                 const float y2 = __uint_as_float(o.z) + pe4.z, y3 = __uint_as_float(o.w) + pe4.w;
                 const size_t orow = (size_t)b * p.S + p.P0 + tau;
-                *reinterpret_cast<float4*>(p.X + orow * p.N + col) = make_float4(y0, y1, y2, y3);
-                *reinterpret_cast<uint2*>(p.Xb + orow * p.N + col) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                uint32_t h0, h1, l0, l1;
+                split_bf16x2(y0, y1, h0, l0);
+                split_bf16x2(y2, y3, h1, l1);
+                *reinterpret_cast<uint2*>(p.Xb + orow * p.N + col) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(p.Xlo + orow * p.N + col) = make_uint2(l0, l1);
               }
             }
             __syncwarp();

@@ -46,18 +46,17 @@ __global__ void r_prep_kernel(const float* __restrict__ x_in, const float* __res
 }
 
 // prefix[b, s, :] (s = 0 hand side: rh -> 0, lh -> e0; s = 1 shape token; s = 2 object token, both precomputed)
-// -> nan_to_num(.) + pe[s] written to token rows b*S + s of X / Xb.
+// -> nan_to_num(.) + pe[s] written to token rows b*S + s of the residual planes Xb / Xlo.
 __global__ void r_prefix_kernel(const float* __restrict__ prefix, const int* __restrict__ hand_side,
-                                const float* __restrict__ pe, float* __restrict__ X, __nv_bfloat16* __restrict__ Xb,
-                                int B, int S, int d) {
+                                const float* __restrict__ pe, __nv_bfloat16* __restrict__ Xlo,
+                                __nv_bfloat16* __restrict__ Xb, int B, int S, int d) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * R_PREFIX * d) return;
   const int c = (int)(i % d), s = (int)((i / d) % R_PREFIX), b = (int)(i / (R_PREFIX * (size_t)d));
   float v = prefix[i];
   if (s == 0) v = (hand_side[b] == 1 && c == 0) ? 1.f : 0.f;
   v = nan_to_num(v) + pe[(size_t)s * d + c];
-  X[((size_t)b * S + s) * d + c] = v;
-  Xb[((size_t)b * S + s) * d + c] = __float2bfloat16_rn(v);
+  store_hilo(Xb, Xlo, ((size_t)b * S + s) * d + c, v);
 }
 
 }  // namespace tamf
@@ -164,7 +163,7 @@ struct RWs {
 static RWs r_layout(const tamf_refiner* h, int B, int T) {
   const size_t d = h->d, ff = h->ff, S = T + R_PREFIX, M = (size_t)B * S, Mf = (size_t)B * T;
   const size_t sz[] = {
-      M * d * 4,                             // 0 X
+      M * d * 2,                             // 0 Xlo
       M * d * 2,                             // 1 Xb
       M * 3 * d * 2,                         // 2 QKV
       M * d * 2,                             // 3 ATT
@@ -205,7 +204,7 @@ extern "C" int tamf_refiner_bind(tamf_refiner* h, int B, int T, void* ws, size_t
   uint8_t* p = static_cast<uint8_t*>(ws);
   h->B = B, h->T = T, h->S = T + R_PREFIX, h->M = B * h->S, h->Mf = B * T;
   h->buf.B = B, h->buf.S = h->S, h->buf.M = h->M;
-  h->buf.X = (float*)(p + L.off[0]);
+  h->buf.Xlo = (__nv_bfloat16*)(p + L.off[0]);
   h->buf.Xb = (__nv_bfloat16*)(p + L.off[1]);
   h->buf.QKV = (__nv_bfloat16*)(p + L.off[2]);
   h->buf.ATT = (__nv_bfloat16*)(p + L.off[3]);
@@ -248,7 +247,7 @@ extern "C" int tamf_refiner_forward(tamf_refiner* h, const float* sample_pose_re
     return rc;
   {
     const size_t n = (size_t)B * R_PREFIX * d;
-    r_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->prefix, hand_side, h->pe, h->buf.X, h->buf.Xb, B, S, d);
+    r_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->prefix, hand_side, h->pe, h->buf.Xlo, h->buf.Xb, B, S, d);
     TAMF_LAUNCH_CHECK();
   }
   // ---- frame tokens ----
@@ -265,7 +264,7 @@ extern "C" int tamf_refiner_forward(tamf_refiner* h, const float* sample_pose_re
   }
   {
     GemmParams p{};
-    p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = R_PREFIX, p.X = h->buf.X,
+    p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = R_PREFIX, p.Xlo = h->buf.Xlo,
     p.Xb = h->buf.Xb;
     if ((rc = launch_gemm<256, EPI_TOKEN_OUT, 2>(h->tm_H0, h->tm_wm2, p, s))) return rc;
   }
