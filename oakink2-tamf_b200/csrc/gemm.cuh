@@ -168,6 +168,45 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of fp32 math, same rounding as the
+// scalar forms).  The epilogues are issue-bound, so every FMA chain that can run on pairs does.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float pk_lo(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float pk_hi(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// gelu_erf on a pair: identical polynomial and operation order as the scalar form (bit-identical results).
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
+  const f32x2 xc = pk2(fminf(fmaxf(pk_lo(x), -4.0f), 4.0f), fminf(fmaxf(pk_hi(x), -4.0f), 4.0f));
+  const f32x2 s = mul2(xc, xc);
+  f32x2 p = pk2(6.699732416e-11f, 6.699732416e-11f);
+  p = fma2(p, s, pk2(-6.040797371e-09f, -6.040797371e-09f));
+  p = fma2(p, s, pk2(2.434135770e-07f, 2.434135770e-07f));
+  p = fma2(p, s, pk2(-5.851926342e-06f, -5.851926342e-06f));
+  p = fma2(p, s, pk2(9.488355446e-05f, 9.488355446e-05f));
+  p = fma2(p, s, pk2(-1.112714840e-03f, -1.112714840e-03f));
+  p = fma2(p, s, pk2(9.816041892e-03f, 9.816041892e-03f));
+  p = fma2(p, s, pk2(-6.632534796e-02f, -6.632534796e-02f));
+  p = fma2(p, s, pk2(3.988829340e-01f, 3.988829340e-01f));
+  return mul2(x, fma2(xc, p, pk2(0.5f, 0.5f)));
+}
+
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -587,23 +626,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (n0 + cl < p.N) {  // warp-uniform (N is a multiple of 64)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float y[8];
+            const uint32_t* v = (j < 4) ? (v0 + j * 8) : (v1 + (j - 4) * 8);
+            uint32_t o[4];
+            if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-            for (int e = 0; e < 8; e += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cl + j * 8 + e);
-              const uint32_t* v = (j < 4) ? (v0 + j * 8 + e) : (v1 + (j - 4) * 8 + e);
-              y[e] = __uint_as_float(v[0]) + b4.x, y[e + 1] = __uint_as_float(v[1]) + b4.y;
-              y[e + 2] = __uint_as_float(v[2]) + b4.z, y[e + 3] = __uint_as_float(v[3]) + b4.w;
+              for (int e = 0; e < 4; ++e) {  // packed pairs: bias add + GELU as FADD2 / FFMA2 chains
+                const float2 b2 = *reinterpret_cast<const float2*>(s_bias + cl + j * 8 + 2 * e);
+                const f32x2 y = gelu_erf2(add2(pk2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), pk2(b2.x, b2.y)));
+                o[e] = pack_bf16x2(pk_lo(y), pk_hi(y));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 b2 = *reinterpret_cast<const float2*>(s_bias + cl + j * 8 + 2 * e);
+                float y0 = __uint_as_float(v[2 * e]) + b2.x, y1 = __uint_as_float(v[2 * e + 1]) + b2.y;
+                if constexpr (EPI == EPI_BIAS_SILU_BF16) y0 = silu(y0), y1 = silu(y1);
+                o[e] = pack_bf16x2(y0, y1);
+              }
             }
-            if constexpr (EPI == EPI_BIAS_SILU_BF16) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) y[e] = silu(y[e]);
-            } else if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) y[e] = gelu_erf(y[e]);
-            }
-            sts128(wst + stg128_off(lane, j), make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                         pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+            sts128(wst + stg128_off(lane, j), make_uint4(o[0], o[1], o[2], o[3]));
           }
           fence_proxy_async_smem();
           __syncwarp();
