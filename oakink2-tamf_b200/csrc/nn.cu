@@ -5,14 +5,22 @@
 // SegmentRefineModel.multi_object_h2o_dist (src/oakink2_tamf/model/segment_refine_model.py:142-168).
 //
 // Layout: one CTA scans one (cloud n, candidate split s) pair for ALL queries of that cloud.  Candidates are
-// staged through shared memory as float4 (coalesced global reads, broadcast LDS.128 in the inner loop); each
-// thread keeps QPT queries in registers so one LDS feeds QPT distance evaluations.  Splits are merged with a
+// staged through shared memory (coalesced global reads, broadcast LDS.128 + LDS.64 in the inner loop); each thread
+// keeps QPT = 4 queries in registers as two packed fp32 pairs, so one candidate load feeds 4 distance evaluations.  Splits are merged with a
 // 64-bit atomicMin on (float_bits(d2) << 32 | idx): d2 >= 0 so the bit pattern orders like the value, and the
 // index in the low word makes the LOWEST index win exact ties -- the oracle's rule.  The int64 `idx` output
 // buffer itself is the packed scratch (memset to all-ones, finalised in place), so no workspace is needed.
 //
-// Arithmetic (bit-exact contract, oracle/nn_oracle.c): d = (dx*dx + dy*dy) + dz*dz with __fsub_rn/__fmul_rn/
-// __fadd_rn, which nvcc never contracts into FMA.
+// Arithmetic (bit-exact contract, oracle/nn_oracle.c): d = (dx*dx + dy*dy) + dz*dz, every operation rounded to fp32
+// and none contracted into an FMA.
+//
+// Inner loop (the kernel is fp32-issue bound: 51 MFLOP per frame and object against 19 KB of traffic): TWO queries per
+// instruction on packed fp32 pairs -- 3 FADD2 (differences) + 3 FMUL2 (squares) per candidate and query pair -- then
+// 2 scalar FADD per query (ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even when both carry .rn, so the sums
+// stay scalar) and ONE FMNMX per query for a running minimum: 6 instructions per (query, candidate) pair instead of
+// 11 with a compare + two selects.  The argmin is recovered afterwards: per group of 16 candidates the thread notes
+// whether its running minimum dropped (strict <, so the earliest group wins ties); after each staged chunk the noted
+// group is re-evaluated with the same arithmetic and the first candidate equal to the minimum is the index.
 #include "common.cuh"
 
 namespace tamf {
@@ -25,20 +33,90 @@ struct NNObj {  // one rigid object of a sequence (fused h2o mode)
   int count;    // number of objects of the sequence
 };
 
-__device__ __forceinline__ void nn_scan_chunk(const float4* __restrict__ sc, int n_c, int base_idx,
-                                              const float (&qx)[NN_QPT], const float (&qy)[NN_QPT],
+constexpr int NN_GROUP = 16;    // candidates per argmin-tracking group
+
+typedef unsigned long long nn_f32x2;
+__device__ __forceinline__ nn_f32x2 nn_pk2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ nn_f32x2 nn_sub2(nn_f32x2 a, nn_f32x2 b) {
+  nn_f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ nn_f32x2 nn_sq2(nn_f32x2 a) {
+  nn_f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(r) : "l"(a));
+  return r;
+}
+__device__ __forceinline__ float nn_lo(nn_f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float nn_hi(nn_f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+
+// Staged candidates: sxy[j] = (x, x, y, y), sz[j] = (z, z) -- every component duplicated so that one 64-bit operand
+// broadcasts it to both queries of a pair.  Slots n_c .. round_up(n_c, NN_GROUP) hold +inf (distance +inf: never a
+// minimum).
+__device__ __forceinline__ void nn_stage(float4* sxy, float2* sz, int j, float x, float y, float z) {
+  sxy[j] = make_float4(x, x, y, y);
+  sz[j] = make_float2(z, z);
+}
+__device__ __forceinline__ void nn_stage_pad(float4* sxy, float2* sz, int n_c) {
+  const int n_pad = (n_c + NN_GROUP - 1) / NN_GROUP * NN_GROUP;
+  const float inf = __int_as_float(0x7f800000);
+  for (int j = n_c + (int)threadIdx.x; j < n_pad; j += blockDim.x) nn_stage(sxy, sz, j, inf, inf, inf);
+}
+
+__device__ __forceinline__ void nn_scan_chunk(const float4* __restrict__ sxy, const float2* __restrict__ sz, int n_c,
+                                              int base_idx, const float (&qx)[NN_QPT], const float (&qy)[NN_QPT],
                                               const float (&qz)[NN_QPT], float (&best)[NN_QPT], int (&bidx)[NN_QPT]) {
-#pragma unroll 4
-  for (int j = 0; j < n_c; ++j) {
-    const float4 c = sc[j];
+  static_assert(NN_QPT == 4, "two packed query pairs per thread");
+  const nn_f32x2 qx2[2] = {nn_pk2(qx[0], qx[1]), nn_pk2(qx[2], qx[3])};
+  const nn_f32x2 qy2[2] = {nn_pk2(qy[0], qy[1]), nn_pk2(qy[2], qy[3])};
+  const nn_f32x2 qz2[2] = {nn_pk2(qz[0], qz[1]), nn_pk2(qz[2], qz[3])};
+  float m[NN_QPT], mprev[NN_QPT];
+  int grp[NN_QPT];
+#pragma unroll
+  for (int q = 0; q < NN_QPT; ++q) m[q] = mprev[q] = best[q], grp[q] = 0;
+  const int n_grp = (n_c + NN_GROUP - 1) / NN_GROUP;
+  for (int g = 0; g < n_grp; ++g) {
+#pragma unroll
+    for (int jj = 0; jj < NN_GROUP; ++jj) {
+      const int j = g * NN_GROUP + jj;
+      const float4 cxy = sxy[j];
+      const float2 czz = sz[j];
+      const nn_f32x2 cx = nn_pk2(cxy.x, cxy.y), cy = nn_pk2(cxy.z, cxy.w), cz = nn_pk2(czz.x, czz.y);
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        const nn_f32x2 px = nn_sq2(nn_sub2(qx2[pr], cx)), py = nn_sq2(nn_sub2(qy2[pr], cy)), pz = nn_sq2(nn_sub2(qz2[pr], cz));
+        const float d0 = __fadd_rn(__fadd_rn(nn_lo(px), nn_lo(py)), nn_lo(pz));
+        const float d1 = __fadd_rn(__fadd_rn(nn_hi(px), nn_hi(py)), nn_hi(pz));
+        m[2 * pr] = fminf(m[2 * pr], d0);  // a NaN distance never becomes the minimum (like `d < best`)
+        m[2 * pr + 1] = fminf(m[2 * pr + 1], d1);
+      }
+    }
 #pragma unroll
     for (int q = 0; q < NN_QPT; ++q) {
-      const float dx = __fsub_rn(qx[q], c.x), dy = __fsub_rn(qy[q], c.y), dz = __fsub_rn(qz[q], c.z);
-      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      if (d < best[q]) {  // strict: ascending scan keeps the lowest index on ties
-        best[q] = d;
-        bidx[q] = base_idx + j;
+      if (m[q] < mprev[q]) {  // strict: the earliest group holding the minimum is remembered
+        mprev[q] = m[q];
+        grp[q] = g;
       }
+    }
+  }
+  // argmin: first candidate of the remembered group whose distance equals the new minimum (same operations, same
+  // rounding as above -> bit-identical distances); ascending scan keeps the lowest index on ties
+#pragma unroll
+  for (int q = 0; q < NN_QPT; ++q) {
+    if (m[q] < best[q]) {
+      best[q] = m[q];
+      int found = -1;
+      for (int jj = NN_GROUP - 1; jj >= 0; --jj) {
+        const int j = grp[q] * NN_GROUP + jj;
+        const float4 cxy = sxy[j];
+        const float2 czz = sz[j];
+        const float dx = __fsub_rn(qx[q], cxy.x), dy = __fsub_rn(qy[q], cxy.z), dz = __fsub_rn(qz[q], czz.x);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        if (d == m[q]) found = j;
+      }
+      bidx[q] = base_idx + found;
     }
   }
 }
@@ -53,7 +131,8 @@ __device__ __forceinline__ void nn_publish(unsigned long long* packed, float bes
 // grid (N, splits); block = ceil(P1 / QPT) rounded up to a warp
 __global__ void __launch_bounds__(1024) nn_scan_kernel(const float* __restrict__ x, const float* __restrict__ y, int P1,
                                                        int P2, int per_split, unsigned long long* __restrict__ packed) {
-  __shared__ float4 sc[NN_CHUNK];
+  __shared__ float4 sxy[NN_CHUNK];
+  __shared__ float2 sz[NN_CHUNK];
   const int n = blockIdx.x;
   const int c_begin = blockIdx.y * per_split;
   const int c_end = min(P2, c_begin + per_split);
@@ -77,10 +156,11 @@ __global__ void __launch_bounds__(1024) nn_scan_kernel(const float* __restrict__
     __syncthreads();
     for (int j = threadIdx.x; j < n_c; j += blockDim.x) {
       const float* p = yn + (size_t)(c0 + j) * 3;
-      sc[j] = make_float4(p[0], p[1], p[2], 0.f);
+      nn_stage(sxy, sz, j, p[0], p[1], p[2]);
     }
+    nn_stage_pad(sxy, sz, n_c);
     __syncthreads();
-    nn_scan_chunk(sc, n_c, c0, qx, qy, qz, best, bidx);
+    nn_scan_chunk(sxy, sz, n_c, c0, qx, qy, qz, best, bidx);
   }
 #pragma unroll
   for (int q = 0; q < NN_QPT; ++q) {
@@ -111,7 +191,8 @@ __global__ void __launch_bounds__(1024)
     h2o_scan_kernel(const float* __restrict__ verts, const float* __restrict__ obj_traj,
                     const float* __restrict__ obj_points, const int* __restrict__ obj_first, int T, int V, int nobj_max,
                     int P, int per_split, unsigned long long* __restrict__ packed) {
-  __shared__ float4 sc[NN_CHUNK];
+  __shared__ float4 sxy[NN_CHUNK];
+  __shared__ float2 sz[NN_CHUNK];
   __shared__ float sR[12];
   const int f = blockIdx.x, b = f / T, t = f % T;
   const int first = obj_first[b], nobj = obj_first[b + 1] - first;
@@ -153,12 +234,13 @@ __global__ void __launch_bounds__(1024)
     for (int j = threadIdx.x; j < n_c; j += blockDim.x) {
       const float px = pts[3 * j], py = pts[3 * j + 1], pz = pts[3 * j + 2];
       // transf_point_array: R p + t   (src/dev_fn/transform/transform.py:36-53)
-      sc[j] = make_float4(fmaf(sR[2], pz, fmaf(sR[1], py, sR[0] * px)) + sR[9],
-                          fmaf(sR[5], pz, fmaf(sR[4], py, sR[3] * px)) + sR[10],
-                          fmaf(sR[8], pz, fmaf(sR[7], py, sR[6] * px)) + sR[11], 0.f);
+      nn_stage(sxy, sz, j, fmaf(sR[2], pz, fmaf(sR[1], py, sR[0] * px)) + sR[9],
+               fmaf(sR[5], pz, fmaf(sR[4], py, sR[3] * px)) + sR[10],
+               fmaf(sR[8], pz, fmaf(sR[7], py, sR[6] * px)) + sR[11]);
     }
+    nn_stage_pad(sxy, sz, n_c);
     __syncthreads();
-    nn_scan_chunk(sc, n_c, c0, qx, qy, qz, best, bidx);
+    nn_scan_chunk(sxy, sz, n_c, c0, qx, qy, qz, best, bidx);
     c0 += n_c;
   }
 #pragma unroll
