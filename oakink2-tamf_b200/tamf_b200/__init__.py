@@ -4,6 +4,9 @@ Same call signatures as the reference (InterationSegmentMDM.forward(x, timesteps
 ManoLayer(...)(pose_coeffs, betas), ChamferDistance()(x, y), point2point_signed, SegmentRefineModel(mano_path, ...)(batch)), backed by libtamf_b200.so."""
 from .chamfer import ChamferDistance, h2o_dist, nn_query, point2point_signed  # noqa: F401
 from .diffusion import GaussianDiffusion, SpacedDiffusion, create_gaussian_diffusion  # noqa: F401
+from .extract_sample import (contact_min_cdist, extract_refined_sample, extract_refined_sample_bihand,  # noqa: F401
+                             extract_refined_samples, interaction_segment_collate, map_copy_select_to,
+                             refine_dataset, sample_dataset, transf_merge_obj_pointcloud)
 from .manolayer import MANOOutput, ManoLayer  # noqa: F401
 from .mdm import InterationSegmentMDM  # noqa: F401
 from .refine import SegmentRefineModel, vertex_normals  # noqa: F401

@@ -176,6 +176,33 @@ def make_batch(B: int, T: int = 160, nobj: int = 2, seed: int = 0, ragged: bool 
     return batch
 
 
+def make_items(n: int, T: int = 160, nobj: int = 2, seed: int = 0, ragged: bool = True, npoints: int = 256,
+               bihand: bool = False) -> list:
+    """`n` dataset items in the schema of `InteractionSegmentData.__getitem__` (dataset/interaction_segment.py:415-448):
+    numpy arrays WITHOUT the batch axis and with the item's own object count (the collate pads).  `bihand` adds the
+    two-hand keys `extract_refined_sample_bihand` reads (pose_repr_{lh,rh}, shape_{lh,rh}, obj_pair)."""
+    b = make_batch(n, T, nobj=nobj, seed=seed, ragged=ragged, npoints=npoints, with_pointcloud=True)
+    rng = np.random.default_rng(seed + 12345)
+    items = []
+    for i in range(n):
+        k = int(b["obj_num"][i])
+        it = {
+            "text": b["text"][i], "hand_side": b["hand_side"][i], "shape": b["shape"][i].numpy(),
+            "obj_traj": b["obj_traj"][i, :k].numpy(), "obj_embedding": b["obj_embedding"][i, :k].numpy(), "obj_num": k,
+            "pose_repr": b["pose_repr"][i].numpy(), "sample_pose_repr": b["sample_pose_repr"][i].numpy(),
+            "mask": b["mask"][i].numpy(), "len": T, "obj_list": list(b["obj_list"][i]),
+            "obj_pointcloud": b["obj_pointcloud"][i], "info": (f"scene/{i:03d}", i, 0),
+            "frame_id": list(range(T)),
+        }
+        if bihand:
+            it["pose_repr_rh"], it["shape_rh"] = it["pose_repr"], it["shape"]
+            it["pose_repr_lh"] = random_pose_repr(rng, 1, T)[0]
+            it["shape_lh"] = np.repeat(0.5 * rng.standard_normal((1, 10)), T, axis=0).astype(np.float32)
+            it["obj_pair"] = (it["obj_list"][:1], it["obj_list"][-1:])  # [0]: left-hand objects, [1]: right-hand
+        items.append(it)
+    return items
+
+
 def text_features(texts, dim: int = 512, seed: int = 99) -> torch.Tensor:
     """Deterministic stand-in for CLIP `encode_text` output ([B,512] fp32): a hash-seeded unit-scale vector per
     string.  CLIP weights are a network download (not offline), so benches/tests use this synthetic encoder."""

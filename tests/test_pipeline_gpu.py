@@ -1,0 +1,116 @@
+"""G -> R pipeline on the GPU: `extract_refined_sample(_bihand)` equals the hand-composed
+call sequence of the reference (extract_sample.py:7-41), the launcher loops write the reference's on-disk layout, and
+`contact_min_cdist` equals the reference's torch.cdist reduction."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+T, P = 24, 128
+
+
+def _models():
+    import tamf_b200
+    from tamf_b200 import synth
+    cg, cr = synth.ARCH["arch_mdm"], synth.ARCH["arch_refine"]
+    g = tamf_b200.InterationSegmentMDM(**cg, text_encoder=synth.text_features)
+    g.load_state_dict(synth.g_state_dict(cg, 0), strict=False)
+    r = tamf_b200.SegmentRefineModel("unused", **cr, use_pc=True,
+                                     mano_assets={"right": synth.mano_assets("right"), "left": synth.mano_assets("left")})
+    r.load_state_dict(synth.r_state_dict(cr, 0), strict=False)
+    diff = tamf_b200.create_gaussian_diffusion(diffusion_steps=1000, noise_schedule="cosine")
+    return g.eval().to("cuda"), r.eval().to("cuda"), diff
+
+
+class ShortChain:
+    """The 1000-step schedule truncated to its last `n` steps (keeps the test in seconds; same code path)."""
+
+    def __init__(self, diff, n):
+        self.diff, self.n = diff, n
+
+    def p_sample_loop(self, model, shape, **kw):
+        kw["skip_timesteps"] = self.diff.num_timesteps - self.n
+        kw["init_image"] = torch.zeros(shape, device="cuda")
+        return self.diff.p_sample_loop(model, shape, **kw)
+
+
+def test_extract_refined_sample_equals_manual_composition():
+    import tamf_b200
+    from tamf_b200 import synth
+    from tamf_b200.extract_sample import SELECT_G, interaction_segment_collate, map_copy_select_to
+    g, r, diff = _models()
+    chain = ShortChain(diff, 6)
+    items = synth.make_items(3, T=T, nobj=2, seed=5, npoints=P)
+    torch.manual_seed(11)
+    got = tamf_b200.extract_refined_sample(g, chain, r, items[1], "cuda", torch.float32, seed=77)
+    assert got.shape == (T, 99) and got.dtype == np.float32 and np.isfinite(got).all()
+    # the reference's sequence, spelled out
+    torch.manual_seed(11)
+    b = map_copy_select_to(interaction_segment_collate([items[1]]), device="cuda", dtype=torch.float32, select=SELECT_G)
+    s = chain.p_sample_loop(g, (1, 99, 1, T), clip_denoised=False, model_kwargs={"batch": b}, progress=False,
+                            dump_steps=None, noise=None, const_noise=False, seed=77)
+    b["sample_pose_repr"] = s.permute((0, 3, 1, 2)).squeeze(3)
+    ref = r(b)["refine_pose_repr"].cpu().numpy()[0]
+    assert np.array_equal(got, ref)
+    # batched form: row 0 of a batch sees the same x_T rows? (x_T is drawn per batch) -> only shape / finiteness here
+    allb = tamf_b200.extract_refined_samples(g, chain, r, [items[0], items[0]], "cuda", seed=77)
+    assert allb.shape == (2, T, 99) and np.isfinite(allb).all()
+
+
+def test_extract_refined_sample_bihand():
+    import tamf_b200
+    from tamf_b200 import synth
+    from tamf_b200.extract_sample import bihand_item
+    g, r, diff = _models()
+    chain = ShortChain(diff, 4)
+    it = synth.make_items(2, T=T, nobj=3, seed=8, ragged=False, npoints=P, bihand=True)[1]
+    for side in ("rh", "lh"):
+        torch.manual_seed(3)
+        a = tamf_b200.extract_refined_sample_bihand(g, chain, r, it, side, "cuda", torch.float32, seed=5)
+        torch.manual_seed(3)
+        b = tamf_b200.extract_refined_sample(g, chain, r, bihand_item(it, side), "cuda", torch.float32, seed=5)
+        assert a.shape == (T, 99) and np.array_equal(a, b)
+
+
+def test_contact_min_cdist_matches_torch_cdist():
+    from tamf_b200 import synth
+    from tamf_b200.extract_sample import contact_min_cdist, transf_merge_obj_pointcloud
+    it = synth.make_items(1, T=T, nobj=2, seed=2, ragged=False, npoints=P)[0]
+    pc = transf_merge_obj_pointcloud(it["obj_pointcloud"], it["obj_traj"])
+    hv = (0.05 * np.random.default_rng(0).standard_normal((T, 778, 3))).astype(np.float32)
+    got = np.asarray(contact_min_cdist(hv, pc, "cuda", torch.float32))
+    d = torch.cdist(torch.from_numpy(hv).double(), torch.from_numpy(pc).double(), p=2)
+    ref = d.reshape(T, -1).min(dim=1).values.numpy()
+    assert got.shape == (T,) and np.abs(got - ref).max() < 1e-6
+
+
+def test_sample_and_refine_dataset_write_the_reference_layout(tmp_path):
+    import tamf_b200
+    from tamf_b200 import synth
+    g, r, diff = _models()
+    chain = ShortChain(diff, 3)
+    data = synth.make_items(5, T=T, nobj=2, seed=4, npoints=P)
+    out = {}
+    for w in range(2):  # two workers, disjoint shares (launch/sample.py:198-199)
+        out.update(tamf_b200.sample_dataset(g, chain, data, str(tmp_path / "sample"), worker_id=w, num_worker=2,
+                                            batch_size=2, seed=9))
+    assert sorted(out) == list(range(5))
+    for i in range(5):
+        a = np.load(tmp_path / "sample" / f"{i:06d}.npy")
+        assert a.shape == (T, 99) and a.dtype == np.float32 and np.array_equal(a, out[i])
+        data[i]["sample_pose_repr"] = a  # what GeneratedPoseReprSampleAdaptor feeds R (dataset/pose_repr_sample.py:28-35)
+    saved = tamf_b200.refine_dataset(r, data, str(tmp_path / "refine"), batch_size=4)
+    assert len(saved) == 5
+    for i, d in enumerate(saved):
+        path = tmp_path / "refine" / f"scene++{i:03d}" / str(i) / "0" / "save_dict.pkl"
+        assert path.is_file()
+        with open(path, "rb") as f:
+            s = pickle.load(f)
+        assert set(s) == {"process_key", "info", "hand_side", "joints", "verts", "faces", "obj_list", "len", "frame_id",
+                          "refine_pose_repr"}
+        assert s["joints"].shape == (T, 21, 3) and s["verts"].shape == (T, 778, 3) and s["faces"].shape == (1552, 3)
+        assert s["refine_pose_repr"].shape == (T, 99) and s["hand_side"] == data[i]["hand_side"]
+        assert np.array_equal(s["refine_pose_repr"], d["refine_pose_repr"])
