@@ -1,0 +1,281 @@
+// attn_tc.cuh -- frame-sequence self-attention on the 5th-gen tensor cores: softmax(Q K^T / sqrt(hd)) V, no mask (the
+// reference applies none: nn.TransformerEncoderLayer built at interaction_segment_mdm.py:63-70, applied :171).
+//
+// One CTA per (head, sequence).  S <= 176 tokens, so the whole head of one sequence is two 128-row query tiles against
+// 176 keys and the softmax is single-pass:
+//   * Q, K, V (176 x hd each) arrive as 128B-swizzled TMA boxes of the [B][S][3d] view of the packed in_proj output
+//     (tokens >= S zero-filled by the tensor map);
+//   * scores:  tcgen05.mma M=128, N=176, K=hd, both operands K-major from shared memory, fp32 accumulators in TMEM
+//     (tile 0 -> columns [0,176), tile 1 -> [176,352));
+//   * softmax: thread = query row; the 176 scores of the row come out of TMEM once (tcgen05.ld), fp32 max / exp2 /
+//     sum in registers, probabilities rounded to bf16 and written to shared memory in the K-major 128B-swizzled
+//     layout the tensor core reads its A operand in;
+//   * P V:     tcgen05.mma M=128, N=hd, K=176 with V as the MN-major B operand (V is [key][hd] in shared memory exactly
+//     as TMA delivered it -- no transpose pass); O tile 0 -> TMEM columns [352,480), O tile 1 reuses [0,128) (the
+//     scores of tile 0 are dead by then);
+//   * epilogue: O * (1 / row sum) -> bf16 -> warp-private swizzled staging in the dead Q/K region -> TMA stores of the
+//     [B][S][d] view (rows >= S clipped).
+// Warps 0-3 own the rows of tile 0, warps 4-5 rows 128..191 (tile 1: at most 48 valid rows), warp 6 issues TMA and MMA.
+// Tile-1 rows beyond the 176 loaded tokens read whatever follows in shared memory: each accumulator row depends on
+// its own A row only, and those rows are never stored.
+#pragma once
+#include "common.cuh"
+
+namespace tamf {
+
+constexpr int ATC_KP = 176;         // padded token count (multiple of 16)
+constexpr int ATC_THREADS = 7 * 32;
+constexpr int ATC_TMEM_COLS = 512;
+constexpr int ATC_O0_COL = 2 * ATC_KP;  // 352
+
+template <int HD>
+struct AttnTcCfg {
+  static constexpr int NB = HD / 64;           // 64-column blocks per Q / K / V operand
+  static constexpr int BLK = ATC_KP * 128;     // bytes of one [176 rows][128 B] block
+  static constexpr int P0_BLK = 128 * 128;     // tile 0 probabilities: 3 blocks of [128 rows][128 B]
+  static constexpr int P1_BLK = 64 * 128;      // tile 1 probabilities: 3 blocks of [64 rows][128 B]
+  static constexpr int OFF_P1 = 0;             // first, so that the 128-row MMA reads past its 64 rows stay in bounds
+  static constexpr int OFF_P0 = 3 * P1_BLK;
+  static constexpr int OFF_Q = OFF_P0 + 3 * P0_BLK;
+  static constexpr int OFF_K = OFF_Q + NB * BLK;
+  static constexpr int OFF_V = OFF_K + NB * BLK;
+  static constexpr int END = OFF_V + NB * BLK;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + END;
+  static_assert(6 * NB * 4096 <= 2 * NB * BLK, "output staging must fit in the dead Q/K region");
+  static_assert(OFF_Q + (NB - 1) * BLK + 256 * 128 <= END, "tile-1 Q over-read must stay inside the allocation");
+};
+
+// MN-major operand with 128-byte swizzle (cute/atom/mma_traits_sm100.hpp, canonical Major-MN layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): 64 contiguous MN elements per K row, rows 128 B apart, 8-row
+// groups SBO = 1024 B apart, 64-element MN groups LBO bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float atc_ex2(float x) {  // x <= 0 here: flush-to-zero of denormal results is harmless
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void atc_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// tmKV: QKV viewed [B][S][3d], box {64, 176, 1}; tmO: ATT viewed [B][S][d], box {64, 32, 1}.
+template <int HD>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+    attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmO, int S, int d,
+                   int dbg) {
+  using C = AttnTcCfg<HD>;
+  constexpr int NB = C::NB;
+  extern __shared__ uint8_t atc_raw[];
+  __shared__ uint64_t bars[8];  // 0: Q+K landed, 1: V landed, 2+t: scores of tile t, 4+t: P of tile t, 6+t: O of tile t
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(atc_raw) + 1023u) & ~1023u;
+  const uint32_t sP1 = base + C::OFF_P1, sP0 = base + C::OFF_P0, sQ = base + C::OFF_Q, sK = base + C::OFF_K,
+                 sV = base + C::OFF_V;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = S > 128 ? 2 : 1;
+
+  if (warp == 6) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmKV);
+      tma_prefetch_desc(&tmO);
+      mbar_init(&bars[0], 1), mbar_init(&bars[1], 1);
+      mbar_init(&bars[2], 1), mbar_init(&bars[3], 1);
+      mbar_init(&bars[4], 4), mbar_init(&bars[5], 2);
+      mbar_init(&bars[6], 1), mbar_init(&bars[7], 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_slot, ATC_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  pdl_launch_dependents();
+
+  if (warp == 6) {
+    if (lane == 0) {
+      pdl_wait();  // QKV is the previous kernel's output
+      mbar_arrive_expect_tx(&bars[0], 2 * NB * C::BLK);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        tma_load_3d_u32(sQ + j * C::BLK, &tmKV, &bars[0], h * HD + j * 64, 0, b);
+        tma_load_3d_u32(sK + j * C::BLK, &tmKV, &bars[0], d + h * HD + j * 64, 0, b);
+      }
+      mbar_arrive_expect_tx(&bars[1], NB * C::BLK);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) tma_load_3d_u32(sV + j * C::BLK, &tmKV, &bars[1], 2 * d + h * HD + j * 64, 0, b);
+
+      // ---- scores = Q K^T, one 128 x 176 accumulator per query tile ----
+      constexpr uint32_t id_s = umma_idesc_bf16(128, ATC_KP);
+      mbar_wait(&bars[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < ntile; ++t) {
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * C::BLK + (ks & 3) * 32;
+          umma_bf16(tmem + t * ATC_KP, umma_desc_k_sw128(sQ + off + t * (128 * 128)), umma_desc_k_sw128(sK + off), id_s,
+                    ks ? 1u : 0u);
+        }
+        umma_commit(&bars[2 + t]);
+      }
+      // ---- O = P V ----
+      constexpr uint32_t id_o = umma_idesc_bf16_bmn(128, HD);
+      mbar_wait(&bars[1], 0);
+      for (int t = 0; t < ntile; ++t) {
+        mbar_wait(&bars[4 + t], 0);
+        tc_fence_after();
+        const uint32_t pb = t ? sP1 : sP0, pblk = t ? C::P1_BLK : C::P0_BLK;
+        const uint32_t ocol = t ? 0u : (uint32_t)ATC_O0_COL;
+#pragma unroll
+        for (int ks = 0; ks < ATC_KP / 16; ++ks) {
+          umma_bf16(tmem + ocol, umma_desc_k_sw128(pb + (ks >> 2) * pblk + (ks & 3) * 32),
+                    umma_desc_mn_sw128(sV + ks * (16 * 128), C::BLK), id_o, ks ? 1u : 0u);
+        }
+        umma_commit(&bars[6 + t]);
+      }
+    }
+  } else {
+    const int t = warp >> 2, lq = warp & 3;
+    if (t < ntile) {
+      const int r = lq * 32 + lane;  // row inside the tile
+      const uint32_t lane_sel = (uint32_t)(lq * 32) << 16;
+      // ---- softmax over the 176 keys of this row ----
+      mbar_wait(&bars[2 + t], 0);
+      tc_fence_after();
+      uint32_t v[ATC_KP];
+      {
+        const uint32_t ta = tmem + lane_sel + t * ATC_KP;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) tmem_ld32(ta + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+        tmem_ld16(ta + 160, &v[160]);
+        tc_wait_ld();
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < ATC_KP; ++k) {
+        float s = __uint_as_float(v[k]);
+        if (k >= S) s = -INFINITY;  // zero-filled keys beyond the sequence
+        v[k] = __float_as_uint(s);
+        mx = fmaxf(mx, s);
+      }
+      const float c2 = rsqrtf((float)HD) * 1.4426950408889634f;
+      const float mc = -mx * c2;
+      float sum0 = 0.f, sum1 = 0.f;
+      const uint32_t prow = (t ? sP1 : sP0) + r * 128;
+      const uint32_t pblk = t ? C::P1_BLK : C::P0_BLK;
+#pragma unroll
+      for (int c8 = 0; c8 < ATC_KP / 8; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = atc_ex2(fmaf(__uint_as_float(v[c8 * 8 + 2 * e]), c2, mc));
+          const float p1 = atc_ex2(fmaf(__uint_as_float(v[c8 * 8 + 2 * e + 1]), c2, mc));
+          sum0 += p0, sum1 += p1;
+          pk[e] = pack_bf16x2(p0, p1);
+        }
+        atc_sts128(prow + (c8 >> 3) * pblk + (((c8 & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      }
+      const float inv = 1.0f / (sum0 + sum1);
+      tc_fence_before();
+      fence_proxy_async_smem();  // P is read by the tensor core through the async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[4 + t]);
+
+      // ---- O * inv -> bf16 -> warp-private staging (dead Q/K region) -> TMA store ----
+      mbar_wait(&bars[6 + t], 0);
+      tc_fence_after();
+      const uint32_t oa = tmem + lane_sel + (t ? 0u : (uint32_t)ATC_O0_COL);
+      const uint32_t stage = sQ + warp * (NB * 4096);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        uint32_t o[64];
+        tmem_ld32(oa + j * 64, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+        tmem_ld32(oa + j * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+        tc_wait_ld();
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            pk[e] = pack_bf16x2(__uint_as_float(o[c8 * 8 + 2 * e]) * inv, __uint_as_float(o[c8 * 8 + 2 * e + 1]) * inv);
+          atc_sts128(stage + j * 4096 + lane * 128 + ((c8 ^ (lane & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      const int row0 = t * 128 + lq * 32;
+      if (lane == 0 && row0 < S && !(dbg & 1)) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) tma_store_3d(&tmO, stage + j * 4096, h * HD + j * 64, row0, b);
+        bulk_commit();
+        bulk_wait<0>();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) tmem_dealloc(tmem, ATC_TMEM_COLS);
+}
+
+struct AttnTcMaps {
+  CUtensorMap kv, o;
+};
+// qkv bf16 [B*S, 3d] (packed in_proj output), out bf16 [B*S, d]
+inline int make_attn_tc_maps(AttnTcMaps* m, const void* qkv, const void* out, int B, int S, int d) {
+  int rc;
+  const uint64_t ld = (uint64_t)3 * d * 2;
+  if ((rc = make_tmap_3d_bf16(&m->kv, qkv, 3 * (uint64_t)d, S, B, ld, ld * S, ATC_KP))) return rc;
+  if ((rc = make_tmap_3d_bf16(&m->o, out, d, S, B, (uint64_t)d * 2, (uint64_t)d * 2 * S, 32))) return rc;
+  return TAMF_OK;
+}
+
+template <int HD>
+int configure_attn_tc() {
+  TAMF_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       AttnTcCfg<HD>::SMEM_BYTES));
+  return TAMF_OK;
+}
+
+template <int HD>
+int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t stream) {
+  TAMF_REQUIRE(S <= ATC_KP, TAMF_E_BADARG, "attention: at most 176 tokens per sequence");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(H, B);
+  cfg.blockDim = dim3(ATC_THREADS);
+  cfg.dynamicSmemBytes = AttnTcCfg<HD>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  static const int dbg = getenv("TAMF_ATTN_DBG") ? atoi(getenv("TAMF_ATTN_DBG")) : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel<HD>, m.kv, m.o, S, d, dbg);
+  count_launch();
+  if (e != cudaSuccess) {
+    set_error(std::string("attention launch failed: ") + cudaGetErrorString(e));
+    return TAMF_E_CUDA;
+  }
+  return TAMF_OK;
+}
+
+}  // namespace tamf

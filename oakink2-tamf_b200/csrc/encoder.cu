@@ -2,6 +2,7 @@
 #include "encoder.cuh"
 
 #include "attn.cuh"
+#include "attn_tc.cuh"
 #include "gemm.cuh"
 
 namespace tamf {
@@ -204,6 +205,9 @@ int EncoderBuffers::make_maps(int d, int ff) {
   AttnMaps am;
   if ((rc = make_attn_maps(&am, QKV, ATT, B, S, d))) return rc;
   tm_att_kv = am.kv, tm_att_q = am.q, tm_att_o = am.o;
+  AttnTcMaps at;
+  if ((rc = make_attn_tc_maps(&at, QKV, ATT, B, S, d))) return rc;
+  tm_att_o32 = at.o;
   return TAMF_OK;
 }
 
@@ -215,6 +219,8 @@ int configure_encoder_kernels() {
   if ((rc = configure_gemm<512, EPI_RES_LN, 2>())) return rc;
   if ((rc = configure_attn<64>())) return rc;
   if ((rc = configure_attn<128>())) return rc;
+  if ((rc = configure_attn_tc<64>())) return rc;
+  if ((rc = configure_attn_tc<128>())) return rc;
   return TAMF_OK;
 }
 
@@ -230,10 +236,16 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
       if ((rc = launch_gemm<256, EPI_BIAS_BF16, 2>(buf.tm_Xb, w.tm_in, p, s))) return rc;
       mark_event(marks, s);
     }
-    {
+    if (attn_legacy()) {
       AttnMaps am;
       am.kv = buf.tm_att_kv, am.q = buf.tm_att_q, am.o = buf.tm_att_o;
       rc = (d / enc.H == 128) ? launch_attn<128>(am, buf.B, buf.S, enc.H, d, s) : launch_attn<64>(am, buf.B, buf.S, enc.H, d, s);
+      if (rc) return rc;
+    } else {
+      AttnTcMaps at;
+      at.kv = buf.tm_att_kv, at.o = buf.tm_att_o32;
+      rc = (d / enc.H == 128) ? launch_attn_tc<128>(at, buf.B, buf.S, enc.H, d, s)
+                              : launch_attn_tc<64>(at, buf.B, buf.S, enc.H, d, s);
       if (rc) return rc;
     }
     mark_event(marks, s);

@@ -51,6 +51,7 @@ struct EncoderBuffers {
   CUtensorMap tm_Xb, tm_ATT, tm_H;              // GEMM A-operand loads, box {64, 128}
   CUtensorMap tm_QKV_st, tm_H_st;               // bf16 epilogue stores, box {64, 32}
   CUtensorMap tm_Xb_st, tm_Xlo;                 // LayerNorm epilogue: Xb / Xlo residual load + store, box {32, 32} bf16
+  CUtensorMap tm_att_o32;                       // attention (tcgen05 kernel): [B][S][d] view of ATT, 32-row store boxes
   CUtensorMap tm_att_kv, tm_att_q, tm_att_o;    // attention: [B][S][3d] views of QKV (K/V box, Q box), [B][S][d] view of ATT
   int make_maps(int d, int ff);
 };
