@@ -144,6 +144,17 @@ int tamf_denoiser_set_cond(tamf_denoiser* h, const float* text_feat, const int32
 /* x0 = model(x_t, t): x_t, x0_out [B,99,1,T] fp32; t [B] int32 (device). */
 int tamf_denoiser_forward(tamf_denoiser* h, const float* x_t, const int32_t* t, float* x0_out, void* stream);
 
+/* Installs the K-step update rule the sampler entries below run, in place of the ancestral rule given at create:
+ *   x_{i-1} = c1[i] x0 + c2[i] x_i + sigma[i] eps,   x0 = model(x_i, timestep_map[i]),   i = K-1 .. 0.
+ * Covers SpacedDiffusion's strided schedules (respace.py:8-57 space_timesteps, :69-83 re-derived betas, :114-119
+ * timestep_map) with either the ancestral posterior (gaussian_diffusion.py:209-229) or DDIM with any eta
+ * (ddim_sample, gaussian_diffusion.py:642-690: eps re-derived from x0 folds into c1/c2).  HOST fp32 / int32 arrays of
+ * length K <= num_steps; K = 0 restores the ancestral rule.  Synchronises the device; not a hot-path call.
+ * tamf_denoiser_forward is unaffected (it takes ORIGINAL timesteps). */
+int tamf_denoiser_set_sampler(tamf_denoiser* h, int K, const float* c1, const float* c2, const float* sigma,
+                              const int32_t* timestep_map);
+int tamf_denoiser_sampler_steps(const tamf_denoiser* h);
+
 /* One ancestral step p_sample (all rows at the same t):
  *   x_{t-1} = c1[t] x0 + c2[t] x_t + 1[t!=0] exp(0.5 logvar[t]) eps,   x0 = model(x_t, t)
  * x_io is updated in place.  eps = `noise` [B,99,1,T] if non-NULL, else Philox4x32-10(seed, t, element) normals.
@@ -231,6 +242,11 @@ int tamf_gemm_selftest(const uint16_t* a, const uint16_t* w, const float* bias, 
  * nn/functional.py), out device bf16 [B*S, d] = softmax(q k^T / sqrt(hd)) v per (sequence, head), no mask
  * (interaction_segment_mdm.py:63-70,171).  S <= 176, hd = d/H in {64, 128}. */
 int tamf_attn_selftest(const uint16_t* qkv, uint16_t* out, int B, int S, int H, int d, void* stream);
+
+/* Debug aid (tools/attn_trace.py): tamf_attn_selftest with per-CTA clock64 stamps of the kernel's phases,
+ * trace int64 [H*B][16] (device): 0 start, 1 setup done, 2 Q+K landed, 3 V landed, 4/5 P of tile 0/1 ready (MMA thread),
+ * 6/7 scores of tile 0/1 ready, 8/9 O ready, 10/11 tile stored, 12 end, 13 SM id, 14/15 globaltimer start/end. */
+int tamf_attn_trace(const uint16_t* qkv, uint16_t* out, int B, int S, int H, int d, long long* trace, void* stream);
 
 /* Debug aid (tools/gemm_trace.py): one launch of a hot-path GEMM shape with per-CTA clock64 event timestamps.
  * which: 0 = in_proj-like (bias -> bf16), 1 = linear1-like (bias + GELU -> bf16), 2 = LayerNorm GEMM (N = 512).

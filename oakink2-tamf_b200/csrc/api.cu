@@ -4,7 +4,6 @@
 
 #include <mutex>
 
-#include "attn.cuh"
 #include "attn_tc.cuh"
 #include "gemm.cuh"
 
@@ -46,15 +45,6 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
-}
-
-bool attn_legacy() {  // TAMF_ATTN=mma selects the mma.sync attention kernel (A/B measurements only)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TAMF_ATTN");
-    v = (e && e[0] == 'm') ? 1 : 0;
-  }
-  return v == 1;
 }
 
 bool pdl_enabled() {
@@ -215,26 +205,35 @@ extern "C" int tamf_attn_selftest(const uint16_t* qkv, uint16_t* out, int B, int
   int rc = check_device();
   if (rc) return rc;
   TAMF_REQUIRE(qkv && out, TAMF_E_BADARG, "tamf_attn_selftest: null pointer");
-  TAMF_REQUIRE(B > 0 && S > 0 && S <= ATT_KP && H > 0 && d % H == 0 && (d / H == 64 || d / H == 128), TAMF_E_BADARG,
+  TAMF_REQUIRE(B > 0 && S > 0 && S <= ATC_KP && H > 0 && d % H == 0 && (d / H == 64 || d / H == 128), TAMF_E_BADARG,
                "tamf_attn_selftest: need 0 < S <= 176 and head_dim 64 or 128");
-  if (!attn_legacy()) {
-    AttnTcMaps at;
-    if ((rc = make_attn_tc_maps(&at, qkv, out, B, S, d))) return rc;
-    if (d / H == 128) {
-      if ((rc = configure_attn_tc<128>())) return rc;
-      return launch_attn_tc<128>(at, B, S, H, d, stream);
-    }
-    if ((rc = configure_attn_tc<64>())) return rc;
-    return launch_attn_tc<64>(at, B, S, H, d, stream);
-  }
-  AttnMaps am;
-  if ((rc = make_attn_maps(&am, qkv, out, B, S, d))) return rc;
+  AttnTcMaps at;
+  if ((rc = make_attn_tc_maps(&at, qkv, out, B, S, d))) return rc;
   if (d / H == 128) {
-    if ((rc = configure_attn<128>())) return rc;
-    return launch_attn<128>(am, B, S, H, d, stream);
+    if ((rc = configure_attn_tc<128>())) return rc;
+    return launch_attn_tc<128>(at, B, S, H, d, stream);
   }
-  if ((rc = configure_attn<64>())) return rc;
-  return launch_attn<64>(am, B, S, H, d, stream);
+  if ((rc = configure_attn_tc<64>())) return rc;
+  return launch_attn_tc<64>(at, B, S, H, d, stream);
+}
+
+// Debug aid (tools/attn_trace.py): the tcgen05 attention kernel with per-CTA clock64 stamps, trace [H*B][16] int64.
+extern "C" int tamf_attn_trace(const uint16_t* qkv, uint16_t* out, int B, int S, int H, int d, long long* trace,
+                               void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_device();
+  if (rc) return rc;
+  TAMF_REQUIRE(qkv && out && trace, TAMF_E_BADARG, "tamf_attn_trace: null pointer");
+  TAMF_REQUIRE(B > 0 && S > 0 && S <= ATC_KP && H > 0 && d % H == 0 && (d / H == 64 || d / H == 128), TAMF_E_BADARG,
+               "tamf_attn_trace: need 0 < S <= 176 and head_dim 64 or 128");
+  AttnTcMaps at;
+  if ((rc = make_attn_tc_maps(&at, qkv, out, B, S, d))) return rc;
+  if (d / H == 128) {
+    if ((rc = configure_attn_tc<128>())) return rc;
+    return launch_attn_tc<128>(at, B, S, H, d, stream, trace);
+  }
+  if ((rc = configure_attn_tc<64>())) return rc;
+  return launch_attn_tc<64>(at, B, S, H, d, stream, trace);
 }
 
 // Debug aid (tools/gemm_trace.py): one launch of the hot-path GEMM shape `which` on caller data with per-CTA

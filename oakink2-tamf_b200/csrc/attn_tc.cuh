@@ -74,7 +74,12 @@ __device__ __forceinline__ void atc_sts128(uint32_t addr, uint32_t a, uint32_t b
 template <int HD>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmO, int S, int d,
-                   int dbg) {
+                   int dbg, long long* trace) {
+  // debug only (tools/attn_trace.py): per-CTA clock64 stamps [grid][16]; null in the product path
+#define ATC_TRACE(slot)                                                                                   \
+  do {                                                                                                    \
+    if (trace) trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64();           \
+  } while (0)
   using C = AttnTcCfg<HD>;
   constexpr int NB = C::NB;
   extern __shared__ uint8_t atc_raw[];
@@ -86,6 +91,17 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntile = S > 128 ? 2 : 1;
+  if (threadIdx.x == 0) {
+    ATC_TRACE(0);
+    if (trace) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 14] = (long long)gt;
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 13] = smid;
+    }
+  }
 
   if (warp == 6) {
     if (lane == 0) {
@@ -106,6 +122,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   pdl_launch_dependents();
+  if (threadIdx.x == 0) ATC_TRACE(1);
 
   if (warp == 6) {
     if (lane == 0) {
@@ -124,6 +141,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       constexpr uint32_t id_s = umma_idesc_bf16(128, ATC_KP);
       mbar_wait(&bars[0], 0);
       tc_fence_after();
+      ATC_TRACE(2);
       for (int t = 0; t < ntile; ++t) {
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
@@ -136,9 +154,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       // ---- O = P V ----
       constexpr uint32_t id_o = umma_idesc_bf16_bmn(128, HD);
       mbar_wait(&bars[1], 0);
+      ATC_TRACE(3);
       for (int t = 0; t < ntile; ++t) {
         mbar_wait(&bars[4 + t], 0);
         tc_fence_after();
+        ATC_TRACE(4 + t);
         const uint32_t pb = t ? sP1 : sP0, pblk = t ? C::P1_BLK : C::P0_BLK;
         const uint32_t ocol = t ? 0u : (uint32_t)ATC_O0_COL;
 #pragma unroll
@@ -157,6 +177,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       // ---- softmax over the 176 keys of this row ----
       mbar_wait(&bars[2 + t], 0);
       tc_fence_after();
+      if (lane == 0 && lq == 0) ATC_TRACE(6 + t);
       uint32_t v[ATC_KP];
       {
         const uint32_t ta = tmem + lane_sel + t * ATC_KP;
@@ -199,6 +220,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       // ---- O * inv -> bf16 -> warp-private staging (dead Q/K region) -> TMA store ----
       mbar_wait(&bars[6 + t], 0);
       tc_fence_after();
+      if (lane == 0 && lq == 0) ATC_TRACE(8 + t);
       const uint32_t oa = tmem + lane_sel + (t ? 0u : (uint32_t)ATC_O0_COL);
       const uint32_t stage = sQ + warp * (NB * 4096);
 #pragma unroll
@@ -223,12 +245,21 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < NB; ++j) tma_store_3d(&tmO, stage + j * 4096, h * HD + j * 64, row0, b);
         bulk_commit();
-        bulk_wait<0>();
+        bulk_wait_read<0>();  // the staging tile must outlive the store's shared-memory reads; kernel end flushes the writes
       }
+      if (lane == 0 && lq == 0) ATC_TRACE(10 + t);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    ATC_TRACE(12);
+    if (trace) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = (long long)gt;
+    }
+  }
   if (warp == 6) tmem_dealloc(tmem, ATC_TMEM_COLS);
 }
 
@@ -252,7 +283,7 @@ int configure_attn_tc() {
 }
 
 template <int HD>
-int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t stream) {
+int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t stream, long long* trace = nullptr) {
   TAMF_REQUIRE(S <= ATC_KP, TAMF_E_BADARG, "attention: at most 176 tokens per sequence");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(H, B);
@@ -269,7 +300,7 @@ int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t
   cfg.attrs = attr;
   cfg.numAttrs = na;
   static const int dbg = getenv("TAMF_ATTN_DBG") ? atoi(getenv("TAMF_ATTN_DBG")) : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel<HD>, m.kv, m.o, S, d, dbg);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel<HD>, m.kv, m.o, S, d, dbg, trace);
   count_launch();
   if (e != cudaSuccess) {
     set_error(std::string("attention launch failed: ") + cudaGetErrorString(e));

@@ -21,7 +21,7 @@
 //   A0 bf16 [B*T,128] | H0 bf16 [B*T,d] | prefix fp32 [B,4,d] | ttab fp32 [steps,d]
 #include <vector>
 
-#include "attn.cuh"
+#include "attn_tc.cuh"
 #include "encoder.cuh"
 #include "gemm.cuh"
 
@@ -54,6 +54,14 @@ __global__ void a0_cond_kernel(const float* __restrict__ trajmean, __nv_bfloat16
   if (i >= (size_t)rows * (KPAD - TRAJ_COL)) return;
   const int r = (int)(i / (KPAD - TRAJ_COL)), c = (int)(i % (KPAD - TRAJ_COL));
   A0[(size_t)r * KPAD + TRAJ_COL + c] = __float2bfloat16_rn(c < 9 ? trajmean[(size_t)r * 9 + c] : 0.f);
+}
+
+// rows[i] = src[map[i]]  (timestep tokens of a respaced schedule)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ map, float* __restrict__ dst,
+                                   int d) {
+  const float* s = src + (size_t)map[blockIdx.x] * d;
+  float* o = dst + (size_t)blockIdx.x * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) o[c] = s[c];
 }
 
 __global__ void add_int_kernel(int* p, int n, int dv) {
@@ -119,7 +127,13 @@ struct tamf_denoiser {
   __nv_bfloat16 *wfold /*[d,128]*/, *wm2 /*[d,d]*/, *wfin /*[99,d]*/;
   float *b_m2, *b_fin;
   CUtensorMap tm_wfold, tm_wm2, tm_wfin;
-  float *c1, *c2, *sigma;  // [num_steps]
+  float *c1, *c2, *sigma;  // [num_steps] ancestral rule of tamf_denoiser_create
+  // update rule the sampler entries run (tamf_denoiser_set_sampler): K steps, x_{i-1} = k1[i] x0 + k2[i] x_i + ks[i] eps,
+  // timestep token of step i = ttab[timestep_map[i]] gathered into k_ttab.  Defaults to the ancestral rule.
+  float *k1 = nullptr, *k2 = nullptr, *ks = nullptr, *k_ttab = nullptr;
+  float *alt1 = nullptr, *alt2 = nullptr, *alts = nullptr, *alt_ttab = nullptr;
+  int* alt_map = nullptr;
+  int K = 0;
   // bound workspace
   int B = 0, T = 0, S = 0, M = 0, Mf = 0;
   bool bound = false, cond_set = false;
@@ -145,12 +159,15 @@ static int upload_bf16(tamf_denoiser* h, __nv_bfloat16** dst, const float* src, 
 
 // One denoiser evaluation (+ optional posterior update) enqueued on `s`.
 // `marks` (profiling only): one event is recorded after every kernel of the step, in launch order.
+// `model_level`: t_ptr holds ORIGINAL timesteps (model(x, t) of the reference); otherwise indices of the installed
+// K-step rule (what SpacedDiffusion hands to _WrappedModel, respace.py:114-119).
 static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, float* x_out, float* x0_out,
-                        const float* noise, uint64_t seed, cudaStream_t s, std::vector<cudaEvent_t>* marks = nullptr) {
+                        const float* noise, uint64_t seed, cudaStream_t s, std::vector<cudaEvent_t>* marks = nullptr,
+                        bool model_level = false) {
   const int d = h->d, B = h->B, T = h->T, S = h->S, M = h->M, Mf = h->Mf;
   int rc;
   mark_event(marks, s);
-  prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, h->ttab, h->pe, h->prefix, h->A0, h->buf.Xlo, h->buf.Xb, T,
+  prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, model_level ? h->ttab : h->k_ttab, h->pe, h->prefix, h->A0, h->buf.Xlo, h->buf.Xb, T,
                                                      S, d, h->nfeat);
   TAMF_LAUNCH_CHECK();
   mark_event(marks, s);
@@ -171,8 +188,8 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, fl
   {  // final projection + DDPM posterior
     GemmParams p{};
     p.M = M, p.N = h->nfeat, p.K = d, p.bias = h->b_fin, p.T = T, p.S = S, p.P0 = 5, p.nfeat = h->nfeat;
-    p.x_t = x_t, p.x_out = x_out, p.x0_out = x0_out, p.noise = noise, p.t_ptr = t_ptr, p.c1 = h->c1, p.c2 = h->c2,
-    p.sigma = h->sigma, p.seed = seed;
+    p.x_t = x_t, p.x_out = x_out, p.x0_out = x0_out, p.noise = noise, p.t_ptr = t_ptr, p.c1 = h->k1, p.c2 = h->k2,
+    p.sigma = h->ks, p.seed = seed;
     if ((rc = launch_gemm<128, EPI_POSTERIOR, 2>(h->tm_Xb_fin, h->tm_wfin, p, s))) return rc;
     mark_event(marks, s);
   }
@@ -273,6 +290,11 @@ extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w
     TRY(upload_f32(h, &h->c1, c1.data(), n));
     TRY(upload_f32(h, &h->c2, c2.data(), n));
     TRY(upload_f32(h, &h->sigma, sg.data(), n));
+    h->k1 = h->c1, h->k2 = h->c2, h->ks = h->sigma, h->K = n;
+    TRY(dev_alloc(h, (void**)&h->alt1, (size_t)n * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&h->alt2, (size_t)n * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&h->alts, (size_t)n * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&h->alt_map, (size_t)n * sizeof(int)));
   }
   {
     // timestep-token table ttab[t] = time_embed(pe[t]) (TimestepEmbedder, interaction_segment_mdm.py:208-215)
@@ -284,6 +306,8 @@ extern "C" int tamf_denoiser_create(const tamf_cfg* cfg, const tamf_g_weights* w
     const int n = cfg->num_steps;
     TRY(dev_alloc(h, (void**)&tmp, (size_t)n * d * sizeof(float)));
     TRY(dev_alloc(h, (void**)&h->ttab, (size_t)n * d * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&h->alt_ttab, (size_t)n * d * sizeof(float)));
+    h->k_ttab = h->ttab;
     TRY(linear_f32(h->pe, d, t0w, d, t0b, tmp, d, n, d, d, 1, nullptr, 0, nullptr));
     TRY(linear_f32(tmp, d, t2w, d, t2b, h->ttab, d, n, d, d, 0, nullptr, 0, nullptr));
     if (cudaDeviceSynchronize() != cudaSuccess) {
@@ -350,7 +374,7 @@ extern "C" size_t tamf_denoiser_workspace_bytes(const tamf_denoiser* h, int B, i
 extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size_t ws_bytes) {
   TAMF_REQUIRE(h && ws, TAMF_E_BADARG, "tamf_denoiser_bind: null argument");
   TAMF_REQUIRE(B > 0 && T > 0, TAMF_E_BADARG, "tamf_denoiser_bind: B and T must be positive");
-  TAMF_REQUIRE(T + 5 <= ATT_KP, TAMF_E_BADARG, "tamf_denoiser_bind: T + 5 tokens must be <= 176");
+  TAMF_REQUIRE(T + 5 <= ATC_KP, TAMF_E_BADARG, "tamf_denoiser_bind: T + 5 tokens must be <= 176");
   TAMF_REQUIRE(T + 5 <= h->pe_rows, TAMF_E_BADARG, "tamf_denoiser_bind: pe table too short");
   TAMF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, TAMF_E_ALIGN, "workspace must be 256-byte aligned");
   WsLayout L = ws_layout(h, B, T);
@@ -434,15 +458,43 @@ extern "C" int tamf_denoiser_set_cond(tamf_denoiser* h, const float* text_feat, 
 extern "C" int tamf_denoiser_forward(tamf_denoiser* h, const float* x_t, const int32_t* t, float* x0_out, void* stream) {
   TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_denoiser_forward: bind + set_cond first");
   TAMF_REQUIRE(x_t && t && x0_out, TAMF_E_BADARG, "tamf_denoiser_forward: null pointer");
-  return enqueue_step(h, x_t, t, nullptr, x0_out, nullptr, 0, (cudaStream_t)stream);
+  return enqueue_step(h, x_t, t, nullptr, x0_out, nullptr, 0, (cudaStream_t)stream, nullptr, /*model_level=*/true);
 }
+
+extern "C" int tamf_denoiser_set_sampler(tamf_denoiser* h, int K, const float* c1, const float* c2, const float* sigma,
+                                         const int32_t* timestep_map) {
+  TAMF_REQUIRE(h, TAMF_E_BADARG, "tamf_denoiser_set_sampler: null handle");
+  const int n = h->cfg.num_steps;
+  drop_graph(h);  // the captured step has the table pointers baked in
+  if (K == 0) {
+    h->k1 = h->c1, h->k2 = h->c2, h->ks = h->sigma, h->k_ttab = h->ttab, h->K = n;
+    return TAMF_OK;
+  }
+  TAMF_REQUIRE(K >= 1 && K <= n, TAMF_E_BADARG, "tamf_denoiser_set_sampler: need 1 <= K <= num_steps");
+  TAMF_REQUIRE(c1 && c2 && sigma && timestep_map, TAMF_E_BADARG, "tamf_denoiser_set_sampler: null table");
+  for (int i = 0; i < K; ++i)
+    TAMF_REQUIRE(timestep_map[i] >= 0 && timestep_map[i] < n, TAMF_E_BADARG,
+                 "tamf_denoiser_set_sampler: timestep_map entry outside [0, num_steps)");
+  TAMF_CUDA_CHECK(cudaDeviceSynchronize());  // nothing in flight may still read the tables being replaced
+  TAMF_CUDA_CHECK(cudaMemcpy(h->alt1, c1, (size_t)K * 4, cudaMemcpyHostToDevice));
+  TAMF_CUDA_CHECK(cudaMemcpy(h->alt2, c2, (size_t)K * 4, cudaMemcpyHostToDevice));
+  TAMF_CUDA_CHECK(cudaMemcpy(h->alts, sigma, (size_t)K * 4, cudaMemcpyHostToDevice));
+  TAMF_CUDA_CHECK(cudaMemcpy(h->alt_map, timestep_map, (size_t)K * 4, cudaMemcpyHostToDevice));
+  gather_rows_kernel<<<K, 128>>>(h->ttab, h->alt_map, h->alt_ttab, h->d);
+  TAMF_LAUNCH_CHECK();
+  TAMF_CUDA_CHECK(cudaDeviceSynchronize());
+  h->k1 = h->alt1, h->k2 = h->alt2, h->ks = h->alts, h->k_ttab = h->alt_ttab, h->K = K;
+  return TAMF_OK;
+}
+
+extern "C" int tamf_denoiser_sampler_steps(const tamf_denoiser* h) { return h ? h->K : 0; }
 
 extern "C" int tamf_p_sample_step(tamf_denoiser* h, float* x_io, int t, const float* noise, uint64_t seed,
                                   float* x0_out, void* stream_) {
   cudaStream_t s = (cudaStream_t)stream_;
   TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_p_sample_step: bind + set_cond first");
   TAMF_REQUIRE(x_io, TAMF_E_BADARG, "tamf_p_sample_step: null pointer");
-  TAMF_REQUIRE(t >= 0 && t < h->cfg.num_steps, TAMF_E_BADARG, "tamf_p_sample_step: t out of range");
+  TAMF_REQUIRE(t >= 0 && t < h->K, TAMF_E_BADARG, "tamf_p_sample_step: t out of range");
   {
     int rc0 = fill_int(h->t_dev, h->B, t, s);
     if (rc0) return rc0;
@@ -455,7 +507,7 @@ extern "C" int tamf_denoiser_profile_step(tamf_denoiser* h, float* x_io, int t, 
   cudaStream_t s = (cudaStream_t)stream_;
   TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_denoiser_profile_step: bind + set_cond first");
   TAMF_REQUIRE(x_io && ms_out && n_out, TAMF_E_BADARG, "tamf_denoiser_profile_step: null pointer");
-  TAMF_REQUIRE(t >= 0 && t < h->cfg.num_steps, TAMF_E_BADARG, "tamf_denoiser_profile_step: t out of range");
+  TAMF_REQUIRE(t >= 0 && t < h->K, TAMF_E_BADARG, "tamf_denoiser_profile_step: t out of range");
   {
     int rc0 = fill_int(h->t_dev, h->B, t, s);
     if (rc0) return rc0;
@@ -479,8 +531,8 @@ extern "C" int tamf_p_sample_chain(tamf_denoiser* h, float* x_io, int t_start, i
   cudaStream_t s = (cudaStream_t)stream_;
   TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_p_sample_chain: bind + set_cond first");
   TAMF_REQUIRE(x_io, TAMF_E_BADARG, "tamf_p_sample_chain: null pointer");
-  TAMF_REQUIRE(t_start < h->cfg.num_steps && t_end >= 0 && t_end <= t_start, TAMF_E_BADARG,
-               "tamf_p_sample_chain: need num_steps > t_start >= t_end >= 0");
+  TAMF_REQUIRE(t_start < h->K && t_end >= 0 && t_end <= t_start, TAMF_E_BADARG,
+               "tamf_p_sample_chain: need sampler steps > t_start >= t_end >= 0");
   if (!h->graph_exec || h->graph_x != x_io || h->graph_seed != seed || h->graph_stream != s) {
     drop_graph(h);
     cudaStream_t cap = s;
@@ -544,9 +596,9 @@ extern "C" int tamf_p_sample_loop_host(tamf_denoiser* h, const float* text_feat,
   if (x_T) {
     TAMF_CUDA_CHECK(cudaMemcpyAsync(h->xbuf, x_T, nx * 4, cudaMemcpyHostToDevice, s));
   } else {
-    if ((rc = philox_fill(h->xbuf, nx, seed, (uint32_t)c.num_steps, s))) return rc;  // th.randn(*shape), :604
+    if ((rc = philox_fill(h->xbuf, nx, seed, (uint32_t)h->K, s))) return rc;  // th.randn(*shape), :604
   }
-  if ((rc = tamf_p_sample_chain(h, h->xbuf, c.num_steps - 1, 0, seed, s))) return rc;
+  if ((rc = tamf_p_sample_chain(h, h->xbuf, h->K - 1, 0, seed, s))) return rc;
   TAMF_CUDA_CHECK(cudaMemcpyAsync(sample_out, h->xbuf, nx * 4, cudaMemcpyDeviceToHost, s));
   TAMF_CUDA_CHECK(cudaStreamSynchronize(s));
   return TAMF_OK;

@@ -1,7 +1,6 @@
 // encoder.cu -- shared transformer encoder stack (see encoder.cuh) + fp32 conditioning helpers.
 #include "encoder.cuh"
 
-#include "attn.cuh"
 #include "attn_tc.cuh"
 #include "gemm.cuh"
 
@@ -202,12 +201,9 @@ int EncoderBuffers::make_maps(int d, int ff) {
   if ((rc = make_tmap_2d_bf16(&tm_H_st, Hb, ff, M, (uint64_t)ff * 2, 64, 32))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_Xb_st, Xb, d, M, (uint64_t)d * 2, 32, 32))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_Xlo, Xlo, d, M, (uint64_t)d * 2, 32, 32))) return rc;
-  AttnMaps am;
-  if ((rc = make_attn_maps(&am, QKV, ATT, B, S, d))) return rc;
-  tm_att_kv = am.kv, tm_att_q = am.q, tm_att_o = am.o;
   AttnTcMaps at;
   if ((rc = make_attn_tc_maps(&at, QKV, ATT, B, S, d))) return rc;
-  tm_att_o32 = at.o;
+  tm_att_kv = at.kv, tm_att_o = at.o;
   return TAMF_OK;
 }
 
@@ -217,8 +213,6 @@ int configure_encoder_kernels() {
   if ((rc = configure_gemm<256, EPI_BIAS_GELU_BF16, 2>())) return rc;
   if ((rc = configure_gemm<256, EPI_RES_LN, 2>())) return rc;
   if ((rc = configure_gemm<512, EPI_RES_LN, 2>())) return rc;
-  if ((rc = configure_attn<64>())) return rc;
-  if ((rc = configure_attn<128>())) return rc;
   if ((rc = configure_attn_tc<64>())) return rc;
   if ((rc = configure_attn_tc<128>())) return rc;
   return TAMF_OK;
@@ -236,14 +230,9 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
       if ((rc = launch_gemm<256, EPI_BIAS_BF16, 2>(buf.tm_Xb, w.tm_in, p, s))) return rc;
       mark_event(marks, s);
     }
-    if (attn_legacy()) {
-      AttnMaps am;
-      am.kv = buf.tm_att_kv, am.q = buf.tm_att_q, am.o = buf.tm_att_o;
-      rc = (d / enc.H == 128) ? launch_attn<128>(am, buf.B, buf.S, enc.H, d, s) : launch_attn<64>(am, buf.B, buf.S, enc.H, d, s);
-      if (rc) return rc;
-    } else {
+    {
       AttnTcMaps at;
-      at.kv = buf.tm_att_kv, at.o = buf.tm_att_o32;
+      at.kv = buf.tm_att_kv, at.o = buf.tm_att_o;
       rc = (d / enc.H == 128) ? launch_attn_tc<128>(at, buf.B, buf.S, enc.H, d, s)
                               : launch_attn_tc<64>(at, buf.B, buf.S, enc.H, d, s);
       if (rc) return rc;

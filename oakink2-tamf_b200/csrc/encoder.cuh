@@ -7,7 +7,7 @@
 //
 // Per layer, 5 kernels over the token matrix (row = b*S + s):
 //   QKV = Xb . Win^T + b                    tcgen05 GEMM, bf16 out           [M,3d]
-//   ATT = softmax(Q K^T / sqrt(hd)) V       fused attention (attn.cuh)       [M,d]
+//   ATT = softmax(Q K^T / sqrt(hd)) V       fused attention (attn_tc.cuh)       [M,d]
 //   X   = LN1(X + ATT . Wo^T + b)           tcgen05 GEMM, residual+LayerNorm epilogue (X = Xb + Xlo, two bf16 planes)
 //   H   = gelu(Xb . W1^T + b)               tcgen05 GEMM, exact-erf GELU epilogue, bf16 out  [M,ff]
 //   X   = LN2(X + H . W2^T + b)             tcgen05 GEMM, residual+LayerNorm epilogue
@@ -51,8 +51,7 @@ struct EncoderBuffers {
   CUtensorMap tm_Xb, tm_ATT, tm_H;              // GEMM A-operand loads, box {64, 128}
   CUtensorMap tm_QKV_st, tm_H_st;               // bf16 epilogue stores, box {64, 32}
   CUtensorMap tm_Xb_st, tm_Xlo;                 // LayerNorm epilogue: Xb / Xlo residual load + store, box {32, 32} bf16
-  CUtensorMap tm_att_o32;                       // attention (tcgen05 kernel): [B][S][d] view of ATT, 32-row store boxes
-  CUtensorMap tm_att_kv, tm_att_q, tm_att_o;    // attention: [B][S][3d] views of QKV (K/V box, Q box), [B][S][d] view of ATT
+  CUtensorMap tm_att_kv, tm_att_o;    // attention: [B][S][3d] views of QKV (K/V box, Q box), [B][S][d] view of ATT
   int make_maps(int d, int ff);
 };
 

@@ -21,7 +21,7 @@ SYMBOLS = [
     "tamf_p_sample_chain", "tamf_p_sample_loop_host", "tamf_denoiser_profile_step", "tamf_kernel_launch_count", "tamf_philox_normal",
     "tamf_gemm_selftest", "tamf_refiner_create", "tamf_refiner_destroy", "tamf_refiner_workspace_bytes",
     "tamf_refiner_bind", "tamf_refiner_forward", "tamf_mano_fk_select", "tamf_vertex_normals", "tamf_gemm_trace",
-    "tamf_attn_selftest",
+    "tamf_attn_selftest", "tamf_attn_trace", "tamf_denoiser_set_sampler", "tamf_denoiser_sampler_steps",
 ]
 
 
@@ -101,6 +101,9 @@ def lib() -> C.CDLL:
     L.tamf_vertex_normals.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.tamf_gemm_trace.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     L.tamf_attn_selftest.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.tamf_denoiser_set_sampler.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.tamf_denoiser_sampler_steps.argtypes = [vp]
+    L.tamf_attn_trace.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     _lib = L
     return L
 

@@ -104,6 +104,7 @@ class InterationSegmentMDM(nn.Module):
         self._ws = None
         self._bound = None
         self._cond_key = None
+        self._rule_key = None
         self._keep = []
 
     # ---- reference surface ----
@@ -144,7 +145,7 @@ class InterationSegmentMDM(nn.Module):
     def _drop_handle(self):
         if self._handle is not None:
             _lib.lib().tamf_denoiser_destroy(self._handle)
-        self._handle, self._bound, self._cond_key, self._ws = None, None, None, None
+        self._handle, self._bound, self._cond_key, self._ws, self._rule_key = None, None, None, None, None
 
     def __del__(self):
         try:
@@ -248,6 +249,27 @@ class InterationSegmentMDM(nn.Module):
         return out
 
     # ---- fused sampler entry points used by tamf_b200.diffusion ----
+    def set_sampler_rule(self, key, c1, c2, sigma, timestep_map, original_num_steps):
+        """Installs x_{i-1} = c1[i] x0 + c2[i] x_i + sigma[i] eps with model timesteps timestep_map[i]
+        (tamf_denoiser_set_sampler); `key` identifies the rule so that repeated calls are free."""
+        dev = next(self.parameters()).device
+        self._ensure_handle(dev)
+        if self._rule_key == key:
+            return
+        if original_num_steps != self._diffusion.num_timesteps:
+            raise ValueError(f"diffusion process has {original_num_steps} base steps, the model was built for "
+                             f"{self._diffusion.num_timesteps}")
+        f32 = lambda t: torch.as_tensor(t).detach().to("cpu", torch.float32).contiguous()
+        c1, c2, sigma = f32(c1), f32(c2), f32(sigma)
+        tmap = torch.tensor(list(timestep_map), dtype=torch.int32)
+        K = int(tmap.numel())
+        if not (c1.numel() == c2.numel() == sigma.numel() == K):
+            raise ValueError("sampler tables and timestep_map must have the same length")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().tamf_denoiser_set_sampler(self._handle, K, _lib.ptr(c1), _lib.ptr(c2), _lib.ptr(sigma),
+                                                            _lib.ptr(tmap)), "tamf_denoiser_set_sampler")
+        self._rule_key = key
+
     def p_sample_step(self, x, t: int, batch, noise=None, seed: int = 0):
         B, _, _, T = x.shape
         dev = x.device

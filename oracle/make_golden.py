@@ -46,9 +46,59 @@ def golden_g(ref, arch: str, B: int, T: int, nobj: int, ragged: bool, steps, tag
     return model, sd, batch, out
 
 
+def golden_spaced(ref):
+    """Strided / DDIM samplers of the reference (respace.py:8-111, gaussian_diffusion.py:642-690): kept timesteps,
+    re-derived tables, ddim_sample / p_sample of a 50-step process at a few indices with given noise, and a free
+    4-step DDIM chain.  Model = the arch_mdm reference module on the g_arch_mdm inputs."""
+    cfg = synth.ARCH["arch_mdm"]
+    model = ref.mdm.InterationSegmentMDM(**cfg)
+    model.eval()
+    model.load_state_dict(synth.g_state_dict(cfg, seed=0), strict=False)
+    B, T = 3, 48
+    batch = synth.make_batch(B, T, nobj=3, seed=11, ragged=True)
+    x = torch.randn(B, 99, 1, T, generator=torch.Generator().manual_seed(5))
+    gd, respace = ref.gd, ref.respace
+    out = {"B": B, "T": T, "noise_seed": 77}
+    for spec in ("ddim50", "ddim25", "100", "10,20,30"):
+        out["steps_" + spec.replace(",", "_")] = np.array(sorted(respace.space_timesteps(1000, spec)))
+    betas = gd.get_named_beta_schedule("cosine", 1000, 1.0)
+    d50 = respace.SpacedDiffusion(use_timesteps=respace.space_timesteps(1000, "ddim50"), betas=betas,
+                                  model_mean_type=gd.ModelMeanType.START_X, model_var_type=gd.ModelVarType.FIXED_SMALL,
+                                  loss_type=gd.LossType.MSE, rescale_timesteps=False)
+    out["map50"] = np.array(d50.timestep_map)
+    for k in ("betas", "alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped"):
+        out["d50_" + k] = getattr(d50, k)
+    orig = gd.th.randn_like
+    mk = {"batch": batch}
+    with torch.no_grad():
+        for eta in (0.0, 0.5):
+            for i in (49, 20, 1, 0):
+                gd.th.randn_like = lambda z, _i=i: synth.step_noise(77, _i, tuple(z.shape))
+                o = d50.ddim_sample(model, x, torch.full((B,), i, dtype=torch.long), clip_denoised=False,
+                                    model_kwargs=mk, eta=eta)
+                out[f"ddim_eta{eta}_i{i}"] = o["sample"].numpy()
+                if eta == 0.0:
+                    out[f"x0_i{i}"] = o["pred_xstart"].numpy()
+        for i in (49, 0):
+            gd.th.randn_like = lambda z, _i=i: synth.step_noise(77, _i, tuple(z.shape))
+            out[f"anc_i{i}"] = d50.p_sample(model, x, torch.full((B,), i, dtype=torch.long), clip_denoised=False,
+                                            model_kwargs=mk)["sample"].numpy()
+        img = x.clone()
+        for i in (3, 2, 1, 0):
+            gd.th.randn_like = lambda z, _i=i: synth.step_noise(77, _i, tuple(z.shape))
+            img = d50.ddim_sample(model, img, torch.full((B,), i, dtype=torch.long), clip_denoised=False, model_kwargs=mk,
+                                  eta=0.5)["sample"]
+        out["ddim_chain_3_0_eta0.5"] = img.numpy()
+    gd.th.randn_like = orig
+    np.savez_compressed(os.path.join(OUT, "spaced_arch_mdm.npz"), **out)
+    print("wrote spaced_arch_mdm")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shims.install()
+    if len(sys.argv) > 1 and sys.argv[1] == "spaced":
+        return golden_spaced(ref)
 
     # ---- G forward: arch_mdm ragged objects (pins the padded-mean quirk), 4 timesteps ----
     model, sd, batch, g = golden_g(ref, "arch_mdm", B=3, T=48, nobj=3, ragged=True, steps=[999, 500, 1, 0], tag="arch_mdm")
@@ -118,6 +168,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "r_arch_refine.npz"), B=B, T=T, P=P, batch_seed=2, weight_seed=0,
                         **{k: ro[k].numpy() for k in keep})
     print("wrote r_arch_refine")
+    golden_spaced(ref)
 
 
 if __name__ == "__main__":

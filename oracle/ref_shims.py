@@ -205,6 +205,7 @@ def install(clip_seed: int = 1234):
     import oakink2_tamf.model.segment_refine_model as refine
     import oakink2_tamf.model.diffusion_util as diffusion_util
     import oakink2_tamf.model.diffusion.gaussian_diffusion as gd
+    import oakink2_tamf.model.diffusion.respace as respace
     import oakink2_tamf.model.loss.chamfer_distance as p2p
     import dev_fn.transform.rotation as rotation
     import dev_fn.transform.transform as transform
@@ -216,6 +217,7 @@ def install(clip_seed: int = 1234):
         refine=refine,
         diffusion_util=diffusion_util,
         gd=gd,
+        respace=respace,
         p2p=p2p,
         rotation=rotation,
         transform=transform,
