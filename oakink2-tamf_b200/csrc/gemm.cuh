@@ -86,7 +86,9 @@ struct GemmParams {
   const CUtensorMap* tmX;
   // debug only (tools/gemm_trace.py): per-CTA event timestamps, [grid][GEMM_TRACE_SLOTS] clock64 values; null in product
   long long* trace;
-  int dbg;  // debug only: 1 skip global stores, 2 skip staging, 4 skip the whole epilogue body (bf16 epilogues)
+  int dbg;  // debug only: 1 skip global stores, 2 skip staging, 4 skip the whole epilogue body (bf16 epilogues),
+            // 16 stop streaming W after the first ring fill (probe: the mainloop rate does not change, so TMA writes
+            // into shared memory are not what bounds it)
 };
 
 constexpr int GEMM_TRACE_SLOTS = 64;
@@ -352,11 +354,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           uint8_t* b_dst = sB + stage * Cfg::B_BYTES;
           if constexpr (CG == 2) {
             const uint32_t bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const bool skip_w = (p.dbg & 16) && (it > 0 || kb >= STAGES);  // probe: W stays whatever the ring holds
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], skip_w ? 2 * Cfg::A_BYTES : 2 * Cfg::STAGE_BYTES);
             tma_load_2d_2sm(a_dst, &tmA, bar, kb * BK, m0);
 #pragma unroll
             for (int h = 0; h < NH; ++h)
-              tma_load_2d_2sm(b_dst + h * Cfg::BOX_B * BK * 2, &tmB, bar, kb * BK, n0 + h * UN + (int)rank * Cfg::BOX_B);
+              if (!skip_w)
+                tma_load_2d_2sm(b_dst + h * Cfg::BOX_B * BK * 2, &tmB, bar, kb * BK, n0 + h * UN + (int)rank * Cfg::BOX_B);
             // (no arrive from the peer: a remote release-arrive blocks ~1500 cycles per k-block; the peer's bytes are
             //  already accounted for by the leader's expect_tx, and its loads for the next use of a slot cannot be
             //  issued before the multicast commit that follows the completion of this phase)
