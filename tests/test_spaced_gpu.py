@@ -96,3 +96,53 @@ def test_ddim_loop_graph_chain():
     assert torch.equal(c, e) and not torch.equal(a, c)
     with pytest.raises(NotImplementedError):
         d.ddim_sample_loop(m, (B, 99, 1, T), model_kwargs={"batch": batch}, dump_steps=[1])
+
+
+def test_full_ddim50_chain_vs_oracle():
+    """The WHOLE 50-step DDIM chain (eta = 0, free running: every step consumes the previous CUDA result) against the
+    fp32 oracle run live on the CPU with the same x_T -- end-to-end drift of the bf16 path over a complete chain."""
+    import tamf_b200
+    from oracle import tamf_oracle as orc
+    from tamf_b200 import synth
+    m, cfg = _model("arch_mdm")
+    B, T = 2, 32
+    batch = synth.make_batch(B, T, nobj=2, seed=8)
+    xT = torch.randn(B, 99, 1, T, generator=torch.Generator().manual_seed(2))
+    d = tamf_b200.create_gaussian_diffusion(1000, "cosine", timestep_respacing="ddim50")
+    out = d.ddim_sample_loop(m, (B, 99, 1, T), noise=xT.cuda(), clip_denoised=False,
+                             model_kwargs={"batch": _dev_batch(batch)}, eta=0.0).cpu()
+    c1, c2, _ = d.ddim_rule(0.0)
+    sd, text = synth.g_state_dict(cfg, 0), synth.text_features(batch["text"])
+    x = xT.clone()
+    with torch.no_grad():
+        for i in range(49, -1, -1):
+            ts = torch.full((B,), d.timestep_map[i], dtype=torch.long)
+            x = c1[i] * orc.g_forward(sd, cfg, x, ts, batch, text) + c2[i] * x
+    r = rel_l2(out.numpy(), x.numpy())
+    print(f"ddim50 full chain rel_l2={r:.3e}")
+    assert r <= 2 * REL_TOL
+
+
+def test_ancestral_200_step_chain_vs_oracle():
+    """200 free-running ancestral steps t = 199..0 with the SAME per-step noise on both sides (synth.step_noise)."""
+    import tamf_b200
+    from oracle import tamf_oracle as orc
+    from tamf_b200 import synth
+    m, cfg = _model("arch_mdm")
+    B, T = 2, 24
+    shape = (B, 99, 1, T)
+    batch = synth.make_batch(B, T, nobj=1, seed=9)
+    dbatch = _dev_batch(batch)
+    x0 = torch.randn(*shape, generator=torch.Generator().manual_seed(4))
+    full = tamf_b200.create_gaussian_diffusion(1000, "cosine")
+    full._install(m, "ancestral")
+    g = x0.cuda()
+    for t in range(199, -1, -1):
+        g = m.p_sample_step(g, t, dbatch, noise=synth.step_noise(31, t, shape))["sample"]
+    sd, text = synth.g_state_dict(cfg, 0), synth.text_features(batch["text"])
+    with torch.no_grad():
+        ref = orc.p_sample_loop(sd, cfg, batch, text, shape, lambda t, s: synth.step_noise(31, t, s), x_T=x0,
+                                t_start=199, t_end=0)
+    r = rel_l2(g.cpu().numpy(), ref.numpy())
+    print(f"ancestral 200-step chain rel_l2={r:.3e}")
+    assert r <= 2 * REL_TOL
