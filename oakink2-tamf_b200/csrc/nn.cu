@@ -250,6 +250,292 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Exact search with block pruning (fused h2o mode, P <= 8192 points per object).
+//
+// The brute-force scan above spends 6 instructions on each of the 778 x 8192 (query, candidate) pairs of a frame and
+// object.  A rigid transform preserves distances, so blocks of candidates can be rejected in the OBJECT frame:
+//   build (once per call and object):  Morton-sort the canonical cloud, cut it into blocks of 64 consecutive points,
+//                                      keep each block's bounding box;
+//   query (CTA per frame and object):  stage the sorted cloud moved to the world exactly like the scan kernel does;
+//     one WARP per hand vertex: q' = R^T (v - t); lower bound LB of |q' - p| to every block box (lanes over blocks);
+//     evaluate the block with the smallest LB -> first upper bound `best`; then only blocks with
+//         LB <= best (1 + 1e-3) + margin
+//     are evaluated (lanes over candidates).  Evaluated candidates use the WORLD points and the scan kernel's
+//     arithmetic, so the distances -- and, with the (d2, lowest index) rule, the indices -- are bit-identical to the
+//     exhaustive scan.  A rejected block holds only points strictly farther than the final minimum: the margin
+//     (1e-3 relative + 2e-5 of the coordinate magnitudes) is >= 10x the fp32 error of the transform, of q' and of a
+//     rot6d rotation's deviation from orthonormality; if R R^T differs from I by more than 1e-4 (degenerate rot6d)
+//     nothing is rejected.
+// ------------------------------------------------------------------------------------------------
+constexpr int NNP_BS = 64;          // candidates per block
+constexpr int NNP_MAXP = 8192;      // points per object handled by the pruned path
+constexpr int NNP_QWARPS = 24;      // query warps per CTA
+constexpr unsigned NNP_PAD = 0xFFFFFFFFu;
+
+__device__ __forceinline__ unsigned nnp_spread3(unsigned v) {  // 10 bits -> every third bit
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+// grid = objects; block 1024.  sorted [obj][Ppad] float4 (x, y, z, original index bits; pads = +inf / NNP_PAD),
+// boxes [obj][2 * (nblk + 1)] float4: lo/hi of each block, then lo/hi of the whole cloud.
+__global__ void __launch_bounds__(1024) nnp_build_kernel(const float* __restrict__ pts, int P, int Ppad, int np2,
+                                                         float4* __restrict__ sorted, float4* __restrict__ boxes) {
+  extern __shared__ unsigned long long keys[];  // np2
+  __shared__ float red[6][32];
+  __shared__ float bb[6];
+  const int o = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* po = pts + (size_t)o * P * 3;
+  const float inf = __int_as_float(0x7f800000);
+  float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  for (int i = tid; i < P; i += blockDim.x)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float c = po[3 * i + a];
+      lo[a] = fminf(lo[a], c), hi[a] = fmaxf(hi[a], c);
+    }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], sft));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], sft));
+    }
+    if (lane == 0) red[a][warp] = lo[a], red[3 + a][warp] = hi[a];
+  }
+  __syncthreads();
+  if (tid < 6) {
+    float v = red[tid][0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = tid < 3 ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
+    bb[tid] = v;
+  }
+  __syncthreads();
+  float scale[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float ext = bb[3 + a] - bb[a];
+    scale[a] = (ext > 0.f && ext < inf) ? 1023.0f / ext : 0.f;
+  }
+  for (int i = tid; i < np2; i += blockDim.x) {
+    unsigned long long k = ~0ull;
+    if (i < P) {
+      unsigned key = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float f = (po[3 * i + a] - bb[a]) * scale[a];
+        const unsigned c = (f >= 0.f) ? (unsigned)fminf(f, 1023.0f) : 0u;  // NaN -> 0
+        key |= nnp_spread3(c) << a;
+      }
+      k = ((unsigned long long)key << 32) | (unsigned)i;
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < np2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) keys[i] = b, keys[ixj] = a;
+        }
+      }
+      __syncthreads();
+    }
+  float4* so = sorted + (size_t)o * Ppad;
+  for (int j = tid; j < Ppad; j += blockDim.x) {
+    float4 v = make_float4(inf, inf, inf, __uint_as_float(NNP_PAD));
+    if (j < P) {
+      const unsigned i = (unsigned)keys[j];
+      v = make_float4(po[3 * i], po[3 * i + 1], po[3 * i + 2], __uint_as_float(i));
+    }
+    so[j] = v;
+  }
+  const int nblk = Ppad / NNP_BS;
+  float4* bo = boxes + (size_t)o * 2 * (nblk + 1);
+  for (int b = warp; b < nblk; b += (int)(blockDim.x >> 5)) {
+    float l[3] = {inf, inf, inf}, h[3] = {-inf, -inf, -inf};
+#pragma unroll
+    for (int e = 0; e < NNP_BS / 32; ++e) {
+      const int j = b * NNP_BS + e * 32 + lane;
+      if (j < P) {
+        const unsigned i = (unsigned)keys[j];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float c = po[3 * i + a];
+          l[a] = fminf(l[a], c), h[a] = fmaxf(h[a], c);
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int sft = 16; sft; sft >>= 1) {
+        l[a] = fminf(l[a], __shfl_xor_sync(0xffffffffu, l[a], sft));
+        h[a] = fmaxf(h[a], __shfl_xor_sync(0xffffffffu, h[a], sft));
+      }
+    if (lane == 0) bo[2 * b] = make_float4(l[0], l[1], l[2], 0.f), bo[2 * b + 1] = make_float4(h[0], h[1], h[2], 0.f);
+  }
+  if (tid == 0) {
+    bo[2 * nblk] = make_float4(bb[0], bb[1], bb[2], 0.f);
+    bo[2 * nblk + 1] = make_float4(bb[3], bb[4], bb[5], 0.f);
+  }
+}
+
+__device__ __forceinline__ float nnp_d2(float qx, float qy, float qz, const float4& c) {  // the scan kernel's arithmetic
+  const float dx = __fsub_rn(qx, c.x), dy = __fsub_rn(qy, c.y), dz = __fsub_rn(qz, c.z);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// grid (B*T, max objects per sequence); block (NNP_QWARPS * 32).  Dynamic shared memory: world points float4[Ppad],
+// block boxes float4[2 * nblk].
+__global__ void __launch_bounds__(NNP_QWARPS * 32, 1)
+    h2o_pruned_kernel(const float* __restrict__ verts, const float* __restrict__ obj_traj,
+                      const float4* __restrict__ sorted, const float4* __restrict__ boxes,
+                      const int* __restrict__ obj_first, int T, int V, int nobj_max, int P, int Ppad,
+                      unsigned long long* __restrict__ packed) {
+  extern __shared__ float4 nnp_smem[];
+  __shared__ float sR[12];
+  __shared__ float s_boxmax;
+  __shared__ int s_prune;
+  const int f = blockIdx.x, b = f / T, t = f % T, o = blockIdx.y;
+  const int first = obj_first[b], nobj = obj_first[b + 1] - first;
+  if (o >= nobj) return;
+  const int nblk = Ppad / NNP_BS;
+  float4* wp = nnp_smem;
+  float4* sbox = nnp_smem + Ppad;
+  const float4* so = sorted + (size_t)(first + o) * Ppad;
+  const float4* bo = boxes + (size_t)(first + o) * 2 * (nblk + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float inf = __int_as_float(0x7f800000);
+  if (tid == 0) {
+    const float* tr = obj_traj + (((size_t)b * nobj_max + o) * T + t) * 9;
+    float R[9];
+    rot6d_rows(tr + 3, R);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sR[k] = R[k];
+    sR[9] = tr[0], sR[10] = tr[1], sR[11] = tr[2];
+    float dev = 0.f;  // || R R^T - I ||_max
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i; j < 3; ++j) {
+        const float g = R[3 * i] * R[3 * j] + R[3 * i + 1] * R[3 * j + 1] + R[3 * i + 2] * R[3 * j + 2];
+        dev = fmaxf(dev, fabsf(g - (i == j ? 1.f : 0.f)));
+      }
+    s_prune = (dev <= 1e-4f) ? 1 : 0;  // NaN -> 0
+    const float4 l = bo[2 * nblk], h = bo[2 * nblk + 1];
+    s_boxmax = fmaxf(fmaxf(fmaxf(fabsf(l.x), fabsf(l.y)), fabsf(l.z)), fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fabsf(h.z)));
+  }
+  __syncthreads();
+  for (int j = tid; j < Ppad; j += blockDim.x) {
+    float4 c = so[j];
+    if (__float_as_uint(c.w) != NNP_PAD) {
+      // transf_point_array: R p + t  (src/dev_fn/transform/transform.py:36-53) -- same operations as h2o_scan_kernel
+      const float wx = fmaf(sR[2], c.z, fmaf(sR[1], c.y, sR[0] * c.x)) + sR[9];
+      const float wy = fmaf(sR[5], c.z, fmaf(sR[4], c.y, sR[3] * c.x)) + sR[10];
+      const float wz = fmaf(sR[8], c.z, fmaf(sR[7], c.y, sR[6] * c.x)) + sR[11];
+      c.x = wx, c.y = wy, c.z = wz;
+    }
+    wp[j] = c;
+  }
+  for (int j = tid; j < 2 * nblk; j += blockDim.x) sbox[j] = bo[j];
+  __syncthreads();
+
+  const bool prune = s_prune != 0;
+  const float tmax = fmaxf(fmaxf(fabsf(sR[9]), fabsf(sR[10])), fabsf(sR[11]));
+  const float* xn = verts + (size_t)f * V * 3;
+  constexpr int KMAX = NNP_MAXP / NNP_BS / 32;  // block-LB registers per lane (4)
+  for (int q = warp; q < V; q += NNP_QWARPS) {
+    const float vx = xn[3 * q], vy = xn[3 * q + 1], vz = xn[3 * q + 2];
+    // the query in the object frame
+    const float ux = vx - sR[9], uy = vy - sR[10], uz = vz - sR[11];
+    const float px = sR[0] * ux + sR[3] * uy + sR[6] * uz;
+    const float py = sR[1] * ux + sR[4] * uy + sR[7] * uz;
+    const float pz = sR[2] * ux + sR[5] * uy + sR[8] * uz;
+    const float mag = fmaxf(fmaxf(fmaxf(fabsf(vx), fabsf(vy)), fabsf(vz)),
+                            fmaxf(fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz)), fmaxf(tmax, s_boxmax)));
+    const float absm = 2e-5f * mag + 1e-30f;
+    float lb[KMAX];
+    float lmin = inf;
+    int lblk = -1;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int blk = k * 32 + lane;
+      lb[k] = inf;
+      if (blk < nblk) {
+        const float4 l = sbox[2 * blk], h = sbox[2 * blk + 1];
+        const float dx = fmaxf(fmaxf(l.x - px, px - h.x), 0.f);
+        const float dy = fmaxf(fmaxf(l.y - py, py - h.y), 0.f);
+        const float dz = fmaxf(fmaxf(l.z - pz, pz - h.z), 0.f);
+        lb[k] = dx * dx + dy * dy + dz * dz;
+        if (lb[k] < lmin || lblk < 0) lmin = lb[k], lblk = blk;  // NaN bounds: the lane keeps its first block
+      }
+    }
+    // warp argmin of the block bounds (any block is a valid start; a NaN never wins a `<`)
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, lmin, sft);
+      const int ob = __shfl_xor_sync(0xffffffffu, lblk, sft);
+      if (ob >= 0 && (lblk < 0 || om < lmin || (om == lmin && ob < lblk))) lmin = om, lblk = ob;
+    }
+    const int fb = lblk;  // warp-uniform
+    float bd = inf;
+    unsigned bi = NNP_PAD;
+    auto eval_block = [&](int blk) {
+#pragma unroll
+      for (int e = 0; e < NNP_BS / 32; ++e) {
+        const float4 c = wp[blk * NNP_BS + e * 32 + lane];
+        const float d = nnp_d2(vx, vy, vz, c);
+        const unsigned ci = __float_as_uint(c.w);
+        if (d < bd || (d == bd && bi != NNP_PAD && ci < bi)) bd = d, bi = ci;
+      }
+    };
+    auto warp_min = [&]() {
+      float m = bd;
+#pragma unroll
+      for (int sft = 16; sft; sft >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, sft));
+      return m;
+    };
+    eval_block(fb);
+    float bound2 = inf;
+    if (prune) {
+      const float r = sqrtf(warp_min()) * 1.001f + absm;
+      bound2 = r * r;
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int blk = k * 32 + lane;
+      const bool want = blk < nblk && blk != fb && !(lb[k] > bound2);
+      unsigned m = __ballot_sync(0xffffffffu, want);
+      const bool any = m != 0;
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        eval_block(k * 32 + bit);
+      }
+      if (any && prune && k + 1 < KMAX) {  // tighten the bound for the remaining groups
+        const float r = sqrtf(warp_min()) * 1.001f + absm;
+        bound2 = r * r;
+      }
+    }
+    // lexicographic (d2, index) minimum over the lanes
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, sft);
+      const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, sft);
+      if (oi != NNP_PAD && (bi == NNP_PAD || od < bd || (od == bd && oi < bi))) bd = od, bi = oi;
+    }
+    if (lane == 0 && bi != NNP_PAD) nn_publish(packed + (size_t)f * V + q, bd, o * P + (int)bi);
+  }
+}
+
 // packed -> (d2 | dist, idx) in place
 __global__ void nn_finalize_kernel(unsigned long long* __restrict__ packed, float* __restrict__ d_out, size_t n,
                                    int take_sqrt) {
@@ -301,9 +587,9 @@ extern "C" int tamf_nn_query(const float* x, const float* y, int N, int P1, int 
   return TAMF_OK;
 }
 
-extern "C" int tamf_h2o_dist(const float* verts, const float* obj_traj, const float* obj_points,
-                             const int32_t* obj_first_host, int B, int T, int V, int nobj_max, int P, float* dist,
-                             int64_t* idx, void* stream_) {
+static int h2o_dist_impl(const float* verts, const float* obj_traj, const float* obj_points,
+                         const int32_t* obj_first_host, int B, int T, int V, int nobj_max, int P, float* dist,
+                         int64_t* idx, void* stream_, bool exhaustive) {
   cudaStream_t stream = (cudaStream_t)stream_;
   TAMF_REQUIRE(B > 0 && T > 0 && V > 0 && P > 0 && nobj_max > 0, TAMF_E_BADARG, "tamf_h2o_dist: bad size");
   TAMF_REQUIRE(verts && obj_traj && obj_points && obj_first_host && dist && idx, TAMF_E_BADARG,
@@ -330,15 +616,62 @@ extern "C" int tamf_h2o_dist(const float* verts, const float* obj_traj, const fl
   TAMF_CUDA_CHECK(cudaMemcpyAsync(d_first, obj_first_host, sizeof(int) * (size_t)(B + 1), cudaMemcpyHostToDevice, stream));
   const size_t total = (size_t)B * T * V;
   TAMF_CUDA_CHECK(cudaMemsetAsync(idx, 0xFF, total * sizeof(int64_t), stream));
-  int threads = ((V + NN_QPT - 1) / NN_QPT + 31) / 32 * 32;
-  int P2 = max_nobj * P;
-  int splits = pick_splits(B * T, P2);
-  int per_split = ((P2 + splits - 1) / splits + 3) / 4 * 4;
-  splits = (P2 + per_split - 1) / per_split;
-  h2o_scan_kernel<<<dim3(B * T, splits), threads, 0, stream>>>(verts, obj_traj, obj_points, d_first, T, V, nobj_max, P,
-                                                               per_split, (unsigned long long*)idx);
-  TAMF_LAUNCH_CHECK();
+  static const bool env_exhaustive = getenv("TAMF_NN_EXHAUSTIVE") && getenv("TAMF_NN_EXHAUSTIVE")[0] == '1';
+  if (!exhaustive && !env_exhaustive && P <= NNP_MAXP) {
+    // block-pruned exact search: sorted clouds + block boxes live in a grow-only per-thread device scratch
+    const int total_obj = obj_first_host[B];
+    const int Ppad = (P + NNP_BS - 1) / NNP_BS * NNP_BS, nblk = Ppad / NNP_BS;
+    int np2 = 64;
+    while (np2 < P) np2 <<= 1;
+    const size_t need = ((size_t)total_obj * Ppad + (size_t)total_obj * 2 * (nblk + 1)) * sizeof(float4);
+    static thread_local void* d_scratch = nullptr;
+    static thread_local size_t d_scratch_cap = 0;
+    if (d_scratch_cap < need) {
+      if (d_scratch) {
+        TAMF_CUDA_CHECK(cudaDeviceSynchronize());
+        cudaFree(d_scratch);
+        d_scratch = nullptr, d_scratch_cap = 0;
+      }
+      TAMF_CUDA_CHECK(cudaMalloc(&d_scratch, need));
+      d_scratch_cap = need;
+    }
+    float4* d_sorted = (float4*)d_scratch;
+    float4* d_boxes = d_sorted + (size_t)total_obj * Ppad;
+    static bool configured = false;
+    if (!configured) {
+      TAMF_CUDA_CHECK(cudaFuncSetAttribute(nnp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NNP_MAXP * 8));
+      TAMF_CUDA_CHECK(cudaFuncSetAttribute(h2o_pruned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (NNP_MAXP + 2 * (NNP_MAXP / NNP_BS)) * (int)sizeof(float4)));
+      configured = true;
+    }
+    nnp_build_kernel<<<total_obj, 1024, (size_t)np2 * 8, stream>>>(obj_points, P, Ppad, np2, d_sorted, d_boxes);
+    TAMF_LAUNCH_CHECK();
+    h2o_pruned_kernel<<<dim3(B * T, max_nobj), NNP_QWARPS * 32, (size_t)(Ppad + 2 * nblk) * sizeof(float4), stream>>>(
+        verts, obj_traj, d_sorted, d_boxes, d_first, T, V, nobj_max, P, Ppad, (unsigned long long*)idx);
+    TAMF_LAUNCH_CHECK();
+  } else {
+    int threads = ((V + NN_QPT - 1) / NN_QPT + 31) / 32 * 32;
+    int P2 = max_nobj * P;
+    int splits = pick_splits(B * T, P2);
+    int per_split = ((P2 + splits - 1) / splits + 3) / 4 * 4;
+    splits = (P2 + per_split - 1) / per_split;
+    h2o_scan_kernel<<<dim3(B * T, splits), threads, 0, stream>>>(verts, obj_traj, obj_points, d_first, T, V, nobj_max, P,
+                                                                 per_split, (unsigned long long*)idx);
+    TAMF_LAUNCH_CHECK();
+  }
   nn_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((unsigned long long*)idx, dist, total, 1);
   TAMF_LAUNCH_CHECK();
   return TAMF_OK;
+}
+
+extern "C" int tamf_h2o_dist(const float* verts, const float* obj_traj, const float* obj_points,
+                             const int32_t* obj_first_host, int B, int T, int V, int nobj_max, int P, float* dist,
+                             int64_t* idx, void* stream) {
+  return h2o_dist_impl(verts, obj_traj, obj_points, obj_first_host, B, T, V, nobj_max, P, dist, idx, stream, false);
+}
+
+extern "C" int tamf_h2o_dist_exhaustive(const float* verts, const float* obj_traj, const float* obj_points,
+                                        const int32_t* obj_first_host, int B, int T, int V, int nobj_max, int P,
+                                        float* dist, int64_t* idx, void* stream) {
+  return h2o_dist_impl(verts, obj_traj, obj_points, obj_first_host, B, T, V, nobj_max, P, dist, idx, stream, true);
 }

@@ -75,9 +75,12 @@ def point2point_signed(x, y, x_normals=None, y_normals=None):
     return y2x_signed, x2y_signed, yidx_near
 
 
-def h2o_dist(verts: torch.Tensor, obj_traj: torch.Tensor, obj_points_list, return_idx: bool = False):
+def h2o_dist(verts: torch.Tensor, obj_traj: torch.Tensor, obj_points_list, return_idx: bool = False,
+             exhaustive: bool = False):
     """Fused `SegmentRefineModel.multi_object_h2o_dist` (segment_refine_model.py:142-168).
-    verts [B,T,V,3] CUDA; obj_traj [B,nobj_max,T,9]; obj_points_list: list of B arrays [nobj_b,P,3] -> [B,T,V]."""
+    verts [B,T,V,3] CUDA; obj_traj [B,nobj_max,T,9]; obj_points_list: list of B arrays [nobj_b,P,3] -> [B,T,V].
+    `exhaustive=True` runs the brute-force scan (tamf_h2o_dist_exhaustive) instead of the block-pruned exact search --
+    same results bit for bit; tests use it as the cross-check."""
     import numpy as np
     dev = verts.device
     B, T, V, _ = verts.shape
@@ -92,7 +95,8 @@ def h2o_dist(verts: torch.Tensor, obj_traj: torch.Tensor, obj_points_list, retur
     dist = torch.empty((B, T, V), dtype=torch.float32, device=dev)
     idx = torch.empty((B, T, V), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().tamf_h2o_dist(_lib.ptr(verts), _lib.ptr(obj_traj), _lib.ptr(pts),
-                                            _lib.C.c_void_p(first_t.data_ptr()), B, T, V, obj_traj.shape[1], P,
-                                            _lib.ptr(dist), _lib.ptr(idx), _lib.stream_ptr(dev)), "tamf_h2o_dist")
+        fn = _lib.lib().tamf_h2o_dist_exhaustive if exhaustive else _lib.lib().tamf_h2o_dist
+        _lib.check(fn(_lib.ptr(verts), _lib.ptr(obj_traj), _lib.ptr(pts),
+                      _lib.C.c_void_p(first_t.data_ptr()), B, T, V, obj_traj.shape[1], P,
+                      _lib.ptr(dist), _lib.ptr(idx), _lib.stream_ptr(dev)), "tamf_h2o_dist")
     return (dist, idx) if return_idx else dist

@@ -98,3 +98,66 @@ def test_h2o_fused_matches_materialised():
     ref = orc.h2o_dist(verts, batch["obj_traj"], obj_num, batch["obj_pointcloud"])
     out = tamf_b200.h2o_dist(verts.cuda(), batch["obj_traj"].cuda(), batch["obj_pointcloud"])
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-6)
+
+
+def _h2o_both(verts, traj, clouds):
+    import tamf_b200
+    a = tamf_b200.h2o_dist(verts.cuda(), traj.cuda(), clouds, return_idx=True)
+    b = tamf_b200.h2o_dist(verts.cuda(), traj.cuda(), clouds, return_idx=True, exhaustive=True)
+    return [t.cpu().numpy() for t in a], [t.cpu().numpy() for t in b]
+
+
+def _assert_same(a, b):
+    assert np.array_equal(a[1], b[1]), f"{(a[1] != b[1]).sum()} indices differ"
+    assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))  # bit-exact distances (NaN patterns included)
+
+
+@pytest.mark.parametrize("B,T,P,nobj,scale", [(3, 5, 1024, 2, 0.1), (2, 3, 8192, 1, 0.1), (2, 4, 1000, 3, 0.02),
+                                              (1, 2, 37, 1, 0.3), (2, 2, 64, 2, 1.0), (4, 6, 4096, 2, 0.005)])
+def test_h2o_pruned_equals_exhaustive(B, T, P, nobj, scale):
+    """The block-pruned exact search must reproduce the exhaustive scan bit for bit -- far hands, hands inside the
+    cloud (scale << cloud size) and ragged object counts."""
+    from tamf_b200 import synth
+    batch = synth.make_batch(B, T, nobj=nobj, seed=P + B, ragged=nobj > 1, npoints=P, with_pointcloud=True)
+    rng = np.random.default_rng(P * 7 + T)
+    verts = torch.from_numpy((scale * rng.standard_normal((B, T, 778, 3))).astype(np.float32))
+    # half of the vertices sit next to object points (contact): exercises small nearest distances
+    for b in range(B):
+        pc = np.asarray(batch["obj_pointcloud"][b], np.float32)[0]
+        tr = batch["obj_traj"][b, 0].numpy()
+        from oracle import tamf_oracle as orc
+        R = orc.rot6d_to_rotmat(torch.from_numpy(tr[:, 3:9])).numpy()  # rows b1,b2,b3 (transform.py:148-154)
+        for t in range(T):
+            sel = rng.integers(0, pc.shape[0], 389)
+            world = pc[sel] @ R[t].T + tr[t, :3]
+            verts[b, t, :389] = torch.from_numpy(world + 1e-3 * rng.standard_normal((389, 3)).astype(np.float32))
+    a, bb = _h2o_both(verts, batch["obj_traj"], batch["obj_pointcloud"])
+    _assert_same(a, bb)
+
+
+def test_h2o_pruned_ties_degenerate_and_nan():
+    """Exact ties (lattice cloud with every point duplicated, axis-aligned transforms), a degenerate rot6d (pruning
+    must switch itself off), NaN vertices."""
+    rng = np.random.default_rng(1)
+    B, T, P = 2, 3, 512
+    base = rng.integers(-4, 5, (1, P // 2, 3)).astype(np.float32) * 0.125
+    cloud = np.concatenate([base, base], 1)  # every point twice: the lower index must win
+    clouds = [cloud.copy(), cloud.copy()]
+    traj = torch.zeros(B, 1, T, 9)
+    traj[..., 3] = 1.0
+    traj[..., 7] = 1.0  # identity rotation
+    traj[..., 0:3] = torch.from_numpy(rng.integers(-2, 3, (B, 1, T, 3)).astype(np.float32) * 0.125)
+    verts = torch.from_numpy(rng.integers(-6, 7, (B, T, 778, 3)).astype(np.float32) * 0.125)
+    a, b = _h2o_both(verts, traj, clouds)
+    _assert_same(a, b)
+    assert a[1].max() < P // 2
+    traj2 = traj.clone()
+    traj2[0, 0, 1, 3:9] = 0.0  # degenerate rot6d: R is not a rotation
+    traj2[1, 0, 0, 3:9] = torch.tensor([1.0, 0.0, 0.0, 2.0, 0.0, 0.0])  # colinear columns
+    a, b = _h2o_both(verts + 0.01 * torch.randn_like(verts), traj2, clouds)
+    _assert_same(a, b)
+    v3 = verts.clone()
+    v3[0, 0, 5, 1] = float("nan")
+    v3[1, 2, 700] = float("inf")
+    a, b = _h2o_both(v3, traj, clouds)
+    _assert_same(a, b)
