@@ -59,6 +59,14 @@ int tamf_nn_query(const float* x, const float* y, int N, int P1, int P2, float* 
  *   idx       [B,T,V] int64        index into the concatenated cloud of that sequence (scratch + output) */
 int tamf_h2o_dist(const float* verts, const float* obj_traj, const float* obj_points, const int32_t* obj_first_host,
                   int B, int T, int V, int nobj_max, int P, float* dist, int64_t* idx, void* stream);
+/* Two-step form for callers that query the same objects several times (SegmentRefineModel.forward runs the query for
+ * the sampled, refined and target hands): build the block index of the canonical clouds once into caller-owned device
+ * memory, then query it.  tamf_h2o_index_bytes returns 0 when P > 8192 (no index: use tamf_h2o_dist). */
+size_t tamf_h2o_index_bytes(int total_obj, int P);
+int tamf_h2o_index_build(const float* obj_points, int total_obj, int P, void* index, size_t index_bytes, void* stream);
+int tamf_h2o_dist_indexed(const float* verts, const float* obj_traj, const void* index, const int32_t* obj_first_host,
+                          int B, int T, int V, int nobj_max, int P, float* dist, int64_t* idx, void* stream);
+
 /* Same contract, exhaustive scan of every (vertex, point) pair.  tamf_h2o_dist rejects whole blocks of 64 points by
  * their bounding boxes in the object frame when P <= 8192 (exact: bit-identical dist / idx, csrc/nn.cu); this entry
  * is the cross-check the parity tests compare it with and the path taken for larger P. */

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(1024)
 // ------------------------------------------------------------------------------------------------
 constexpr int NNP_BS = 64;          // candidates per block
 constexpr int NNP_MAXP = 8192;      // points per object handled by the pruned path
-constexpr int NNP_QWARPS = 24;      // query warps per CTA
+constexpr int NNP_QWARPS = 32;      // query warps per CTA
 constexpr unsigned NNP_PAD = 0xFFFFFFFFu;
 
 __device__ __forceinline__ unsigned nnp_spread3(unsigned v) {  // 10 bits -> every third bit
@@ -388,6 +388,8 @@ __global__ void __launch_bounds__(1024) nnp_build_kernel(const float* __restrict
   }
 }
 
+__device__ unsigned long long nnp_stats[2];  // debug (TAMF_NN_STATS=1): blocks evaluated, queries
+
 __device__ __forceinline__ float nnp_d2(float qx, float qy, float qz, const float4& c) {  // the scan kernel's arithmetic
   const float dx = __fsub_rn(qx, c.x), dy = __fsub_rn(qy, c.y), dz = __fsub_rn(qz, c.z);
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(NNP_QWARPS * 32, 1)
     h2o_pruned_kernel(const float* __restrict__ verts, const float* __restrict__ obj_traj,
                       const float4* __restrict__ sorted, const float4* __restrict__ boxes,
                       const int* __restrict__ obj_first, int T, int V, int nobj_max, int P, int Ppad,
-                      unsigned long long* __restrict__ packed) {
+                      unsigned long long* __restrict__ packed, int stats) {
   extern __shared__ float4 nnp_smem[];
   __shared__ float sR[12];
   __shared__ float s_boxmax;
@@ -478,12 +480,13 @@ __global__ void __launch_bounds__(NNP_QWARPS * 32, 1)
         if (lb[k] < lmin || lblk < 0) lmin = lb[k], lblk = blk;  // NaN bounds: the lane keeps its first block
       }
     }
-    // warp argmin of the block bounds (any block is a valid start; a NaN never wins a `<`)
-#pragma unroll
-    for (int sft = 16; sft; sft >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, lmin, sft);
-      const int ob = __shfl_xor_sync(0xffffffffu, lblk, sft);
-      if (ob >= 0 && (lblk < 0 || om < lmin || (om == lmin && ob < lblk))) lmin = om, lblk = ob;
+    // warp argmin of the block bounds: bounds are sums of squares (>= +0 or NaN), so their bit patterns order like
+    // the values (NaN patterns above +inf) and one REDUX finds the minimum; any block is a valid start
+    {
+      const unsigned mine = lblk >= 0 ? __float_as_uint(lmin) : 0xFFFFFFFFu;
+      const unsigned wmin = __reduce_min_sync(0xffffffffu, mine);
+      const unsigned who = __ballot_sync(0xffffffffu, mine == wmin);
+      lblk = __shfl_sync(0xffffffffu, lblk, __ffs(who) - 1);
     }
     const int fb = lblk;  // warp-uniform
     float bd = inf;
@@ -497,13 +500,11 @@ __global__ void __launch_bounds__(NNP_QWARPS * 32, 1)
         if (d < bd || (d == bd && bi != NNP_PAD && ci < bi)) bd = d, bi = ci;
       }
     };
-    auto warp_min = [&]() {
-      float m = bd;
-#pragma unroll
-      for (int sft = 16; sft; sft >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, sft));
-      return m;
+    auto warp_min = [&]() {  // bd >= +0 or +inf, never NaN: unsigned order of the bits == order of the values
+      return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(bd)));
     };
     eval_block(fb);
+    int n_eval = 1;
     float bound2 = inf;
     if (prune) {
       const float r = sqrtf(warp_min()) * 1.001f + absm;
@@ -519,20 +520,25 @@ __global__ void __launch_bounds__(NNP_QWARPS * 32, 1)
         const int bit = __ffs(m) - 1;
         m &= m - 1;
         eval_block(k * 32 + bit);
+        ++n_eval;
       }
       if (any && prune && k + 1 < KMAX) {  // tighten the bound for the remaining groups
         const float r = sqrtf(warp_min()) * 1.001f + absm;
         bound2 = r * r;
       }
     }
-    // lexicographic (d2, index) minimum over the lanes
-#pragma unroll
-    for (int sft = 16; sft; sft >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, bd, sft);
-      const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, sft);
-      if (oi != NNP_PAD && (bi == NNP_PAD || od < bd || (od == bd && oi < bi))) bd = od, bi = oi;
+    // lexicographic (d2, index) minimum over the lanes: smallest distance first, lowest index among its holders
+    {
+      const unsigned dmin = __reduce_min_sync(0xffffffffu, bi != NNP_PAD ? __float_as_uint(bd) : 0xFFFFFFFFu);
+      const unsigned imin = __reduce_min_sync(
+          0xffffffffu, (bi != NNP_PAD && __float_as_uint(bd) == dmin) ? bi : NNP_PAD);
+      bd = __uint_as_float(dmin), bi = imin;
     }
     if (lane == 0 && bi != NNP_PAD) nn_publish(packed + (size_t)f * V + q, bd, o * P + (int)bi);
+    if (stats && lane == 0) {
+      atomicAdd(&nnp_stats[0], (unsigned long long)n_eval);
+      atomicAdd(&nnp_stats[1], 1ull);
+    }
   }
 }
 
@@ -587,12 +593,41 @@ extern "C" int tamf_nn_query(const float* x, const float* y, int N, int P1, int 
   return TAMF_OK;
 }
 
-static int h2o_dist_impl(const float* verts, const float* obj_traj, const float* obj_points,
+static int nnp_configure() {
+  static bool configured = false;
+  if (!configured) {
+    TAMF_CUDA_CHECK(cudaFuncSetAttribute(nnp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NNP_MAXP * 8));
+    TAMF_CUDA_CHECK(cudaFuncSetAttribute(h2o_pruned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (NNP_MAXP + 2 * (NNP_MAXP / NNP_BS)) * (int)sizeof(float4)));
+    configured = true;
+  }
+  return TAMF_OK;
+}
+static size_t nnp_index_bytes(int total_obj, int P) {
+  if (P > NNP_MAXP || P <= 0 || total_obj <= 0) return 0;
+  const int Ppad = (P + NNP_BS - 1) / NNP_BS * NNP_BS, nblk = Ppad / NNP_BS;
+  return ((size_t)total_obj * Ppad + (size_t)total_obj * 2 * (nblk + 1)) * sizeof(float4);
+}
+static int nnp_build(const float* obj_points, int total_obj, int P, void* index, cudaStream_t stream) {
+  int rc = nnp_configure();
+  if (rc) return rc;
+  const int Ppad = (P + NNP_BS - 1) / NNP_BS * NNP_BS;
+  int np2 = 64;
+  while (np2 < P) np2 <<= 1;
+  float4* d_sorted = (float4*)index;
+  float4* d_boxes = d_sorted + (size_t)total_obj * Ppad;
+  nnp_build_kernel<<<total_obj, 1024, (size_t)np2 * 8, stream>>>(obj_points, P, Ppad, np2, d_sorted, d_boxes);
+  TAMF_LAUNCH_CHECK();
+  return TAMF_OK;
+}
+
+// `index`: block-pruned search over a built index (obj_points unused); else the exhaustive scan of obj_points.
+static int h2o_dist_impl(const float* verts, const float* obj_traj, const float* obj_points, const void* index,
                          const int32_t* obj_first_host, int B, int T, int V, int nobj_max, int P, float* dist,
-                         int64_t* idx, void* stream_, bool exhaustive) {
+                         int64_t* idx, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   TAMF_REQUIRE(B > 0 && T > 0 && V > 0 && P > 0 && nobj_max > 0, TAMF_E_BADARG, "tamf_h2o_dist: bad size");
-  TAMF_REQUIRE(verts && obj_traj && obj_points && obj_first_host && dist && idx, TAMF_E_BADARG,
+  TAMF_REQUIRE(verts && obj_traj && (obj_points || index) && obj_first_host && dist && idx, TAMF_E_BADARG,
                "tamf_h2o_dist: null pointer");
   TAMF_REQUIRE(V <= 1024 * NN_QPT, TAMF_E_BADARG, "tamf_h2o_dist: V > 4096 unsupported");
   TAMF_REQUIRE(B <= 4096, TAMF_E_BADARG, "tamf_h2o_dist: B > 4096 unsupported");
@@ -605,7 +640,7 @@ static int h2o_dist_impl(const float* verts, const float* obj_traj, const float*
                  "tamf_h2o_dist: every sequence needs 1..nobj_max objects (empty cloud has no nearest neighbour)");
     if (n > max_nobj) max_nobj = n;
   }
-  // obj_first goes to the device through a small pinned-less async copy from a static staging buffer
+  // obj_first goes to the device through a small async copy into a grow-only per-thread buffer
   static thread_local int* d_first = nullptr;
   static thread_local int d_first_cap = 0;
   if (d_first_cap < B + 1) {
@@ -616,39 +651,24 @@ static int h2o_dist_impl(const float* verts, const float* obj_traj, const float*
   TAMF_CUDA_CHECK(cudaMemcpyAsync(d_first, obj_first_host, sizeof(int) * (size_t)(B + 1), cudaMemcpyHostToDevice, stream));
   const size_t total = (size_t)B * T * V;
   TAMF_CUDA_CHECK(cudaMemsetAsync(idx, 0xFF, total * sizeof(int64_t), stream));
-  static const bool env_exhaustive = getenv("TAMF_NN_EXHAUSTIVE") && getenv("TAMF_NN_EXHAUSTIVE")[0] == '1';
-  if (!exhaustive && !env_exhaustive && P <= NNP_MAXP) {
-    // block-pruned exact search: sorted clouds + block boxes live in a grow-only per-thread device scratch
+  static const bool env_stats = getenv("TAMF_NN_STATS") && getenv("TAMF_NN_STATS")[0] == '1';
+  if (index) {
+    TAMF_REQUIRE(P <= NNP_MAXP, TAMF_E_BADARG, "tamf_h2o_dist_indexed: an index exists only for P <= 8192");
+    if ((rc = nnp_configure())) return rc;
     const int total_obj = obj_first_host[B];
     const int Ppad = (P + NNP_BS - 1) / NNP_BS * NNP_BS, nblk = Ppad / NNP_BS;
-    int np2 = 64;
-    while (np2 < P) np2 <<= 1;
-    const size_t need = ((size_t)total_obj * Ppad + (size_t)total_obj * 2 * (nblk + 1)) * sizeof(float4);
-    static thread_local void* d_scratch = nullptr;
-    static thread_local size_t d_scratch_cap = 0;
-    if (d_scratch_cap < need) {
-      if (d_scratch) {
-        TAMF_CUDA_CHECK(cudaDeviceSynchronize());
-        cudaFree(d_scratch);
-        d_scratch = nullptr, d_scratch_cap = 0;
-      }
-      TAMF_CUDA_CHECK(cudaMalloc(&d_scratch, need));
-      d_scratch_cap = need;
-    }
-    float4* d_sorted = (float4*)d_scratch;
-    float4* d_boxes = d_sorted + (size_t)total_obj * Ppad;
-    static bool configured = false;
-    if (!configured) {
-      TAMF_CUDA_CHECK(cudaFuncSetAttribute(nnp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NNP_MAXP * 8));
-      TAMF_CUDA_CHECK(cudaFuncSetAttribute(h2o_pruned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (NNP_MAXP + 2 * (NNP_MAXP / NNP_BS)) * (int)sizeof(float4)));
-      configured = true;
-    }
-    nnp_build_kernel<<<total_obj, 1024, (size_t)np2 * 8, stream>>>(obj_points, P, Ppad, np2, d_sorted, d_boxes);
-    TAMF_LAUNCH_CHECK();
+    const float4* d_sorted = (const float4*)index;
+    const float4* d_boxes = d_sorted + (size_t)total_obj * Ppad;
     h2o_pruned_kernel<<<dim3(B * T, max_nobj), NNP_QWARPS * 32, (size_t)(Ppad + 2 * nblk) * sizeof(float4), stream>>>(
-        verts, obj_traj, d_sorted, d_boxes, d_first, T, V, nobj_max, P, Ppad, (unsigned long long*)idx);
+        verts, obj_traj, d_sorted, d_boxes, d_first, T, V, nobj_max, P, Ppad, (unsigned long long*)idx, env_stats ? 1 : 0);
     TAMF_LAUNCH_CHECK();
+    if (env_stats) {
+      unsigned long long h[2] = {0, 0};
+      cudaStreamSynchronize(stream);
+      cudaMemcpyFromSymbol(h, nnp_stats, sizeof(h));
+      fprintf(stderr, "[tamf nn stats] blocks evaluated per query: %.2f of %d (cumulative over %llu queries)\n",
+              h[1] ? (double)h[0] / (double)h[1] : 0.0, nblk, h[1]);
+    }
   } else {
     int threads = ((V + NN_QPT - 1) / NN_QPT + 31) / 32 * 32;
     int P2 = max_nobj * P;
@@ -664,14 +684,56 @@ static int h2o_dist_impl(const float* verts, const float* obj_traj, const float*
   return TAMF_OK;
 }
 
+extern "C" size_t tamf_h2o_index_bytes(int total_obj, int P) { return nnp_index_bytes(total_obj, P); }
+
+extern "C" int tamf_h2o_index_build(const float* obj_points, int total_obj, int P, void* index, size_t index_bytes,
+                                    void* stream) {
+  TAMF_REQUIRE(obj_points && index && total_obj > 0 && P > 0, TAMF_E_BADARG, "tamf_h2o_index_build: bad argument");
+  TAMF_REQUIRE(P <= NNP_MAXP, TAMF_E_BADARG, "tamf_h2o_index_build: P > 8192 has no index (use tamf_h2o_dist)");
+  TAMF_REQUIRE(index_bytes >= nnp_index_bytes(total_obj, P), TAMF_E_BADARG, "tamf_h2o_index_build: index buffer too small");
+  TAMF_REQUIRE(aligned16(index), TAMF_E_ALIGN, "tamf_h2o_index_build: index must be 16-byte aligned");
+  int rc = check_device();
+  if (rc) return rc;
+  return nnp_build(obj_points, total_obj, P, index, (cudaStream_t)stream);
+}
+
+extern "C" int tamf_h2o_dist_indexed(const float* verts, const float* obj_traj, const void* index,
+                                     const int32_t* obj_first_host, int B, int T, int V, int nobj_max, int P, float* dist,
+                                     int64_t* idx, void* stream) {
+  TAMF_REQUIRE(index, TAMF_E_BADARG, "tamf_h2o_dist_indexed: null index");
+  return h2o_dist_impl(verts, obj_traj, nullptr, index, obj_first_host, B, T, V, nobj_max, P, dist, idx, stream);
+}
+
 extern "C" int tamf_h2o_dist(const float* verts, const float* obj_traj, const float* obj_points,
                              const int32_t* obj_first_host, int B, int T, int V, int nobj_max, int P, float* dist,
                              int64_t* idx, void* stream) {
-  return h2o_dist_impl(verts, obj_traj, obj_points, obj_first_host, B, T, V, nobj_max, P, dist, idx, stream, false);
+  static const bool env_exhaustive = getenv("TAMF_NN_EXHAUSTIVE") && getenv("TAMF_NN_EXHAUSTIVE")[0] == '1';
+  TAMF_REQUIRE(obj_points && obj_first_host && B > 0, TAMF_E_BADARG, "tamf_h2o_dist: null pointer");
+  if (env_exhaustive || P > NNP_MAXP || P <= 0)
+    return h2o_dist_impl(verts, obj_traj, obj_points, nullptr, obj_first_host, B, T, V, nobj_max, P, dist, idx, stream);
+  // one-shot form: the index lives in a grow-only per-thread device scratch and is rebuilt on every call
+  const int total_obj = obj_first_host[B];
+  TAMF_REQUIRE(total_obj > 0, TAMF_E_BADARG, "tamf_h2o_dist: no objects");
+  const size_t need = nnp_index_bytes(total_obj, P);
+  static thread_local void* d_scratch = nullptr;
+  static thread_local size_t d_scratch_cap = 0;
+  if (d_scratch_cap < need) {
+    if (d_scratch) {
+      TAMF_CUDA_CHECK(cudaDeviceSynchronize());
+      cudaFree(d_scratch);
+      d_scratch = nullptr, d_scratch_cap = 0;
+    }
+    TAMF_CUDA_CHECK(cudaMalloc(&d_scratch, need));
+    d_scratch_cap = need;
+  }
+  int rc = check_device();
+  if (rc) return rc;
+  if ((rc = nnp_build(obj_points, total_obj, P, d_scratch, (cudaStream_t)stream))) return rc;
+  return h2o_dist_impl(verts, obj_traj, nullptr, d_scratch, obj_first_host, B, T, V, nobj_max, P, dist, idx, stream);
 }
 
 extern "C" int tamf_h2o_dist_exhaustive(const float* verts, const float* obj_traj, const float* obj_points,
                                         const int32_t* obj_first_host, int B, int T, int V, int nobj_max, int P,
                                         float* dist, int64_t* idx, void* stream) {
-  return h2o_dist_impl(verts, obj_traj, obj_points, obj_first_host, B, T, V, nobj_max, P, dist, idx, stream, true);
+  return h2o_dist_impl(verts, obj_traj, obj_points, nullptr, obj_first_host, B, T, V, nobj_max, P, dist, idx, stream);
 }

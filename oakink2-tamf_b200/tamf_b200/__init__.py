@@ -2,7 +2,7 @@
 
 Same call signatures as the reference (InterationSegmentMDM.forward(x, timesteps, batch), p_sample_loop,
 ManoLayer(...)(pose_coeffs, betas), ChamferDistance()(x, y), point2point_signed, SegmentRefineModel(mano_path, ...)(batch)), backed by libtamf_b200.so."""
-from .chamfer import ChamferDistance, h2o_dist, nn_query, point2point_signed  # noqa: F401
+from .chamfer import ChamferDistance, H2OIndex, h2o_dist, nn_query, point2point_signed  # noqa: F401
 from .diffusion import (GaussianDiffusion, SpacedDiffusion, create_gaussian_diffusion,  # noqa: F401
                         space_timesteps)
 from .extract_sample import (contact_min_cdist, extract_refined_sample, extract_refined_sample_bihand,  # noqa: F401

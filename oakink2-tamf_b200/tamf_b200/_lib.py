@@ -15,7 +15,8 @@ POSE_QUAT, POSE_REPR = 0, 1
 
 # every symbol include/tamf_b200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [
-    "tamf_version", "tamf_last_error", "tamf_nn_query", "tamf_h2o_dist", "tamf_h2o_dist_exhaustive", "tamf_mano_create", "tamf_mano_destroy",
+    "tamf_version", "tamf_last_error", "tamf_nn_query", "tamf_h2o_dist", "tamf_h2o_dist_exhaustive", "tamf_h2o_index_bytes",
+    "tamf_h2o_index_build", "tamf_h2o_dist_indexed", "tamf_mano_create", "tamf_mano_destroy",
     "tamf_mano_fk", "tamf_denoiser_create", "tamf_denoiser_destroy", "tamf_denoiser_workspace_bytes",
     "tamf_denoiser_bind", "tamf_denoiser_set_cond", "tamf_denoiser_forward", "tamf_p_sample_step",
     "tamf_p_sample_chain", "tamf_p_sample_loop_host", "tamf_denoiser_profile_step", "tamf_kernel_launch_count", "tamf_philox_normal",
@@ -76,6 +77,10 @@ def lib() -> C.CDLL:
     L.tamf_nn_query.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     L.tamf_h2o_dist.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
     L.tamf_h2o_dist_exhaustive.argtypes = L.tamf_h2o_dist.argtypes
+    L.tamf_h2o_dist_indexed.argtypes = L.tamf_h2o_dist.argtypes
+    L.tamf_h2o_index_bytes.argtypes = [i32, i32]
+    L.tamf_h2o_index_bytes.restype = sz
+    L.tamf_h2o_index_build.argtypes = [vp, i32, i32, vp, sz, vp]
     L.tamf_mano_create.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(vp)]
     L.tamf_mano_destroy.argtypes = [vp]
     L.tamf_mano_fk.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp]

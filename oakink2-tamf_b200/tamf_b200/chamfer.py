@@ -75,28 +75,52 @@ def point2point_signed(x, y, x_normals=None, y_normals=None):
     return y2x_signed, x2y_signed, yidx_near
 
 
+class H2OIndex:
+    """Canonical object clouds of one batch on the device plus the block index of the pruned exact search
+    (tamf_h2o_index_build).  Build once, query with h2o_dist(..., index=...) as often as needed."""
+
+    def __init__(self, obj_points_list, device, build: bool = True):
+        import numpy as np
+        first = [0]
+        for o in obj_points_list:
+            first.append(first[-1] + int(o.shape[0]))
+        self.first = torch.tensor(first, dtype=torch.int32)
+        self.P = int(obj_points_list[0].shape[1])
+        self.total_obj = first[-1]
+        self.pts = torch.from_numpy(np.concatenate([np.asarray(o, np.float32) for o in obj_points_list], 0)).to(
+            device).contiguous()
+        self.index = None
+        nbytes = _lib.lib().tamf_h2o_index_bytes(self.total_obj, self.P) if build else 0
+        if nbytes:
+            self.index = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                _lib.check(_lib.lib().tamf_h2o_index_build(_lib.ptr(self.pts), self.total_obj, self.P,
+                                                           _lib.ptr(self.index), nbytes, _lib.stream_ptr(device)),
+                           "tamf_h2o_index_build")
+
+
 def h2o_dist(verts: torch.Tensor, obj_traj: torch.Tensor, obj_points_list, return_idx: bool = False,
-             exhaustive: bool = False):
+             exhaustive: bool = False, index: "H2OIndex | None" = None):
     """Fused `SegmentRefineModel.multi_object_h2o_dist` (segment_refine_model.py:142-168).
     verts [B,T,V,3] CUDA; obj_traj [B,nobj_max,T,9]; obj_points_list: list of B arrays [nobj_b,P,3] -> [B,T,V].
+    `index`: a prebuilt H2OIndex of the same clouds (obj_points_list is then ignored).
     `exhaustive=True` runs the brute-force scan (tamf_h2o_dist_exhaustive) instead of the block-pruned exact search --
     same results bit for bit; tests use it as the cross-check."""
-    import numpy as np
     dev = verts.device
     B, T, V, _ = verts.shape
-    first = [0]
-    for o in obj_points_list:
-        first.append(first[-1] + int(o.shape[0]))
-    P = int(obj_points_list[0].shape[1])
-    pts = torch.from_numpy(np.concatenate([np.asarray(o, np.float32) for o in obj_points_list], 0)).to(dev).contiguous()
-    first_t = torch.tensor(first, dtype=torch.int32)
+    if index is None:
+        index = H2OIndex(obj_points_list, dev, build=not exhaustive)
     verts = verts.detach().to(torch.float32).contiguous()
     obj_traj = obj_traj.detach().to(device=dev, dtype=torch.float32).contiguous()
     dist = torch.empty((B, T, V), dtype=torch.float32, device=dev)
     idx = torch.empty((B, T, V), dtype=torch.int64, device=dev)
+    L = _lib.lib()
     with torch.cuda.device(dev):
-        fn = _lib.lib().tamf_h2o_dist_exhaustive if exhaustive else _lib.lib().tamf_h2o_dist
-        _lib.check(fn(_lib.ptr(verts), _lib.ptr(obj_traj), _lib.ptr(pts),
-                      _lib.C.c_void_p(first_t.data_ptr()), B, T, V, obj_traj.shape[1], P,
-                      _lib.ptr(dist), _lib.ptr(idx), _lib.stream_ptr(dev)), "tamf_h2o_dist")
+        if exhaustive or index.index is None:
+            fn, third = (L.tamf_h2o_dist_exhaustive if exhaustive else L.tamf_h2o_dist), index.pts
+        else:
+            fn, third = L.tamf_h2o_dist_indexed, index.index
+        _lib.check(fn(_lib.ptr(verts), _lib.ptr(obj_traj), _lib.ptr(third), _lib.C.c_void_p(index.first.data_ptr()), B, T,
+                      V, obj_traj.shape[1], index.P, _lib.ptr(dist), _lib.ptr(idx), _lib.stream_ptr(dev)),
+                   "tamf_h2o_dist")
     return (dist, idx) if return_idx else dist

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .chamfer import h2o_dist
+from .chamfer import H2OIndex, h2o_dist
 from .manolayer import ManoLayer
 from .mdm import InterationSegmentMDM, _Holder, _positional_table, build_encoder_container, layer_weight_structs
 
@@ -173,11 +173,18 @@ class SegmentRefineModel(nn.Module):
         return verts.view(B, T, 778, 3), joints.view(B, T, 21, 3), normals.view(B, T, 778, 3)
 
     def multi_object_h2o_dist(self, batch_hand_verts, batch_hand_normals, batch_obj_list, batch_obj_traj,
-                              batch_obj_verts_list):
+                              batch_obj_verts_list, index=None):
         """segment_refine_model.py:142-168 -> [B,T,778] unsigned hand->object distance (normals only feed the
-        discarded y2x_signed, :165)."""
+        discarded y2x_signed, :165).  `index`: an H2OIndex of the same clouds built by the caller (forward() builds
+        one for its three queries)."""
+        if index is None:
+            index = self.object_index(batch_obj_list, batch_obj_verts_list, batch_hand_verts.device)
+        return h2o_dist(batch_hand_verts, batch_obj_traj, None, index=index)
+
+    @staticmethod
+    def object_index(batch_obj_list, batch_obj_verts_list, device):
         pts = [np.asarray(o, np.float32)[: len(l)] for o, l in zip(batch_obj_verts_list, batch_obj_list)]
-        return h2o_dist(batch_hand_verts, batch_obj_traj, pts)
+        return H2OIndex(pts, device)
 
     def forward(self, batch):
         x_in = batch["sample_pose_repr"]
@@ -193,16 +200,17 @@ class SegmentRefineModel(nn.Module):
         obj_pts = batch["obj_pointcloud"] if self.use_pc else batch["obj_verts"]
         side = torch.tensor(InterationSegmentMDM.hand_side_ids(batch["hand_side"]), dtype=torch.int32, device=dev)
         hv, hj, hn = self.batch_recover_mano_from_pose_repr(x_in, shape, batch["hand_side"])
-        h2o = self.multi_object_h2o_dist(hv, hn, batch["obj_list"], traj, obj_pts)
+        oix = self.object_index(batch["obj_list"], obj_pts, dev)  # clouds uploaded + indexed once for the three queries
+        h2o = self.multi_object_h2o_dist(hv, hn, batch["obj_list"], traj, obj_pts, index=oix)
         out = torch.empty_like(x_in)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().tamf_refiner_forward(self._handle, _lib.ptr(x_in), _lib.ptr(h2o), _lib.ptr(side),
                                                        _lib.ptr(shape), _lib.ptr(traj), _lib.ptr(emb), traj.shape[1],
                                                        _lib.ptr(out), _lib.stream_ptr(dev)), "tamf_refiner_forward")
         rv, rj, rn = self.batch_recover_mano_from_pose_repr(out, shape, batch["hand_side"])
-        r_h2o = self.multi_object_h2o_dist(rv, rn, batch["obj_list"], traj, obj_pts)
+        r_h2o = self.multi_object_h2o_dist(rv, rn, batch["obj_list"], traj, obj_pts, index=oix)
         tv, tj, tn = self.batch_recover_mano_from_pose_repr(f32(batch["pose_repr"]), shape, batch["hand_side"])
-        t_h2o = self.multi_object_h2o_dist(tv, tn, batch["obj_list"], traj, obj_pts)
+        t_h2o = self.multi_object_h2o_dist(tv, tn, batch["obj_list"], traj, obj_pts, index=oix)
         return {
             "refine_pose_repr": out, "refine_hand_verts": rv, "refine_hand_joints": rj, "refine_hand_normals": rn,
             "refine_h2o_dist": r_h2o, "target_hand_verts": tv, "target_hand_joints": tj, "target_hand_normals": tn,
