@@ -159,8 +159,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"MF-MDM G {ARCH}, batch {B} synthetic sequences, T={T_FRAMES}, nobj={NOBJ}, full "
-                               f"{DIFF_STEPS}-step reverse chain (BASELINE.json configs[1])", "parallelism": "cpu"},
+        "config": {"workload": f"MF-MDM G {ARCH}, batch {B} synthetic sequences per GPU, T={T_FRAMES}, nobj={NOBJ}, "
+                               f"full {DIFF_STEPS}-step reverse chain (BASELINE.json configs[1])",
+                   "global_batch": B, "parallelism": "host CPU cores (reference arm, rank 0 only)",
+                   "weights": "random init"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -336,7 +338,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--chain-steps", type=int, default=DIFF_STEPS, help="debug only: shorter chains are not the metric")
-    ap.add_argument("--ref-diff-steps", type=int, default=2)
+    ap.add_argument("--ref-diff-steps", type=int, default=24,
+                    help="diffusion steps per timed CPU sample (about 10 s of host work at B=64)")
     ap.add_argument("--profile-reps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -101,6 +101,41 @@ def test_chain_graph_matches_stepwise():
     assert torch.equal(a, c)  # deterministic replay
 
 
+def test_full_1000_step_chain_two_hand_sequence():
+    """BASELINE.json configs[0] as a parity test: arch_mdm, ONE two-hand sequence (rows rh + lh sharing text and
+    objects), T=160, nobj=2, the full 1000-step ancestral chain, free running on both sides with the same per-step
+    noise: CUDA bf16 path vs the fp32 oracle on the host cores (about 10 s).  tools/parity_full_chain.py prints the
+    drift along the chain (profiles/r01_parity_full_chain.json: 3.7e-3 at t = 0)."""
+    import tamf_b200
+    from oracle import tamf_oracle as orc
+    from tamf_b200 import synth
+    m, cfg = _model("arch_mdm")
+    B, T = 2, 160
+    batch = synth.make_batch(B, T, nobj=2, seed=0)
+    for k in ("text", "obj_list"):
+        if k in batch:
+            batch[k] = [batch[k][0]] * B
+    for k in ("shape", "obj_traj", "obj_embedding"):
+        batch[k] = batch[k][:1].repeat(B, *([1] * (batch[k].ndim - 1)))
+    batch["hand_side"] = ["rh", "lh"]
+    shape = (B, 99, 1, T)
+    sd, text, tab = synth.g_state_dict(cfg, 0), synth.text_features(batch["text"]), orc.diffusion_tables(1000)
+    tamf_b200.create_gaussian_diffusion(1000, "cosine")._install(m, "ancestral")
+    dbatch = _dev_batch(batch)
+    xT = synth.step_noise(123, 1000, shape)
+    g, r = xT.cuda(), xT.clone()
+    with torch.no_grad():
+        for t in range(999, -1, -1):
+            n = synth.step_noise(123, t, shape)
+            g = m.p_sample_step(g, t, dbatch, noise=n)["sample"]
+            r = orc.p_sample_update(tab, r, orc.g_forward(sd, cfg, r, torch.full((B,), t, dtype=torch.long), batch, text),
+                                    t, n)
+    rl = rel_l2(g.cpu().numpy(), r.numpy())
+    print(f"full 1000-step chain rel_l2={rl:.3e}")
+    assert torch.isfinite(g).all() and rl <= 2 * REL_TOL
+    assert not torch.equal(g[0], g[1])  # rh / lh rows differ only through the hand-side token
+
+
 def test_philox_normal_statistics():
     from tamf_b200 import _lib
     n = 1 << 22
