@@ -256,8 +256,8 @@ __global__ void __launch_bounds__(1024)
 //
 // The brute-force scan above spends 6 instructions on each of the 778 x 8192 (query, candidate) pairs of a frame and
 // object.  A rigid transform preserves distances, so blocks of candidates can be rejected in the OBJECT frame:
-//   build (once per call and object):  Morton-sort the canonical cloud, cut it into blocks of 64 consecutive points,
-//                                      keep each block's bounding box;
+//   build (once per batch and object):  k-d order the canonical cloud (recursive median splits of the widest axis)
+//                                      into blocks of 64 consecutive points, keep each block's bounding box;
 //   query (CTA per frame and object):  stage the sorted cloud moved to the world exactly like the scan kernel does;
 //     one WARP per hand vertex: q' = R^T (v - t); lower bound LB of |q' - p| to every block box (lanes over blocks);
 //     evaluate the block with the smallest LB -> first upper bound `best`; then only blocks with
@@ -274,98 +274,102 @@ constexpr int NNP_MAXP = 8192;      // points per object handled by the pruned p
 constexpr int NNP_QWARPS = 32;      // query warps per CTA
 constexpr unsigned NNP_PAD = 0xFFFFFFFFu;
 
-__device__ __forceinline__ unsigned nnp_spread3(unsigned v) {  // 10 bits -> every third bit
-  v = (v | (v << 16)) & 0x030000FFu;
-  v = (v | (v << 8)) & 0x0300F00Fu;
-  v = (v | (v << 4)) & 0x030C30C3u;
-  v = (v | (v << 2)) & 0x09249249u;
-  return v;
+__device__ __forceinline__ unsigned nnp_ord(float f) {  // order-preserving float -> unsigned
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float nnp_unord(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
+// Index build, one CTA per object: k-d ordering of the canonical cloud.  The points are split recursively at the
+// median of the widest axis of their bounding box (log2(np2 / 64) levels) until runs of 64 consecutive points remain;
+// every level is one bitonic sort of the composite keys (segment | coordinate | index) restricted to the segment
+// length.  Balanced runs with tight boxes: what the query kernel's block bounds prune on.
 // grid = objects; block 1024.  sorted [obj][Ppad] float4 (x, y, z, original index bits; pads = +inf / NNP_PAD),
 // boxes [obj][2 * (nblk + 1)] float4: lo/hi of each block, then lo/hi of the whole cloud.
 __global__ void __launch_bounds__(1024) nnp_build_kernel(const float* __restrict__ pts, int P, int Ppad, int np2,
                                                          float4* __restrict__ sorted, float4* __restrict__ boxes) {
   extern __shared__ unsigned long long keys[];  // np2
-  __shared__ float red[6][32];
-  __shared__ float bb[6];
+  __shared__ unsigned segbox[6][NNP_MAXP / NNP_BS];  // per segment: ord(lo xyz), ord(hi xyz)
   const int o = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarp = (int)(blockDim.x >> 5);
   const float* po = pts + (size_t)o * P * 3;
   const float inf = __int_as_float(0x7f800000);
-  float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
-  for (int i = tid; i < P; i += blockDim.x)
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float c = po[3 * i + a];
-      lo[a] = fminf(lo[a], c), hi[a] = fmaxf(hi[a], c);
-    }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int sft = 16; sft; sft >>= 1) {
-      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], sft));
-      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], sft));
-    }
-    if (lane == 0) red[a][warp] = lo[a], red[3 + a][warp] = hi[a];
-  }
+  for (int i = tid; i < np2; i += blockDim.x) keys[i] = i < P ? (unsigned long long)i : ~0ull;
   __syncthreads();
-  if (tid < 6) {
-    float v = red[tid][0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = tid < 3 ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
-    bb[tid] = v;
-  }
-  __syncthreads();
-  float scale[3];
+  for (int seglen = np2; seglen > NNP_BS; seglen >>= 1) {
+    const int nseg = np2 / seglen;
+    for (int sgi = tid; sgi < nseg; sgi += blockDim.x)
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float ext = bb[3 + a] - bb[a];
-    scale[a] = (ext > 0.f && ext < inf) ? 1023.0f / ext : 0.f;
-  }
-  for (int i = tid; i < np2; i += blockDim.x) {
-    unsigned long long k = ~0ull;
-    if (i < P) {
-      unsigned key = 0;
+      for (int a = 0; a < 3; ++a) segbox[a][sgi] = 0xFFFFFFFFu, segbox[3 + a][sgi] = 0u;
+    __syncthreads();
+    // segment boxes: a warp's 32 consecutive positions share a segment (seglen >= 128)
+    for (int base = warp * 32; base < P; base += nwarp * 32) {
+      const int i = base + lane;
+      unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+      if (i < P) {
+        const unsigned id = (unsigned)(keys[i] & 0x1FFFu);
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const float f = (po[3 * i + a] - bb[a]) * scale[a];
-        const unsigned c = (f >= 0.f) ? (unsigned)fminf(f, 1023.0f) : 0u;  // NaN -> 0
-        key |= nnp_spread3(c) << a;
-      }
-      k = ((unsigned long long)key << 32) | (unsigned)i;
-    }
-    keys[i] = k;
-  }
-  __syncthreads();
-  for (int k = 2; k <= np2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < np2; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = keys[i], b = keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) keys[i] = b, keys[ixj] = a;
+        for (int a = 0; a < 3; ++a) {
+          const float c = po[3 * id + a];
+          if (c == c) lo[a] = hi[a] = nnp_ord(c);  // NaN coordinates do not shape the boxes
         }
       }
-      __syncthreads();
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = __reduce_min_sync(0xffffffffu, lo[a]);
+        hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
+      }
+      if (lane == 0) {
+        const int sgi = base / seglen;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) atomicMin(&segbox[a][sgi], lo[a]), atomicMax(&segbox[3 + a][sgi], hi[a]);
+      }
     }
+    __syncthreads();
+    for (int i = tid; i < P; i += blockDim.x) {
+      const int sgi = i / seglen;
+      const unsigned id = (unsigned)(keys[i] & 0x1FFFu);
+      float ext[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) ext[a] = nnp_unord(segbox[3 + a][sgi]) - nnp_unord(segbox[a][sgi]);
+      const int ax = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[1] >= ext[2] ? 1 : 2);
+      keys[i] = ((unsigned long long)sgi << 45) | ((unsigned long long)nnp_ord(po[3 * id + ax]) << 13) | id;
+    }
+    __syncthreads();
+    for (int k = 2; k <= seglen; k <<= 1)  // keys of different segments never meet: the network stops at seglen
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < np2; i += blockDim.x) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = keys[i], b = keys[ixj];
+            const bool up = (i & k) == 0 || k == seglen;  // the last merge of a segment sorts it ascending
+            if ((a > b) == up) keys[i] = b, keys[ixj] = a;
+          }
+        }
+        __syncthreads();
+      }
+  }
   float4* so = sorted + (size_t)o * Ppad;
   for (int j = tid; j < Ppad; j += blockDim.x) {
     float4 v = make_float4(inf, inf, inf, __uint_as_float(NNP_PAD));
     if (j < P) {
-      const unsigned i = (unsigned)keys[j];
+      const unsigned i = (unsigned)(keys[j] & 0x1FFFu);
       v = make_float4(po[3 * i], po[3 * i + 1], po[3 * i + 2], __uint_as_float(i));
     }
     so[j] = v;
   }
   const int nblk = Ppad / NNP_BS;
   float4* bo = boxes + (size_t)o * 2 * (nblk + 1);
-  for (int b = warp; b < nblk; b += (int)(blockDim.x >> 5)) {
+  float gl[3] = {inf, inf, inf}, gh[3] = {-inf, -inf, -inf};
+  for (int b = warp; b < nblk; b += nwarp) {
     float l[3] = {inf, inf, inf}, h[3] = {-inf, -inf, -inf};
 #pragma unroll
     for (int e = 0; e < NNP_BS / 32; ++e) {
       const int j = b * NNP_BS + e * 32 + lane;
       if (j < P) {
-        const unsigned i = (unsigned)keys[j];
+        const unsigned i = (unsigned)(keys[j] & 0x1FFFu);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const float c = po[3 * i + a];
@@ -374,17 +378,30 @@ __global__ void __launch_bounds__(1024) nnp_build_kernel(const float* __restrict
       }
     }
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    for (int a = 0; a < 3; ++a) {
 #pragma unroll
       for (int sft = 16; sft; sft >>= 1) {
         l[a] = fminf(l[a], __shfl_xor_sync(0xffffffffu, l[a], sft));
         h[a] = fmaxf(h[a], __shfl_xor_sync(0xffffffffu, h[a], sft));
       }
+      gl[a] = fminf(gl[a], l[a]), gh[a] = fmaxf(gh[a], h[a]);
+    }
     if (lane == 0) bo[2 * b] = make_float4(l[0], l[1], l[2], 0.f), bo[2 * b + 1] = make_float4(h[0], h[1], h[2], 0.f);
   }
+  // whole-cloud box (only its magnitude is used, for the rejection margin)
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(&segbox[0][0]);  // 32 warps x 6 floats; the segment boxes are dead
+  if (lane == 0)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) red[warp * 6 + a] = gl[a], red[warp * 6 + 3 + a] = gh[a];
+  __syncthreads();
   if (tid == 0) {
-    bo[2 * nblk] = make_float4(bb[0], bb[1], bb[2], 0.f);
-    bo[2 * nblk + 1] = make_float4(bb[3], bb[4], bb[5], 0.f);
+    float l[3] = {inf, inf, inf}, h[3] = {-inf, -inf, -inf};
+    for (int w = 0; w < nwarp; ++w)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) l[a] = fminf(l[a], red[w * 6 + a]), h[a] = fmaxf(h[a], red[w * 6 + 3 + a]);
+    bo[2 * nblk] = make_float4(l[0], l[1], l[2], 0.f);
+    bo[2 * nblk + 1] = make_float4(h[0], h[1], h[2], 0.f);
   }
 }
 
