@@ -123,8 +123,9 @@ class GaussianDiffusion:
 
     def _install(self, model, kind, eta=0.0):
         """Hands this process's update rule to the device path (no-op when it is already installed)."""
-        key = (kind, float(eta), self.num_timesteps, self.original_num_steps, tuple(self.timestep_map[:4]),
-               self.timestep_map[-1])
+        key = (kind, float(eta), self.original_num_steps, tuple(self.timestep_map))
+        if getattr(model, "_rule_key", None) == key and getattr(model, "_handle", None) is not None:
+            return  # already installed: the step-by-step API calls this once per step
         c1, c2, sigma = self.ancestral_rule() if kind == "ancestral" else self.ddim_rule(eta)
         model.set_sampler_rule(key, c1, c2, sigma, self.timestep_map, self.original_num_steps)
 
