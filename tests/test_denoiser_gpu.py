@@ -175,3 +175,30 @@ def test_errors():
         m(x, torch.zeros(2, dtype=torch.long, device="cuda"), bad)
     with pytest.raises(ValueError):
         m(torch.zeros(2, 98, 1, 16, device="cuda"), torch.zeros(2, dtype=torch.long, device="cuda"), batch)
+
+
+@pytest.mark.parametrize("B,T,nobj", [(1, 171, 1), (3, 1, 2), (2, 7, 8), (5, 123, 3)])
+def test_forward_edge_shapes_vs_oracle(B, T, nobj):
+    """Edge shapes against the live fp32 oracle: the longest sequence the path accepts (T = 171: 176 tokens, the full
+    attention tile), a single frame, the maximum object count (8, ragged + zero padded), a frame count that is not a
+    multiple of any tile size."""
+    from oracle import tamf_oracle as orc
+    from tamf_b200 import synth
+    m, cfg = _model("arch_mdm")
+    batch = synth.make_batch(B, T, nobj=nobj, seed=B * 100 + T, ragged=nobj > 1)
+    x = torch.randn(B, 99, 1, T, generator=torch.Generator().manual_seed(T))
+    ts = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(B))
+    with torch.no_grad():
+        ref = orc.g_forward(synth.g_state_dict(cfg, 0), cfg, x, ts, batch, synth.text_features(batch["text"]))
+    out = m(x.cuda(), ts.cuda(), _dev_batch(batch)).cpu()
+    r, a = rel_l2(out.numpy(), ref.numpy()), float((out - ref).abs().max())
+    print(f"B={B} T={T} nobj={nobj} rel_l2={r:.3e} max_abs={a:.3e}")
+    assert r <= REL_TOL and a <= ABS_TOL
+
+
+def test_sequence_too_long_is_rejected():
+    from tamf_b200 import synth
+    m, cfg = _model("arch_mdm")
+    batch = _dev_batch(synth.make_batch(1, 172, nobj=1, seed=0))
+    with pytest.raises(ValueError, match="176"):
+        m(torch.zeros(1, 99, 1, 172, device="cuda"), torch.zeros(1, dtype=torch.long, device="cuda"), batch)
