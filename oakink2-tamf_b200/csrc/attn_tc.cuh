@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
   if (threadIdx.x == 0) ATC_TRACE(1);
 
   if (warp == 6) {
-    if (lane == 0) {
+    // all lanes run the issue sequence (uniform descriptors / coordinates, see elect_one()); one elected lane issues
+    if (elect_one()) {
       pdl_wait();  // QKV is the previous kernel's output
       mbar_arrive_expect_tx(&bars[0], 2 * NB * C::BLK);
 #pragma unroll
@@ -136,13 +137,15 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       mbar_arrive_expect_tx(&bars[1], NB * C::BLK);
 #pragma unroll
       for (int j = 0; j < NB; ++j) tma_load_3d_u32(sV + j * C::BLK, &tmKV, &bars[1], 2 * d + h * HD + j * 64, 0, b);
-
-      // ---- scores = Q K^T, one 128 x 176 accumulator per query tile ----
-      constexpr uint32_t id_s = umma_idesc_bf16(128, ATC_KP);
-      mbar_wait(&bars[0], 0);
-      tc_fence_after();
-      ATC_TRACE(2);
-      for (int t = 0; t < ntile; ++t) {
+    }
+    __syncwarp();
+    // ---- scores = Q K^T, one 128 x 176 accumulator per query tile ----
+    constexpr uint32_t id_s = umma_idesc_bf16(128, ATC_KP);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    if (lane == 0) ATC_TRACE(2);
+    for (int t = 0; t < ntile; ++t) {
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
           const uint32_t off = (ks >> 2) * C::BLK + (ks & 3) * 32;
@@ -151,16 +154,19 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         }
         umma_commit(&bars[2 + t]);
       }
-      // ---- O = P V ----
-      constexpr uint32_t id_o = umma_idesc_bf16_bmn(128, HD);
-      mbar_wait(&bars[1], 0);
-      ATC_TRACE(3);
-      for (int t = 0; t < ntile; ++t) {
-        mbar_wait(&bars[4 + t], 0);
-        tc_fence_after();
-        ATC_TRACE(4 + t);
-        const uint32_t pb = t ? sP1 : sP0, pblk = t ? C::P1_BLK : C::P0_BLK;
-        const uint32_t ocol = t ? 0u : (uint32_t)ATC_O0_COL;
+      __syncwarp();
+    }
+    // ---- O = P V ----
+    constexpr uint32_t id_o = umma_idesc_bf16_bmn(128, HD);
+    mbar_wait(&bars[1], 0);
+    if (lane == 0) ATC_TRACE(3);
+    for (int t = 0; t < ntile; ++t) {
+      mbar_wait(&bars[4 + t], 0);
+      tc_fence_after();
+      if (lane == 0) ATC_TRACE(4 + t);
+      const uint32_t pb = t ? sP1 : sP0, pblk = t ? C::P1_BLK : C::P0_BLK;
+      const uint32_t ocol = t ? 0u : (uint32_t)ATC_O0_COL;
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < ATC_KP / 16; ++ks) {
           umma_bf16(tmem + ocol, umma_desc_k_sw128(pb + (ks >> 2) * pblk + (ks & 3) * 32),
@@ -168,6 +174,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         }
         umma_commit(&bars[6 + t]);
       }
+      __syncwarp();
     }
   } else {
     const int t = warp >> 2, lq = warp & 3;

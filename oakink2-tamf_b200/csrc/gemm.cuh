@@ -124,6 +124,8 @@ struct GemmCfg {
   static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 256) ? 256 : 512;
   // LN: bias | gamma | beta | row statistics sum[4][128], sumsq[4][128];  otherwise: the tile's bias slice
+  // LN: bias | gamma | beta | row statistics;  otherwise the tile's bias slice (BN floats: a 5th ring stage of the
+  // BN = 256 kernels depends on this staying at 1 KB)
   static constexpr int PARAM_BYTES = epi_is_ln(EPI) ? (3 * BN * 4 + 2 * 4 * 128 * 4) : (BN * 4);
   static constexpr int STG_BYTES = epi_staged(EPI) ? GEMM_EPI_WARPS * GEMM_STG_WARP : 0;
   static constexpr int RING_BUDGET = GEMM_SMEM_MAX - 1024 - GEMM_CTRL_BYTES - PARAM_BYTES - STG_BYTES;
@@ -284,7 +286,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
-  const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
+  // Tile schedule: tiles are numbered n-major (tile = n * tiles_m + m) and every CTA pair takes a CONTIGUOUS run of
+  // ceil(num_tiles / pairs) tiles, so consecutive tiles of a pair share the weight tile and the bias slice (restaged
+  // only when n changes) -- same makespan as a strided schedule (252 / 336 tiles over 74 pairs: 4 / 5 tiles per pair).
+  const int n_pairs = gridDim.x / CG;
+  const int per_pair = (num_tiles + n_pairs - 1) / n_pairs;
+  const int first_tile = (blockIdx.x / CG) * per_pair;
+  const int last_tile = min(num_tiles, first_tile + per_pair);
 
   if (threadIdx.x == 0) GEMM_TRACE(0);
   if (warp == PW && lane == 0) {
@@ -337,12 +345,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   if (warp == PW) {
     // ===================== TMA producer (both CTAs of a pair) =====================
-    if (lane == 0) {
+    // all lanes run the loop (uniform addresses / coordinates); one elected lane issues
+    {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       int it = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
-        const int m0 = (tile / tiles_n) * (GEMM_BM * CG) + (int)rank * GEMM_BM, n0 = (tile % tiles_n) * BN;
-        GEMM_TRACE(8 + 2 * it);
+      for (int tile = first_tile; tile < last_tile; ++tile, ++it) {
+        const int m0 = (tile % tiles_m) * (GEMM_BM * CG) + (int)rank * GEMM_BM, n0 = (tile / tiles_m) * BN;
+        if (lane == 0) GEMM_TRACE(8 + 2 * it);
         if constexpr (LN) {
           // the LN epilogue stages through this CTA's ring: do not refill it before that epilogue has drained
           mbar_wait(&ldone_bar[acc], acc_phase ^ 1u);
@@ -355,68 +364,79 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if constexpr (CG == 2) {
             const uint32_t bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
             const bool skip_w = (p.dbg & 16) && (it > 0 || kb >= STAGES);  // probe: W stays whatever the ring holds
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], skip_w ? 2 * Cfg::A_BYTES : 2 * Cfg::STAGE_BYTES);
-            tma_load_2d_2sm(a_dst, &tmA, bar, kb * BK, m0);
+            if (elect_one()) {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], skip_w ? 2 * Cfg::A_BYTES : 2 * Cfg::STAGE_BYTES);
+              tma_load_2d_2sm(a_dst, &tmA, bar, kb * BK, m0);
 #pragma unroll
-            for (int h = 0; h < NH; ++h)
-              if (!skip_w)
-                tma_load_2d_2sm(b_dst + h * Cfg::BOX_B * BK * 2, &tmB, bar, kb * BK, n0 + h * UN + (int)rank * Cfg::BOX_B);
+              for (int h = 0; h < NH; ++h)
+                if (!skip_w)
+                  tma_load_2d_2sm(b_dst + h * Cfg::BOX_B * BK * 2, &tmB, bar, kb * BK, n0 + h * UN + (int)rank * Cfg::BOX_B);
+            }
             // (no arrive from the peer: a remote release-arrive blocks ~1500 cycles per k-block; the peer's bytes are
             //  already accounted for by the leader's expect_tx, and its loads for the next use of a slot cannot be
             //  issued before the multicast commit that follows the completion of this phase)
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
 #pragma unroll
-            for (int h = 0; h < NH; ++h)
-              tma_load_2d(b_dst + h * Cfg::BOX_B * BK * 2, &tmB, &full_bar[stage], kb * BK, n0 + h * UN);
+              for (int h = 0; h < NH; ++h)
+                tma_load_2d(b_dst + h * Cfg::BOX_B * BK * 2, &tmB, &full_bar[stage], kb * BK, n0 + h * UN);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1u;
         }
-        GEMM_TRACE(9 + 2 * it);
+        if (lane == 0) GEMM_TRACE(9 + 2 * it);
       }
     }
   } else if (warp == PW + 1) {
     // ===================== MMA issuer (leader CTA) =====================
-    if (lane == 0 && rank == 0) {
+    // all lanes run the loop so that the shared-memory descriptors are warp-uniform; one elected lane issues
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, UN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       int it = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+      for (int tile = first_tile; tile < last_tile; ++tile, ++it) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (kb == 0) GEMM_TRACE(24 + 2 * it);
-          if (it == 1 && kb < 8) GEMM_TRACE(56 + kb);
+          if (lane == 0) {
+            if (kb == 0) GEMM_TRACE(24 + 2 * it);
+            if (it == 1 && kb < 8) GEMM_TRACE(56 + kb);
+          }
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = (BK == 64) ? umma_desc_k_sw128(a_addr + k * 32) : umma_desc_k_sw64(a_addr + k * 32);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = (BK == 64) ? umma_desc_k_sw128(a_addr + k * 32) : umma_desc_k_sw64(a_addr + k * 32);
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {
-              const uint32_t bh = b_addr + h * Cfg::BOX_B * BK * 2 + k * 32;
-              const uint64_t bd = (BK == 64) ? umma_desc_k_sw128(bh) : umma_desc_k_sw64(bh);
-              if constexpr (CG == 2)
-                umma_bf16_2sm(d_tmem + h * UN, ad, bd, idesc, (kb | k) ? 1u : 0u);
-              else
-                umma_bf16(d_tmem + h * UN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+              for (int h = 0; h < NH; ++h) {
+                const uint32_t bh = b_addr + h * Cfg::BOX_B * BK * 2 + k * 32;
+                const uint64_t bd = (BK == 64) ? umma_desc_k_sw128(bh) : umma_desc_k_sw64(bh);
+                if constexpr (CG == 2)
+                  umma_bf16_2sm(d_tmem + h * UN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                else
+                  umma_bf16(d_tmem + h * UN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+              }
+            }
+            // ring slot reusable (in both CTAs) once these MMAs have read it; last k-block publishes the accumulator
+            if constexpr (CG == 2) {
+              umma_commit_2sm(&empty_bar[stage]);
+              if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
             }
           }
-          // ring slot reusable (in both CTAs) once these MMAs have read it; last k-block publishes the accumulator
-          if constexpr (CG == 2) {
-            umma_commit_2sm(&empty_bar[stage]);
-            if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
-          } else {
-            umma_commit(&empty_bar[stage]);
-            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
-          }
+          __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1u;
         }
-        GEMM_TRACE(25 + 2 * it);
+        if (lane == 0) GEMM_TRACE(25 + 2 * it);
         if (++acc == ACC) acc = 0, acc_phase ^= 1u;
       }
     }
@@ -431,12 +451,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint32_t rpar = 0;  // LN: parity bits of the two residual-tile mbarriers of this warp
     int staged_n0 = -1;
     int it = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
-      const int m0 = (tile / tiles_n) * (GEMM_BM * CG) + (int)rank * GEMM_BM, n0 = (tile % tiles_n) * BN;
+    for (int tile = first_tile; tile < last_tile; ++tile, ++it) {
+      const int m0 = (tile % tiles_m) * (GEMM_BM * CG) + (int)rank * GEMM_BM, n0 = (tile / tiles_m) * BN;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < p.M;
       const int grow0 = m0 + lq * 32;  // first global row of this warp
-      if constexpr (!LN) {
+      if constexpr (epi_tma_bf16(EPI)) {
+        if (n0 != staged_n0) {  // the 64 bias values of this column quarter, shared by its 4 warps (named barrier of
+                                // 128 threads instead of a CTA-wide one between tiles)
+          float* wb = s_bias + cq * QW;
+          const int c = n0 + cq * QW + lane;
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + cq) : "memory");  // the quarter has left the previous slice
+          if (lq == 0) {
+            wb[lane] = (p.bias && c < p.N) ? p.bias[c] : 0.f;
+            wb[lane + 32] = (p.bias && c + 32 < p.N) ? p.bias[c + 32] : 0.f;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + cq) : "memory");
+          staged_n0 = n0;
+        }
+      } else if constexpr (!LN) {
         if (n0 != staged_n0) {  // (re)stage the tile's bias slice; all 16 warps walk the same tile sequence
           asm volatile("bar.sync 1, 512;" ::: "memory");
           for (int i = threadIdx.x; i < BN; i += PT) s_bias[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
@@ -620,29 +653,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         static_assert(BN == 256, "the TMA-store bf16 epilogue is written for 64-column warp slabs (BN = 256)");
         const uint32_t wst = smem_u32(s_stage) + warp * GEMM_STG_WARP;
         const int cl = cq * QW;
+        const float* wb = s_bias + cl;
+        // The TMEM read port (16 B/clk per sub-partition) and the math would otherwise alternate: all four warps of a
+        // sub-partition wait for their loads, then all compute.  Load the second 32 columns while the first are
+        // processed, so that one warp's loads overlap another's arithmetic.
         uint32_t v0[32], v1[32];
         tmem_ld32(taddr, v0);
+        tc_wait_ld_dep(v0);
         tmem_ld32(taddr + 32, v1);
-        tc_wait_ld();
-        release_acc();
         if (lane == 0) bulk_wait_read<0>();  // the previous tile's store has finished reading the staging tile
         __syncwarp();
-        if (n0 + cl < p.N) {  // warp-uniform (N is a multiple of 64)
+        const bool live = n0 + cl < p.N;  // warp-uniform (N is a multiple of 64)
+        auto half = [&](const uint32_t (&vv)[32], int j0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t* v = (j < 4) ? (v0 + j * 8) : (v1 + (j - 4) * 8);
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j0 + jj;
+            const uint32_t* v = vv + jj * 8;
             uint32_t o[4];
             if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {  // packed pairs: bias add + GELU as FADD2 / FFMA2 chains
-                const float2 b2 = *reinterpret_cast<const float2*>(s_bias + cl + j * 8 + 2 * e);
+                const float2 b2 = *reinterpret_cast<const float2*>(wb + j * 8 + 2 * e);
                 const f32x2 y = gelu_erf2(add2(pk2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), pk2(b2.x, b2.y)));
                 o[e] = pack_bf16x2(pk_lo(y), pk_hi(y));
               }
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 b2 = *reinterpret_cast<const float2*>(s_bias + cl + j * 8 + 2 * e);
+                const float2 b2 = *reinterpret_cast<const float2*>(wb + j * 8 + 2 * e);
                 float y0 = __uint_as_float(v[2 * e]) + b2.x, y1 = __uint_as_float(v[2 * e + 1]) + b2.y;
                 if constexpr (EPI == EPI_BIAS_SILU_BF16) y0 = silu(y0), y1 = silu(y1);
                 o[e] = pack_bf16x2(y0, y1);
@@ -650,6 +688,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
             sts128(wst + stg128_off(lane, j), make_uint4(o[0], o[1], o[2], o[3]));
           }
+        };
+        if (live) half(v0, 0);
+        tc_wait_ld_dep(v1);
+        release_acc();  // the whole accumulator slab of this warp is in registers
+        if (live) {
+          half(v1, 4);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
