@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           tma_load_2d_u32(wst + (ck & 1) * 4096, &tmC, smem_u32(&rb[ck & 1]), ccol0 + ck * 32, grow0);
           tma_load_2d_u32(wst + (ck & 1) * 4096 + 2048, &tmX, smem_u32(&rb[ck & 1]), ccol0 + ck * 32, grow0);
         };
-        if (lane == 0) {
+        if (elect_one()) {  // TMA issue on uniform operands (see elect_one())
           prefetch(0);
           if (CHUNKS > 1) prefetch(1);
         }
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
           tmem_st32(taddr + ck * 32, v);
           __syncwarp();  // every lane has read this residual buffer: it may be refilled
-          if (lane == 0 && ck + 2 < CHUNKS) prefetch(ck + 2);
+          if (ck + 2 < CHUNKS && elect_one()) prefetch(ck + 2);
         }
         tc_wait_st();
         if (threadIdx.x == 0) GEMM_TRACE(4);
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           tc_wait_ld();
           if (ck == CHUNKS - 1) release_acc();  // last TMEM read of this tile
           if (ck >= 2) {  // the stores of chunk ck - 2 must have finished reading this staging set
-            if (lane == 0) bulk_wait_read<1>();
+            if (elect_one()) bulk_wait_read<1>();
             __syncwarp();
           }
           const int c0 = ccol0 + ck * 32;
@@ -592,13 +592,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(p.dbg & 1)) {
+          if (!(p.dbg & 1) && elect_one()) {
             if (!(p.dbg & 8)) tma_store_2d(&tmC, s_outh, c0, grow0);  // rows past M are clipped by the tensor map
             if (!(p.dbg & 4)) tma_store_2d(&tmX, s_outl, c0, grow0);
             bulk_commit();
           }
         }
-        if (lane == 0) {
+        if (elect_one()) {
           bulk_wait_read<0>();          // staging lives in the ring: the producer may refill it only now
           mbar_arrive(&ldone_bar[acc]);
         }
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tmem_ld32(taddr, v0);
         tc_wait_ld_dep(v0);
         tmem_ld32(taddr + 32, v1);
-        if (lane == 0) bulk_wait_read<0>();  // the previous tile's store has finished reading the staging tile
+        if (elect_one()) bulk_wait_read<0>();  // the previous tile's store has finished reading the staging tile
         __syncwarp();
         const bool live = n0 + cl < p.N;  // warp-uniform (N is a multiple of 64)
         auto half = [&](const uint32_t (&vv)[32], int j0) {
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           half(v1, 4);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_2d(&tmC, wst, n0 + cl, grow0);  // rows past M / columns past N are clipped
             bulk_commit();
           }
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (++acc == ACC) acc = 0, acc_phase ^= 1u;
     }
     if constexpr (LN || epi_tma_bf16(EPI)) {
-      if (lane == 0) bulk_wait<0>();  // this thread's TMA stores have been performed before the CTA retires
+      if (elect_one()) bulk_wait<0>();  // this thread's TMA stores have been performed before the CTA retires
     }
     (void)rpar;
   }
