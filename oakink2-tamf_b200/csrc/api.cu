@@ -252,8 +252,10 @@ extern "C" int tamf_gemm_trace(int which, const uint16_t* a, const uint16_t* w, 
   p.dbg = getenv("TAMF_GEMM_DBG") ? atoi(getenv("TAMF_GEMM_DBG")) : 0;
   CUtensorMap tmC, tmX;
   if (which == 2) {
-    if ((rc = make_tmap_2d_bf16(&tmC, out, N, M, (uint64_t)N * 2, 32, 32))) return rc;
-    if ((rc = make_tmap_2d_bf16(&tmX, X, N, M, (uint64_t)N * 2, 32, 32))) return rc;  // low plane (bf16 view of the buffer)
+    p.ln_rq = gemm_ln_rq(M);
+    if ((rc = make_tmap_2d_bf16(&tmA, a, K, M, (uint64_t)K * 2, 64, 32))) return rc;  // one box per TMEM lane quarter
+    if ((rc = make_tmap_2d_bf16(&tmC, out, N, M, (uint64_t)N * 2, 32, (uint32_t)p.ln_rq))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tmX, X, N, M, (uint64_t)N * 2, 32, (uint32_t)p.ln_rq))) return rc;  // low plane (bf16 view of the buffer)
     p.tmC = &tmC, p.tmX = &tmX;
     p.Xlo = (__nv_bfloat16*)X, p.Xb = (__nv_bfloat16*)out, p.gamma = bias, p.beta = bias;
     if ((rc = configure_gemm<512, EPI_RES_LN, 2>())) return rc;

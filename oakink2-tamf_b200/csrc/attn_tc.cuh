@@ -19,6 +19,8 @@
 // Tile-1 rows beyond the 176 loaded tokens read whatever follows in shared memory: each accumulator row depends on
 // its own A row only, and those rows are never stored.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tamf {
@@ -65,6 +67,36 @@ __device__ __forceinline__ float atc_ex2(float x) {  // x <= 0 here: flush-to-ze
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x for a pair of arguments x <= 0 on the FMA pipe (packed fp32 pairs), for the share of the softmax exponentials
+// the MUFU unit (16 results / clk / SM) cannot take: x = n + f with n = rint(x) (magic-number rounding), |f| <= 0.5,
+// 2^f by the degree-4 Taylor polynomial of e^(f ln 2) (relative error < 5e-5, far below the bf16 rounding of the
+// probabilities), 2^n added into the exponent field.  Arguments below -125 (and the -inf of masked keys) give 2^-125:
+// such keys meet zero rows of V and add nothing visible to the row sum.
+__device__ __forceinline__ void atc_ex2_poly2(float x0, float x1, float& p0, float& p1) {
+  typedef unsigned long long u64;
+  auto pk = [](float lo, float hi) { return (u64)__float_as_uint(lo) | ((u64)__float_as_uint(hi) << 32); };
+  auto fma2 = [](u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+  };
+  auto add2 = [](u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+  };
+  const u64 x = pk(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const u64 t = add2(x, pk(12582912.f, 12582912.f));       // 1.5 * 2^23 + n in the low mantissa bits
+  const u64 n = add2(t, pk(-12582912.f, -12582912.f));
+  const u64 f = fma2(n, pk(-1.f, -1.f), x);
+  u64 q = pk(9.618129e-3f, 9.618129e-3f);
+  q = fma2(q, f, pk(5.550411e-2f, 5.550411e-2f));
+  q = fma2(q, f, pk(2.402265e-1f, 2.402265e-1f));
+  q = fma2(q, f, pk(6.931472e-1f, 6.931472e-1f));
+  q = fma2(q, f, pk(1.f, 1.f));
+  p0 = __uint_as_float((uint32_t)q + ((uint32_t)t << 23));
+  p1 = __uint_as_float((uint32_t)(q >> 32) + ((uint32_t)(t >> 32) << 23));
 }
 __device__ __forceinline__ void atc_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -185,6 +217,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       mbar_wait(&bars[2 + t], 0);
       tc_fence_after();
       if (lane == 0 && lq == 0) ATC_TRACE(6 + t);
+      // The row's 176 scores come out of TMEM with all six loads in flight at once (a chunk-by-chunk pipeline against the
+      // maximum was slower: tcgen05.wait::ld waits for every outstanding load, so each chunk paid the full latency).
+      // Row maximum on four independent chains.  Keys >= S are zero-filled by TMA and masked here; with S >= 160 (the
+      // production shape) only the last 16 columns can be masked, which spares the other 160 a compare and a select.
       uint32_t v[ATC_KP];
       {
         const uint32_t ta = tmem + lane_sel + t * ATC_KP;
@@ -193,31 +229,61 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         tmem_ld16(ta + 160, &v[160]);
         tc_wait_ld();
       }
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (S >= 160) {  // warp-uniform
 #pragma unroll
-      for (int k = 0; k < ATC_KP; ++k) {
-        float s = __uint_as_float(v[k]);
-        if (k >= S) s = -INFINITY;  // zero-filled keys beyond the sequence
-        v[k] = __float_as_uint(s);
-        mx = fmaxf(mx, s);
+        for (int k = 0; k < 160; ++k) mx4[k & 3] = fmaxf(mx4[k & 3], __uint_as_float(v[k]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 160; ++k) {
+          float sc = __uint_as_float(v[k]);
+          if (k >= S) sc = -INFINITY;
+          v[k] = __float_as_uint(sc);
+          mx4[k & 3] = fmaxf(mx4[k & 3], sc);
+        }
       }
+#pragma unroll
+      for (int k = 160; k < ATC_KP; ++k) {
+        float sc = __uint_as_float(v[k]);
+        if (k >= S) sc = -INFINITY;
+        v[k] = __float_as_uint(sc);
+        mx4[k & 3] = fmaxf(mx4[k & 3], sc);
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float c2 = rsqrtf((float)HD) * 1.4426950408889634f;
       const float mc = -mx * c2;
       float sum0 = 0.f, sum1 = 0.f;
       const uint32_t prow = (t ? sP1 : sP0) + r * 128;
       const uint32_t pblk = t ? C::P1_BLK : C::P0_BLK;
+      // Experiment kept behind TAMF_ATTN_DBG=2: exp2 of 3 in 8 elements as a polynomial on the FMA pipe (atc_ex2_poly2),
+      // because two softmax warps share sub-partitions 0 and 1 (tile 0 and tile 1 rows) and 176 MUFU results per row set
+      // their pace.  It shortens the softmax phase of a CTA by ~0.4 k cycles (3.6 k -> 3.2 k) but neither the grid span
+      // (two waves of 148 + 108 CTAs, 13.8 us) nor the in-chain time (20.5 us per launch) moves, so the exact-path MUFU
+      // form stays the default (profiles/r01_exp_attn_softmax.txt).
+      auto exp_pass = [&](auto poly) {
 #pragma unroll
-      for (int c8 = 0; c8 < ATC_KP / 8; ++c8) {
-        uint32_t pk[4];
+        for (int c8 = 0; c8 < ATC_KP / 8; ++c8) {
+          uint32_t pk[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float p0 = atc_ex2(fmaf(__uint_as_float(v[c8 * 8 + 2 * e]), c2, mc));
-          const float p1 = atc_ex2(fmaf(__uint_as_float(v[c8 * 8 + 2 * e + 1]), c2, mc));
-          sum0 += p0, sum1 += p1;
-          pk[e] = pack_bf16x2(p0, p1);
+          for (int e = 0; e < 4; ++e) {
+            const float a0 = fmaf(__uint_as_float(v[c8 * 8 + 2 * e]), c2, mc);
+            const float a1 = fmaf(__uint_as_float(v[c8 * 8 + 2 * e + 1]), c2, mc);
+            float p0, p1;
+            if (decltype(poly)::value && (e == 3 || (e == 2 && (c8 & 1)))) {
+              atc_ex2_poly2(a0, a1, p0, p1);
+            } else {
+              p0 = atc_ex2(a0), p1 = atc_ex2(a1);
+            }
+            sum0 += p0, sum1 += p1;
+            pk[e] = pack_bf16x2(p0, p1);
+          }
+          atc_sts128(prow + (c8 >> 3) * pblk + (((c8 & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
-        atc_sts128(prow + (c8 >> 3) * pblk + (((c8 & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
-      }
+      };
+      if (dbg & 2)  // experiment (TAMF_ATTN_DBG=2): 3 in 8 exponentials on the FMA pipe
+        exp_pass(std::true_type{});
+      else
+        exp_pass(std::false_type{});
       const float inv = 1.0f / (sum0 + sum1);
       tc_fence_before();
       fence_proxy_async_smem();  // P is read by the tensor core through the async proxy

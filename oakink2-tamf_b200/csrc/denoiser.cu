@@ -64,19 +64,18 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
   for (int c = threadIdx.x; c < d; c += blockDim.x) o[c] = s[c];
 }
 
-__global__ void add_int_kernel(int* p, int n, int dv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] += dv;
-}
-
 // prep: grid (ceil(T/32), B), 256 threads.
 //  (a) A0[b*T+tau, k] = bf16(x[b,k,0,tau]) (k < nfeat), 0 for the K padding -- transposed through shared memory so
 //      both the read (along tau) and the write (along k) are coalesced.
 //  (b) blockIdx.x == 0 also writes the 5 prefix token rows of sequence b into the residual planes Xb / Xlo.
+//  (c) chain mode (t_cur != null): the same CTA publishes this step's timestep as t_cur[b] (read by the posterior
+//      epilogue at the end of the step) and advances the chain counter t_ptr[b] to t - 1 for the next replay of the
+//      step graph -- no other CTA of the step reads t_ptr.
 __global__ void __launch_bounds__(256)
-    prep_kernel(const float* __restrict__ x, const int* __restrict__ t_ptr, const float* __restrict__ ttab,
-                const float* __restrict__ pe, const float* __restrict__ prefix, __nv_bfloat16* __restrict__ A0,
-                __nv_bfloat16* __restrict__ Xlo, __nv_bfloat16* __restrict__ Xb, int T, int S, int d, int nfeat) {
+    prep_kernel(const float* __restrict__ x, int* __restrict__ t_ptr, int* __restrict__ t_cur,
+                const float* __restrict__ ttab, const float* __restrict__ pe, const float* __restrict__ prefix,
+                __nv_bfloat16* __restrict__ A0, __nv_bfloat16* __restrict__ Xlo, __nv_bfloat16* __restrict__ Xb, int T,
+                int S, int d, int nfeat) {
   __shared__ float tile[KPAD][33];
   const int b = blockIdx.y, tau0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -95,6 +94,10 @@ __global__ void __launch_bounds__(256)
   }
   if (blockIdx.x == 0) {
     const int t = t_ptr[b];
+    if (t_cur) {
+      __syncthreads();  // every thread of the CTA has read t_ptr[b]
+      if (threadIdx.x == 0) t_cur[b] = t, t_ptr[b] = t - 1;
+    }
     for (int i = threadIdx.x; i < 5 * d; i += 256) {
       const int s = i / d, c = i % d;
       float v;
@@ -139,7 +142,7 @@ struct tamf_denoiser {
   bool bound = false, cond_set = false;
   float *prefix, *trajmean, *shapemean, *embmean, *xbuf;
   float *st_text, *st_shape, *st_traj, *st_emb;  // host-API staging
-  int *st_side, *t_dev;
+  int *st_side, *t_dev, *t_cur;
   __nv_bfloat16 *A0, *H0;
   CUtensorMap tm_A0, tm_H0, tm_H0_st, tm_Xb_fin;
   // cached step graph
@@ -161,14 +164,17 @@ static int upload_bf16(tamf_denoiser* h, __nv_bfloat16** dst, const float* src, 
 // `marks` (profiling only): one event is recorded after every kernel of the step, in launch order.
 // `model_level`: t_ptr holds ORIGINAL timesteps (model(x, t) of the reference); otherwise indices of the installed
 // K-step rule (what SpacedDiffusion hands to _WrappedModel, respace.py:114-119).
-static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, float* x_out, float* x0_out,
+// `advance` (chain graph): t_ptr is the chain counter h->t_dev; prep copies it to h->t_cur for the rest of the step and
+// decrements it for the next replay.
+static int enqueue_step(tamf_denoiser* h, const float* x_t, int* t_ptr, float* x_out, float* x0_out,
                         const float* noise, uint64_t seed, cudaStream_t s, std::vector<cudaEvent_t>* marks = nullptr,
-                        bool model_level = false) {
+                        bool model_level = false, bool advance = false) {
   const int d = h->d, B = h->B, T = h->T, S = h->S, M = h->M, Mf = h->Mf;
   int rc;
   mark_event(marks, s);
-  prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, model_level ? h->ttab : h->k_ttab, h->pe, h->prefix, h->A0, h->buf.Xlo, h->buf.Xb, T,
-                                                     S, d, h->nfeat);
+  prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, advance ? h->t_cur : nullptr,
+                                                     model_level ? h->ttab : h->k_ttab, h->pe, h->prefix, h->A0,
+                                                     h->buf.Xlo, h->buf.Xb, T, S, d, h->nfeat);
   TAMF_LAUNCH_CHECK();
   mark_event(marks, s);
   {  // embed-a
@@ -188,7 +194,7 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, const int* t_ptr, fl
   {  // final projection + DDPM posterior
     GemmParams p{};
     p.M = M, p.N = h->nfeat, p.K = d, p.bias = h->b_fin, p.T = T, p.S = S, p.P0 = 5, p.nfeat = h->nfeat;
-    p.x_t = x_t, p.x_out = x_out, p.x0_out = x0_out, p.noise = noise, p.t_ptr = t_ptr, p.c1 = h->k1, p.c2 = h->k2,
+    p.x_t = x_t, p.x_out = x_out, p.x0_out = x0_out, p.noise = noise, p.t_ptr = advance ? h->t_cur : t_ptr, p.c1 = h->k1, p.c2 = h->k2,
     p.sigma = h->ks, p.seed = seed;
     if ((rc = launch_gemm<128, EPI_POSTERIOR, 2>(h->tm_Xb_fin, h->tm_wfin, p, s))) return rc;
     mark_event(marks, s);
@@ -353,7 +359,7 @@ static WsLayout ws_layout(const tamf_denoiser* h, int B, int T) {
       (size_t)B * MAX_NOBJ * T * 9 * 4,          // 16 st_traj
       (size_t)B * MAX_NOBJ * h->cfg.obj_embed_dim * 4,  // 17 st_emb
       (size_t)B * 4,                             // 18 st_side
-      (size_t)B * 4,                             // 19 t_dev
+      (size_t)B * 4 * 2,                         // 19 t_dev (chain counter) | t_cur (timestep of the running step)
   };
   WsLayout L{};
   size_t o = 0;
@@ -401,6 +407,7 @@ extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size
   h->st_emb = (float*)(p + L.off[17]);
   h->st_side = (int*)(p + L.off[18]);
   h->t_dev = (int*)(p + L.off[19]);
+  h->t_cur = h->t_dev + B;
   const int d = h->d, ff = h->ff;
   int rc;
   if ((rc = h->buf.make_maps(d, ff))) return rc;
@@ -458,7 +465,9 @@ extern "C" int tamf_denoiser_set_cond(tamf_denoiser* h, const float* text_feat, 
 extern "C" int tamf_denoiser_forward(tamf_denoiser* h, const float* x_t, const int32_t* t, float* x0_out, void* stream) {
   TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_denoiser_forward: bind + set_cond first");
   TAMF_REQUIRE(x_t && t && x0_out, TAMF_E_BADARG, "tamf_denoiser_forward: null pointer");
-  return enqueue_step(h, x_t, t, nullptr, x0_out, nullptr, 0, (cudaStream_t)stream, nullptr, /*model_level=*/true);
+  // (t is only written in chain mode, `advance`)
+  return enqueue_step(h, x_t, const_cast<int32_t*>(t), nullptr, x0_out, nullptr, 0, (cudaStream_t)stream, nullptr,
+                      /*model_level=*/true);
 }
 
 extern "C" int tamf_denoiser_set_sampler(tamf_denoiser* h, int K, const float* c1, const float* c2, const float* sigma,
@@ -544,11 +553,7 @@ extern "C" int tamf_p_sample_chain(tamf_denoiser* h, float* x_io, int t_start, i
     cudaGraph_t g = nullptr;
     TAMF_CUDA_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     const uint64_t before = g_launches.load();
-    int rc = enqueue_step(h, x_io, h->t_dev, x_io, nullptr, nullptr, seed, cap);
-    if (rc == TAMF_OK) {
-      add_int_kernel<<<(h->B + 255) / 256, 256, 0, cap>>>(h->t_dev, h->B, -1);
-      count_launch();
-    }
+    int rc = enqueue_step(h, x_io, h->t_dev, x_io, nullptr, nullptr, seed, cap, nullptr, false, /*advance=*/true);
     g_launches.store(before);  // capture records, it does not launch; replays are counted below
     cudaError_t e = cudaStreamEndCapture(cap, &g);
     if (own) cudaStreamDestroy(own);
@@ -566,7 +571,7 @@ extern "C" int tamf_p_sample_chain(tamf_denoiser* h, float* x_io, int t_start, i
     int rc0 = fill_int(h->t_dev, h->B, t_start, s);
     if (rc0) return rc0;
   }
-  const int per_step = 2 + 5 * h->L + 2 + 1;
+  const int per_step = 2 + 5 * h->L + 2;
   for (int t = t_start; t >= t_end; --t) {
     TAMF_CUDA_CHECK(cudaGraphLaunch(h->graph_exec, s));
     count_launch(per_step);

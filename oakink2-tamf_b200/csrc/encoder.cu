@@ -195,12 +195,14 @@ int EncoderStack::upload(DevPool& pool, const tamf_layer_weights* w, int d_, int
 int EncoderBuffers::make_maps(int d, int ff) {
   int rc;
   if ((rc = make_tmap_2d_bf16(&tm_Xb, Xb, d, M, (uint64_t)d * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tm_ATT, ATT, d, M, (uint64_t)d * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tm_H, Hb, ff, M, (uint64_t)ff * 2, 64, 128))) return rc;
+  // A operands of the two LayerNorm GEMMs: 32-row boxes (one per TMEM lane quarter, ln_rq rows apart; gemm_ln_rq())
+  ln_rq = gemm_ln_rq(M);
+  if ((rc = make_tmap_2d_bf16(&tm_ATT, ATT, d, M, (uint64_t)d * 2, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_H, Hb, ff, M, (uint64_t)ff * 2, 64, 32))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_QKV_st, QKV, 3 * d, M, (uint64_t)3 * d * 2, 64, 32))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_H_st, Hb, ff, M, (uint64_t)ff * 2, 64, 32))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tm_Xb_st, Xb, d, M, (uint64_t)d * 2, 32, 32))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tm_Xlo, Xlo, d, M, (uint64_t)d * 2, 32, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_Xb_st, Xb, d, M, (uint64_t)d * 2, 32, (uint32_t)ln_rq))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_Xlo, Xlo, d, M, (uint64_t)d * 2, 32, (uint32_t)ln_rq))) return rc;
   AttnTcMaps at;
   if ((rc = make_attn_tc_maps(&at, QKV, ATT, B, S, d))) return rc;
   tm_att_kv = at.kv, tm_att_o = at.o;
@@ -241,7 +243,7 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     {
       GemmParams p{};
       p.M = M, p.N = d, p.K = d, p.bias = w.b_out, p.Xlo = buf.Xlo, p.Xb = buf.Xb, p.gamma = w.g1, p.beta = w.be1;
-      p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_Xlo;
+      p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_Xlo, p.ln_rq = buf.ln_rq;
       rc = (d == 512) ? launch_gemm<512, EPI_RES_LN, 2>(buf.tm_ATT, w.tm_out, p, s)
                       : launch_gemm<256, EPI_RES_LN, 2>(buf.tm_ATT, w.tm_out, p, s);
       if (rc) return rc;
@@ -256,7 +258,7 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     {
       GemmParams p{};
       p.M = M, p.N = d, p.K = ff, p.bias = w.b2, p.Xlo = buf.Xlo, p.Xb = buf.Xb, p.gamma = w.g2, p.beta = w.be2;
-      p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_Xlo;
+      p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_Xlo, p.ln_rq = buf.ln_rq;
       rc = (d == 512) ? launch_gemm<512, EPI_RES_LN, 2>(buf.tm_H, w.tm_w2, p, s)
                       : launch_gemm<256, EPI_RES_LN, 2>(buf.tm_H, w.tm_w2, p, s);
       if (rc) return rc;

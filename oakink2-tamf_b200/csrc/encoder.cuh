@@ -48,9 +48,11 @@ struct EncoderBuffers {
   __nv_bfloat16* QKV = nullptr;   // [M,3d]
   __nv_bfloat16* ATT = nullptr;   // [M,d]
   __nv_bfloat16* Hb = nullptr;    // [M,ff]
-  CUtensorMap tm_Xb, tm_ATT, tm_H;              // GEMM A-operand loads, box {64, 128}
+  CUtensorMap tm_Xb, tm_ATT, tm_H;              // GEMM A-operand loads, box {64, 128} (tm_ATT / tm_H feed the LayerNorm
+                                                // GEMMs: box {64, 32}, one per TMEM lane quarter)
+  int ln_rq = 32;                               // rows per lane quarter of the LayerNorm tiles (gemm_ln_rq(M))
   CUtensorMap tm_QKV_st, tm_H_st;               // bf16 epilogue stores, box {64, 32}
-  CUtensorMap tm_Xb_st, tm_Xlo;                 // LayerNorm epilogue: Xb / Xlo residual load + store, box {32, 32} bf16
+  CUtensorMap tm_Xb_st, tm_Xlo;                 // LayerNorm epilogue: Xb / Xlo residual load + store, box {32, ln_rq} bf16
   CUtensorMap tm_att_kv, tm_att_o;    // attention: [B][S][3d] views of QKV (K/V box, Q box), [B][S][d] view of ATT
   int make_maps(int d, int ff);
 };

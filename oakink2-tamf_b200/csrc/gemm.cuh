@@ -70,6 +70,10 @@ struct GemmParams {
   __nv_bfloat16* Xb;
   const float* gamma;
   const float* beta;
+  // EPI_RES_LN: rows of the result each TMEM lane quarter of a CTA owns (1..32, gemm_ln_rq()).  A CTA covers 4 * ln_rq
+  // consecutive rows: quarter q computes rows [m0 + q ln_rq, +32) (A arrives as four 32-row boxes) and keeps the first
+  // ln_rq of them.  32 = dense 128-row tiles; fewer rows spread the store-bound epilogue over more SMs (see gemm_ln_rq).
+  int ln_rq;
   // EPI_POSTERIOR / EPI_RESIDUAL_OUT: GEMM row m = b*S + s (token); frame tau = s - P0
   const float* x_t;    // [B,nfeat,1,T] (POSTERIOR) | x_in [B,T,nfeat] (RESIDUAL_OUT)
   float* x_out;        // x_{t-1}, may alias x_t; null -> forward only
@@ -80,8 +84,8 @@ struct GemmParams {
   unsigned long long seed;
   int nfeat;
   // host pointers to the TMA-store maps (copied into kernel parameters by launch_gemm):
-  //   tmC: bf16 output [M,N], box {64 cols, 32 rows} (bias/GELU/SiLU epilogues) | Xb [M,N], box {32, 32} (LN)
-  //   tmX: Xlo [M,N] bf16, box {32, 32}; the LN epilogue loads (residual) and stores (normalised) through tmC + tmX
+  //   tmC: bf16 output [M,N], box {64 cols, 32 rows} (bias/GELU/SiLU epilogues) | Xb [M,N], box {32, ln_rq} (LN)
+  //   tmX: Xlo [M,N] bf16, box {32, ln_rq}; the LN epilogue loads (residual) and stores (normalised) through tmC + tmX
   const CUtensorMap* tmC;
   const CUtensorMap* tmX;
   // debug only (tools/gemm_trace.py): per-CTA event timestamps, [grid][GEMM_TRACE_SLOTS] clock64 values; null in product
@@ -282,7 +286,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader
-  const int tiles_m = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
+  // rows per CTA / per TMEM lane quarter: dense 128 / 32, except the LayerNorm tiles (GemmParams::ln_rq)
+  const int RQ = LN ? p.ln_rq : 32;
+  const int ROWS_CTA = 4 * RQ;
+  const int tiles_m = (p.M + ROWS_CTA * CG - 1) / (ROWS_CTA * CG);
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       int it = 0;
       for (int tile = first_tile; tile < last_tile; ++tile, ++it) {
-        const int m0 = (tile % tiles_m) * (GEMM_BM * CG) + (int)rank * GEMM_BM, n0 = (tile / tiles_m) * BN;
+        const int m0 = (tile % tiles_m) * (ROWS_CTA * CG) + (int)rank * ROWS_CTA, n0 = (tile / tiles_m) * BN;
         if (lane == 0) GEMM_TRACE(8 + 2 * it);
         if constexpr (LN) {
           // the LN epilogue stages through this CTA's ring: do not refill it before that epilogue has drained
@@ -366,7 +373,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const bool skip_w = (p.dbg & 16) && (it > 0 || kb >= STAGES);  // probe: W stays whatever the ring holds
             if (elect_one()) {
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], skip_w ? 2 * Cfg::A_BYTES : 2 * Cfg::STAGE_BYTES);
-              tma_load_2d_2sm(a_dst, &tmA, bar, kb * BK, m0);
+              if constexpr (LN) {  // four 32-row boxes, RQ rows apart: TMEM lane quarter q <- rows m0 + q RQ ...
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tma_load_2d_2sm(a_dst + q * 32 * BK * 2, &tmA, bar, kb * BK, m0 + q * RQ);
+              } else {
+                tma_load_2d_2sm(a_dst, &tmA, bar, kb * BK, m0);
+              }
 #pragma unroll
               for (int h = 0; h < NH; ++h)
                 if (!skip_w)
@@ -378,7 +390,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           } else {
             if (elect_one()) {
               mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-              tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
+              if constexpr (LN) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tma_load_2d(a_dst + q * 32 * BK * 2, &tmA, &full_bar[stage], kb * BK, m0 + q * RQ);
+              } else {
+                tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
+              }
 #pragma unroll
               for (int h = 0; h < NH; ++h)
                 tma_load_2d(b_dst + h * Cfg::BOX_B * BK * 2, &tmB, &full_bar[stage], kb * BK, n0 + h * UN);
@@ -452,10 +469,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int staged_n0 = -1;
     int it = 0;
     for (int tile = first_tile; tile < last_tile; ++tile, ++it) {
-      const int m0 = (tile % tiles_m) * (GEMM_BM * CG) + (int)rank * GEMM_BM, n0 = (tile / tiles_m) * BN;
-      const int row = m0 + row_in_tile;
+      const int m0 = (tile % tiles_m) * (ROWS_CTA * CG) + (int)rank * ROWS_CTA, n0 = (tile / tiles_m) * BN;
+      const int row = m0 + lq * RQ + lane;  // dense tiles: RQ = 32
       const bool row_ok = row < p.M;
-      const int grow0 = m0 + lq * 32;  // first global row of this warp
+      const int grow0 = m0 + lq * RQ;  // first global row of this warp
       if constexpr (epi_tma_bf16(EPI)) {
         if (n0 != staged_n0) {  // the 64 bias values of this column quarter, shared by its 4 warps (named barrier of
                                 // 128 threads instead of a CTA-wide one between tiles)
@@ -477,6 +494,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           staged_n0 = n0;
         }
       }
+      // EPI_POSTERIOR: x_t and the step's coefficients do not depend on the accumulator -- fetch them before waiting
+      // for it, so their latency hides behind the mainloop.  (Inside the store loop the compiler must keep every
+      // x_t load behind the preceding x_out store, x_out may alias x_t: 25 serialised L2 round trips per thread.)
+      [[maybe_unused]] float xt[32];
+      [[maybe_unused]] float post_k1 = 0.f, post_k2 = 0.f, post_sg = 0.f;
+      [[maybe_unused]] int pt = 0;
+      if constexpr (EPI == EPI_POSTERIOR) {
+        static_assert(EPI != EPI_POSTERIOR || CHUNKS == 1, "the posterior epilogue handles one 32-column chunk per warp");
+        const int c0 = n0 + cq * QW;
+        const int b = row / p.S, s = row % p.S;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xt[j] = 0.f;
+        if (row_ok && s >= p.P0 && c0 < p.nfeat) {
+          pt = p.t_ptr[b];
+          if (p.x_out) {
+            const float* xr = p.x_t + ((size_t)b * p.nfeat + c0) * p.T + (s - p.P0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < p.nfeat) xt[j] = xr[(size_t)j * p.T];
+          }
+          post_k1 = p.c1[pt], post_k2 = p.c2[pt], post_sg = p.sigma[pt];
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 0) GEMM_TRACE(40 + 2 * it);
@@ -495,14 +535,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       };
       if constexpr (LN) {
         // ---------------- x = LayerNorm(x + acc + b), two passes over TMEM ----------------
-        // Warp-private 8 KB region of the drained ring: pass 1 receives the residual as TMA tiles [32 rows x 32 cols]
+        // Lanes >= RQ carry rows that belong to the next quarter / CTA: they run the arithmetic on whatever the
+        // staging buffers hold and nothing of theirs is stored (the TMA boxes are RQ rows tall).
+        // Warp-private 8 KB region of the drained ring: pass 1 receives the residual as TMA tiles [RQ rows x 32 cols]
         // of the two bf16 planes (two buffers, two chunks in flight); pass 2 stages the normalised hi / lo tiles
         // (two sets) and hands them to TMA stores, so no LSU global access is left in the epilogue.
         const uint32_t wst = smem_u32(s_stage) + warp * GEMM_LN_STG_WARP;
         uint64_t* rb = rbar + warp * 2;
         const int ccol0 = cq * QW;  // first column of this warp's quarter
         auto prefetch = [&](int ck) {  // lane 0: residual tiles of chunk ck -> buffer ck & 1 (rows past M arrive as zeros)
-          mbar_arrive_expect_tx(&rb[ck & 1], 4096);
+          mbar_arrive_expect_tx(&rb[ck & 1], (uint32_t)RQ * 128u);
           tma_load_2d_u32(wst + (ck & 1) * 4096, &tmC, smem_u32(&rb[ck & 1]), ccol0 + ck * 32, grow0);
           tma_load_2d_u32(wst + (ck & 1) * 4096 + 2048, &tmX, smem_u32(&rb[ck & 1]), ccol0 + ck * 32, grow0);
         };
@@ -715,8 +757,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int b = row / p.S, s = row % p.S;
             if (row_ok && s >= p.P0 && c0 < p.nfeat) {
               const int tau = s - p.P0;
-              const int t = p.t_ptr[b];
-              const float k1 = p.c1[t], k2 = p.c2[t], sg = p.sigma[t];
+              const int t = pt;
+              const float k1 = post_k1, k2 = post_k2, sg = post_sg;
               const unsigned long long frame = (unsigned long long)b * p.T + tau;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -732,7 +774,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     if (p.x0_out) p.x0_out[e] = x0;
                     if (p.x_out) {
                       const float n = p.noise ? p.noise[e] : eps[e4];
-                      p.x_out[e] = (k1 * x0 + k2 * p.x_t[e]) + sg * n;
+                      p.x_out[e] = (k1 * x0 + k2 * xt[j + e4]) + sg * n;
                     }
                   }
                 }
@@ -795,10 +837,29 @@ int configure_gemm() {  // once per process, outside any stream capture
   return TAMF_OK;
 }
 
-// tmA: A [M,K] with box {gemm_bk(BN,CG), 128}; tmB: W [N,K] with box {gemm_bk(BN,CG), gemm_b_box_rows(BN,CG)}.
+// Rows per TMEM lane quarter of the LayerNorm tiles for an [M, N] result.  The LN epilogue cannot overlap a mainloop
+// (the accumulator fills TMEM) and its second pass is bound by the ~32 B/clk one SM can store, so dense 128-row tiles
+// (M = 10 560: 83 CTAs) leave 64 SMs idle while the others push 256 KB each.  With RQ = ceil(M / (4 SMs)) = 18 rows per
+// quarter every SM takes part: the MMA still computes 128 rows per CTA (mainloop time unchanged, the extra rows are
+// discarded) and the stores per SM shrink by RQ / 32.  Measured (profiles/r01_exp_ln_rq_ab.txt): the epilogue drops
+// from 17.3 k to 13.2 k cycles as predicted, but the 1.78 x redundant tensor work on all 148 SMs pushes the board into
+// its power cap (986 W, SM clock 1965 -> 1837 MHz) and the chain slows from 69.0 to 66.7 sequences/s; RQ = 24 is a
+// wash (69.0, clock 1935 MHz).  So dense tiles (32) stay the default and TAMF_LN_RQ selects the others.
+inline int gemm_ln_rq(int M) {
+  static const int forced = getenv("TAMF_LN_RQ") ? atoi(getenv("TAMF_LN_RQ")) : 32;
+  int rq = forced > 0 ? forced : (M + 4 * num_sms() - 1) / (4 * num_sms());  // 0: one wave over all SMs
+  return rq < 8 ? 8 : (rq > 32 ? 32 : rq);
+}
+
+// tmA: A [M,K] with box {gemm_bk(BN,CG), 128} (EPI_RES_LN: box {.., 32}); tmB: W [N,K] with box {gemm_bk(BN,CG),
+// gemm_b_box_rows(BN,CG)}.
 template <int BN, int EPI, int CG>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((p.N + BN - 1) / BN);
+  if (EPI == EPI_RES_LN) {
+    TAMF_REQUIRE(p.ln_rq >= 1 && p.ln_rq <= 32, TAMF_E_BADARG, "gemm: LayerNorm tiles need 1 <= ln_rq <= 32");
+  }
+  const int rows_pair = (EPI == EPI_RES_LN ? 4 * p.ln_rq : GEMM_BM) * CG;
+  const int tiles = ((p.M + rows_pair - 1) / rows_pair) * ((p.N + BN - 1) / BN);
   const int slots = num_sms() / CG;
   const int grid = (tiles < slots ? tiles : slots) * CG;
   if (epi_staged(EPI) || EPI == EPI_F32) {
