@@ -174,7 +174,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, s, 3.988829340e-01f);
   return x * fmaf(xc, p, 0.5f);
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+// x sigmoid(x) with the two MUFU approximations (ex2, rcp; ~2 ulp each) instead of expf and an IEEE division: the
+// result is rounded to bf16 (8 bits) right after, and the exact form cost ~30 instructions per element.
+// x -> -inf: ex2 -> +inf, rcp -> 0, x * 0 = -0 (the limit); x -> +inf: x * 1.
+__device__ __forceinline__ float silu(float x) { return x * fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x)); }
 
 // Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of fp32 math, same rounding as the
 // scalar forms).  The epilogues are issue-bound, so every FMA chain that can run on pairs does.
@@ -655,6 +658,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (cg >= p.N) break;  // warp-uniform
           uint32_t v[32];
           tmem_ld32(taddr + ck * 32, v);
+          // positional-encoding values of this lane's 8 (row, 4-column) pieces of the chunk, fetched up front: inside
+          // the store loop every load would have to stay behind the previous iteration's stores (possible aliasing),
+          // i.e. 8 serialised L2 round trips per chunk
+          float4 pe4[2][4];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int gr = grow0 + i * 8 + prow;
+              pe4[hh][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (gr < p.M) {
+                const int tau = gr % p.T;
+                pe4[hh][i] = *reinterpret_cast<const float4*>(p.pe + (size_t)(p.P0 + tau) * p.N + cg + hh * 16 + pc * 4);
+              }
+            }
+          }
           tc_wait_ld();
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {  // 16 columns (64 B per row) per staging round
@@ -675,9 +694,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 const uint4 o = lds128(wst + stg64_off(r, pc));
                 const int b = gr / p.T, tau = gr - b * p.T;
                 const int col = cg + hh * 16 + pc * 4;
-                const float4 pe4 = *reinterpret_cast<const float4*>(p.pe + (size_t)(p.P0 + tau) * p.N + col);
-                const float y0 = __uint_as_float(o.x) + pe4.x, y1 = __uint_as_float(o.y) + pe4.y;
-                const float y2 = __uint_as_float(o.z) + pe4.z, y3 = __uint_as_float(o.w) + pe4.w;
+                const float4 q4 = pe4[hh][i];
+                const float y0 = __uint_as_float(o.x) + q4.x, y1 = __uint_as_float(o.y) + q4.y;
+                const float y2 = __uint_as_float(o.z) + q4.z, y3 = __uint_as_float(o.w) + q4.w;
                 const size_t orow = (size_t)b * p.S + p.P0 + tau;
                 uint32_t h0, h1, l0, l1;
                 split_bf16x2(y0, y1, h0, l0);
