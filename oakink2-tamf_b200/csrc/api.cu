@@ -98,19 +98,20 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64
 }
 
 int make_tmap_3d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t mid, uint64_t outer,
-                      uint64_t mid_pitch_bytes, uint64_t outer_pitch_bytes, uint32_t box_mid) {
+                      uint64_t mid_pitch_bytes, uint64_t outer_pitch_bytes, uint32_t box_mid, uint32_t box_inner) {
   EncodeTiledFn enc = get_encode();
   TAMF_REQUIRE(enc != nullptr, TAMF_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   TAMF_REQUIRE(aligned16(gptr) && (mid_pitch_bytes % 16) == 0 && (outer_pitch_bytes % 16) == 0, TAMF_E_ALIGN,
                "TMA tensor must be 16-byte aligned");
-  TAMF_REQUIRE(box_mid >= 1 && box_mid <= 256, TAMF_E_BADARG, "TMA box must be <= 256 rows");
+  TAMF_REQUIRE(box_mid >= 1 && box_mid <= 256 && (box_inner == 64 || box_inner == 32), TAMF_E_BADARG,
+               "TMA box must be 64 or 32 bf16 x <=256 rows");
   cuuint64_t dims[3] = {inner, mid, outer};
   cuuint64_t strides[2] = {mid_pitch_bytes, outer_pitch_bytes};
-  cuuint32_t box[3] = {64, box_mid, 1};
+  cuuint32_t box[3] = {box_inner, box_mid, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (3d) failed with CUresult " + std::to_string((int)r));
     return TAMF_E_CUDA;
@@ -261,9 +262,23 @@ extern "C" int tamf_gemm_trace(int which, const uint16_t* a, const uint16_t* w, 
     if ((rc = configure_gemm<512, EPI_RES_LN, 2>())) return rc;
     return launch_gemm<512, EPI_RES_LN, 2>(tmA, tmB, p, stream);
   }
+  if (which == 4) {  // embed-b shape: token epilogue, M = 64 * 160 frame rows -> token rows b*165 + 5 + tau of the pair
+                     // out (Xb, [64*165, N] bf16) / X + 4 MB (Xlo); positional encoding read from the head of X
+    TAMF_REQUIRE(M == 64 * 160, TAMF_E_BADARG, "tamf_gemm_trace: which = 4 expects M = 10240");
+    p.pe = X, p.T = 160, p.S = 165, p.P0 = 5;
+    p.Xb = (__nv_bfloat16*)out, p.Xlo = (__nv_bfloat16*)((char*)X + (4u << 20));
+    if ((rc = make_token_out_maps(&tmC, &tmX, p.Xb, p.Xlo, 64, p.T, p.S, p.P0, N))) return rc;
+    p.tmC = &tmC, p.tmX = &tmX;
+    if ((rc = configure_gemm<256, EPI_TOKEN_OUT, 2>())) return rc;
+    return launch_gemm<256, EPI_TOKEN_OUT, 2>(tmA, tmB, p, stream);
+  }
   p.out_bf16 = (__nv_bfloat16*)out, p.ld_bf16 = N;
   if ((rc = make_tmap_2d_bf16(&tmC, out, N, M, (uint64_t)N * 2, 64, 32))) return rc;
   p.tmC = &tmC;
+  if (which == 5) {  // embed-a shape: bias + SiLU -> bf16
+    if ((rc = configure_gemm<256, EPI_BIAS_SILU_BF16, 2>())) return rc;
+    return launch_gemm<256, EPI_BIAS_SILU_BF16, 2>(tmA, tmB, p, stream);
+  }
   if (which == 10) {  // single-CTA form of the in_proj shape (comparison only)
     if ((rc = make_tmap_2d_bf16(&tmB, w, K, N, (uint64_t)K * 2, 64, gemm_b_box_rows(256, 1)))) return rc;
     if ((rc = configure_gemm<256, EPI_BIAS_BF16, 1>())) return rc;

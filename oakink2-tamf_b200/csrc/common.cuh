@@ -59,7 +59,7 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* gptr, uint64_t inner /*elemen
 
 // bf16 [outer][mid][inner] tensor (strides in bytes), box {64, box_mid, 1}, 128-byte swizzle
 int make_tmap_3d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t mid, uint64_t outer,
-                      uint64_t mid_pitch_bytes, uint64_t outer_pitch_bytes, uint32_t box_mid);
+                      uint64_t mid_pitch_bytes, uint64_t outer_pitch_bytes, uint32_t box_mid, uint32_t box_inner = 64);
 bool pdl_enabled();  // TAMF_PDL=0 turns programmatic dependent launch off (debug aid)
 
 // ---------------------------------------------------------------------------------------------

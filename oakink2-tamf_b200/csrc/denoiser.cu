@@ -144,6 +144,7 @@ struct tamf_denoiser {
   float *st_text, *st_shape, *st_traj, *st_emb;  // host-API staging
   int *st_side, *t_dev, *t_cur;
   __nv_bfloat16 *A0, *H0;
+  CUtensorMap tm_tok_hi, tm_tok_lo;  // EPI_TOKEN_OUT stores (make_token_out_maps)
   CUtensorMap tm_A0, tm_H0, tm_H0_st, tm_Xb_fin;
   // cached step graph
   cudaGraphExec_t graph_exec = nullptr;
@@ -187,6 +188,7 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, int* t_ptr, float* x
     GemmParams p{};
     p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = 5, p.Xlo = h->buf.Xlo,
     p.Xb = h->buf.Xb;
+    p.tmC = &h->tm_tok_hi, p.tmX = &h->tm_tok_lo;
     if ((rc = launch_gemm<256, EPI_TOKEN_OUT, 2>(h->tm_H0, h->tm_wm2, p, s))) return rc;
     mark_event(marks, s);
   }
@@ -415,6 +417,7 @@ extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size
   if ((rc = make_tmap_2d_bf16(&h->tm_A0, h->A0, KPAD, h->Mf, (uint64_t)KPAD * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_H0, h->H0, d, h->Mf, (uint64_t)d * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_H0_st, h->H0, d, h->Mf, (uint64_t)d * 2, 64, 32))) return rc;
+  if ((rc = make_token_out_maps(&h->tm_tok_hi, &h->tm_tok_lo, h->buf.Xb, h->buf.Xlo, h->B, h->T, h->S, 5, h->d))) return rc;
   h->bound = true;
   h->cond_set = false;
   return TAMF_OK;

@@ -324,6 +324,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tma_prefetch_desc(&tmC);
       if constexpr (LN) tma_prefetch_desc(&tmX);
     }
+    if constexpr (EPI == EPI_TOKEN_OUT) {
+      if (p.tmC) tma_prefetch_desc(&tmC), tma_prefetch_desc(&tmX);
+    }
     fence_mbar_init();
   }
   if (warp == PW + 1) {
@@ -652,6 +655,68 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         // ---- y = nan_to_num(acc + b) + pe[P0+tau] -> the bf16 pair Xb / Xlo at token row b*S + P0 + tau ----
         const uint32_t wst = smem_u32(s_stage) + warp * GEMM_STG_WARP;
         const int prow = lane >> 2, pc = lane & 3;  // global side: 8 rows x 4 pieces (16 fp32 columns) per pass
+        // Fast path (T a multiple of 32, tmC / tmX given): the 32 rows of a warp are 32 consecutive frames of ONE
+        // sequence.  The positional-encoding tile [32 frames x 32 cols] fp32 is read with full-line loads (8 lanes = one
+        // 128-byte row segment) and turned to thread = row through the warp's staging tile; the hi / lo bf16 tiles of
+        // the result are staged like the LayerNorm output and leave as TMA stores through the [B][T][N] view of the
+        // frame tokens (make_token_out_maps).  Same arithmetic as the row-piece path below (bit-identical results);
+        // that path read pe with one line per lane and row (L1 tag-rate bound, 17 k cycles per tile).
+        const bool tok_tma = p.tmC != nullptr && (p.T & 31) == 0;  // grid-uniform
+        if (tok_tma) {
+          const int wb0 = grow0 / p.T, wtau0 = grow0 - wb0 * p.T;  // warp-uniform
+          const float* pe_w = p.pe + (size_t)(p.P0 + wtau0) * p.N;
+          const int gr4 = lane >> 3, gpc = lane & 7;
+#pragma unroll 1
+          for (int ck = 0; ck < CHUNKS; ++ck) {
+            const int cl = cq * QW + ck * 32, cg = n0 + cl;
+            if (cg >= p.N || grow0 >= p.M) break;  // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(taddr + ck * 32, v);
+            float4 g[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              g[k] = *reinterpret_cast<const float4*>(pe_w + (size_t)(k * 4 + gr4) * p.N + cg + gpc * 4);
+            if (elect_one()) bulk_wait_read<0>();  // the previous stores have finished reading the staging tiles
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              sts128(wst + stg128_off(k * 4 + gr4, gpc), make_uint4(__float_as_uint(g[k].x), __float_as_uint(g[k].y),
+                                                                     __float_as_uint(g[k].z), __float_as_uint(g[k].w)));
+            __syncwarp();
+            uint4 q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = lds128(wst + stg128_off(lane, j));
+            __syncwarp();  // every lane holds its pe row: the tile may be overwritten
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 ba = *reinterpret_cast<const float4*>(s_bias + cl + j * 8);
+              const float4 bb = *reinterpret_cast<const float4*>(s_bias + cl + j * 8 + 4);
+              const float y0 = nan_to_num(__uint_as_float(v[8 * j]) + ba.x) + __uint_as_float(q[2 * j].x);
+              const float y1 = nan_to_num(__uint_as_float(v[8 * j + 1]) + ba.y) + __uint_as_float(q[2 * j].y);
+              const float y2 = nan_to_num(__uint_as_float(v[8 * j + 2]) + ba.z) + __uint_as_float(q[2 * j].z);
+              const float y3 = nan_to_num(__uint_as_float(v[8 * j + 3]) + ba.w) + __uint_as_float(q[2 * j].w);
+              const float y4 = nan_to_num(__uint_as_float(v[8 * j + 4]) + bb.x) + __uint_as_float(q[2 * j + 1].x);
+              const float y5 = nan_to_num(__uint_as_float(v[8 * j + 5]) + bb.y) + __uint_as_float(q[2 * j + 1].y);
+              const float y6 = nan_to_num(__uint_as_float(v[8 * j + 6]) + bb.z) + __uint_as_float(q[2 * j + 1].z);
+              const float y7 = nan_to_num(__uint_as_float(v[8 * j + 7]) + bb.w) + __uint_as_float(q[2 * j + 1].w);
+              uint32_t hi[4], lo[4];
+              split_bf16x2(y0, y1, hi[0], lo[0]);
+              split_bf16x2(y2, y3, hi[1], lo[1]);
+              split_bf16x2(y4, y5, hi[2], lo[2]);
+              split_bf16x2(y6, y7, hi[3], lo[3]);
+              sts128(wst + stg64_off(lane, j), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+              sts128(wst + 2048 + stg64_off(lane, j), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+              tma_store_3d(&tmC, wst, cg, wtau0, wb0);
+              tma_store_3d(&tmX, wst + 2048, cg, wtau0, wb0);
+              bulk_commit();
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int ck = 0; ck < CHUNKS; ++ck) {
           const int cl = cq * QW + ck * 32, cg = n0 + cl;
@@ -707,6 +772,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
             __syncwarp();
           }
+        }
         }
       } else if constexpr (epi_tma_bf16(EPI)) {
         // ---- bias (+ activation) -> bf16: the warp's 32 x 64 slab is staged as one 128-byte-swizzled tile and
@@ -828,7 +894,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (threadIdx.x == 0) GEMM_TRACE(41 + 2 * it);
       if (++acc == ACC) acc = 0, acc_phase ^= 1u;
     }
-    if constexpr (LN || epi_tma_bf16(EPI)) {
+    if constexpr (LN || epi_tma_bf16(EPI) || EPI == EPI_TOKEN_OUT) {
       if (elect_one()) bulk_wait<0>();  // this thread's TMA stores have been performed before the CTA retires
     }
     (void)rpar;
@@ -868,6 +934,17 @@ inline int gemm_ln_rq(int M) {
   static const int forced = getenv("TAMF_LN_RQ") ? atoi(getenv("TAMF_LN_RQ")) : 32;
   int rq = forced > 0 ? forced : (M + 4 * num_sms() - 1) / (4 * num_sms());  // 0: one wave over all SMs
   return rq < 8 ? 8 : (rq > 32 ? 32 : rq);
+}
+
+// EPI_TOKEN_OUT store maps: the frame tokens of the residual planes Xb / Xlo ([B][S][N] bf16, frames at rows P0 ..
+// P0 + T - 1 of every sequence) viewed as [B][T][N] with box {32 cols, 32 frames, 1}.  The kernel takes this path when
+// T is a multiple of 32: a warp's 32 GEMM rows (b*T + tau) are then exactly one box of one sequence.
+inline int make_token_out_maps(CUtensorMap* hi, CUtensorMap* lo, const void* Xb, const void* Xlo, int B, int T, int S,
+                               int P0, int N) {
+  int rc;
+  const uint64_t row = (uint64_t)N * 2;
+  if ((rc = make_tmap_3d_bf16(hi, (const char*)Xb + (size_t)P0 * row, N, T, B, row, row * S, 32, 32))) return rc;
+  return make_tmap_3d_bf16(lo, (const char*)Xlo + (size_t)P0 * row, N, T, B, row, row * S, 32, 32);
 }
 
 // tmA: A [M,K] with box {gemm_bk(BN,CG), 128} (EPI_RES_LN: box {.., 32}); tmB: W [N,K] with box {gemm_bk(BN,CG),

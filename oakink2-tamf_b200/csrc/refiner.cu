@@ -73,6 +73,7 @@ struct tamf_refiner {
   int pe_rows = 0;
   __nv_bfloat16 *wfold /*[d,960]*/, *wm2, *wfin;
   CUtensorMap tm_wfold, tm_wm2, tm_wfin, tm_A0, tm_H0, tm_H0_st;
+  CUtensorMap tm_tok_hi, tm_tok_lo;  // EPI_TOKEN_OUT stores (make_token_out_maps)
   int B = 0, T = 0, S = 0, M = 0, Mf = 0;
   bool bound = false;
   float *prefix, *trajmean, *shapemean, *embmean;
@@ -220,6 +221,7 @@ extern "C" int tamf_refiner_bind(tamf_refiner* h, int B, int T, void* ws, size_t
   if ((rc = make_tmap_2d_bf16(&h->tm_A0, h->A0, R_K, h->Mf, (uint64_t)R_K * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_H0, h->H0, h->d, h->Mf, (uint64_t)h->d * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_H0_st, h->H0, h->d, h->Mf, (uint64_t)h->d * 2, 64, 32))) return rc;
+  if ((rc = make_token_out_maps(&h->tm_tok_hi, &h->tm_tok_lo, h->buf.Xb, h->buf.Xlo, h->B, h->T, h->S, R_PREFIX, h->d))) return rc;
   h->bound = true;
   return TAMF_OK;
 }
@@ -266,6 +268,7 @@ extern "C" int tamf_refiner_forward(tamf_refiner* h, const float* sample_pose_re
     GemmParams p{};
     p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = R_PREFIX, p.Xlo = h->buf.Xlo,
     p.Xb = h->buf.Xb;
+    p.tmC = &h->tm_tok_hi, p.tmX = &h->tm_tok_lo;
     if ((rc = launch_gemm<256, EPI_TOKEN_OUT, 2>(h->tm_H0, h->tm_wm2, p, s))) return rc;
   }
   if ((rc = enqueue_encoder(h->enc, h->buf, s, nullptr))) return rc;

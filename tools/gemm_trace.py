@@ -1,5 +1,6 @@
 """Debug aid: per-CTA timeline (clock64) of one hot-path GEMM launch.  Run under gpurun:
-   python tools/gemm_trace.py [which]      which: 0 in_proj, 1 linear1+GELU, 2 LN GEMM (linear2 shape)"""
+   python tools/gemm_trace.py [which]      which: 0 in_proj, 1 linear1+GELU, 2 LN GEMM (linear2 shape), 3 LN GEMM (out_proj shape),
+   4 embed-b (token epilogue), 5 embed-a (SiLU)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oakink2-tamf_b200"))
@@ -7,15 +8,15 @@ import torch
 from tamf_b200 import _lib
 
 which = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-M = 10560
-N, K = {0: (1536, 512), 1: (2048, 512), 2: (512, 2048), 3: (512, 512), 10: (1536, 512)}[which]
-w_id = 2 if which == 3 else which
+M = 10240 if which in (4, 5) else 10560
+N, K = {0: (1536, 512), 1: (2048, 512), 2: (512, 2048), 3: (512, 512), 4: (512, 512), 5: (512, 128), 10: (1536, 512)}[which]
+w_id = 2 if which == 3 else which  # 4: embed-b (token epilogue), 5: embed-a (SiLU)
 L = _lib.lib()
 a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
 w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
 bias = torch.randn(N, device="cuda")
-out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-X = torch.randn(M, N, device="cuda")
+out = torch.empty(10560, N, device="cuda", dtype=torch.bfloat16)
+X = torch.randn(10560, N, device="cuda")
 trace = torch.zeros(148, 64, dtype=torch.int64, device="cuda")
 for rep in range(3):
     trace.zero_()
