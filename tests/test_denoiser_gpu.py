@@ -177,11 +177,12 @@ def test_errors():
         m(torch.zeros(2, 98, 1, 16, device="cuda"), torch.zeros(2, dtype=torch.long, device="cuda"), batch)
 
 
-@pytest.mark.parametrize("B,T,nobj", [(1, 171, 1), (3, 1, 2), (2, 7, 8), (5, 123, 3)])
+@pytest.mark.parametrize("B,T,nobj", [(1, 171, 1), (3, 1, 2), (2, 7, 8), (5, 123, 3), (3, 64, 2), (5, 96, 1), (7, 32, 2)])
 def test_forward_edge_shapes_vs_oracle(B, T, nobj):
     """Edge shapes against the live fp32 oracle: the longest sequence the path accepts (T = 171: 176 tokens, the full
     attention tile), a single frame, the maximum object count (8, ragged + zero padded), a frame count that is not a
-    multiple of any tile size."""
+    multiple of any tile size, and frame counts that are multiples of 32 (TMA-store form of the token epilogue, with
+    row tiles that end inside and past the batch)."""
     from oracle import tamf_oracle as orc
     from tamf_b200 import synth
     m, cfg = _model("arch_mdm")

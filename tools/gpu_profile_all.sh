@@ -18,7 +18,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|attn_tc_kernel|prep_kernel' \
     -s 88 -c 8 -o gpurun_out/prof_denoiser -f python bench.py --steps 1 --warmup 1 --chain-steps 4 --no-cpu-baseline \
     --profile-reps 1 > gpurun_out/ncu_denoiser.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel<128' \
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:'Li128ELi5ELi2' \
     -s 2 -c 1 -o gpurun_out/prof_final -f python bench.py --steps 1 --warmup 1 --chain-steps 4 --no-cpu-baseline \
     --profile-reps 1 > gpurun_out/ncu_final.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on \
@@ -27,7 +27,7 @@ timeout 900 ncu --set full --clock-control none --import-source on \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'h2o_scan|nn_scan' -s 0 -c 1 \
     -o gpurun_out/prof_nn_scan -f python tools/bench_refine.py --reps 1 --warmup 1 > gpurun_out/ncu_nn_scan.log 2>&1
 timeout 300 python tools/parity_full_chain.py > gpurun_out/parity_full_chain.json 2> gpurun_out/parity_full_chain.err
-for w in 0 1 2 3; do timeout 120 python tools/gemm_trace.py $w; done > gpurun_out/gemm_timelines.txt 2>&1
+for w in 0 1 2 3 4 5; do timeout 120 python tools/gemm_trace.py $w; done > gpurun_out/gemm_timelines.txt 2>&1
 timeout 120 python tools/attn_trace.py 64 165 512 > gpurun_out/attn_timeline.txt 2>&1
 tail -n 4 gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/bench.json gpurun_out/bench_ref.json gpurun_out/bench_refine.json \
     gpurun_out/ncu_denoiser.log gpurun_out/ncu_final.log gpurun_out/ncu_refine.log gpurun_out/ncu_nn_scan.log gpurun_out/parity_full_chain.json
