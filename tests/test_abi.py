@@ -66,3 +66,22 @@ def test_product_path_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f"{fn} references oracle/"
+
+
+def test_library_carries_tcgen05_and_tma_sass():
+    """The shipped kernels are sm_100a code that issues tensor-core MMAs from shared-memory descriptors (UTCHMMA), reads
+    accumulators out of TMEM (LDTM) and moves tiles with TMA loads / stores (UTMALDG / UTMASTG) -- checked on the SASS
+    of the in-tree library (mnemonics as listed in the B200 profiling recipe)."""
+    import shutil
+    import subprocess
+    from tamf_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert "arch = sm_100a" in sass
+    for mnemonic, least in (("UTCHMMA", 50), ("LDTM", 20), ("UTMALDG", 20), ("UTMASTG", 10)):
+        assert sass.count(mnemonic) >= least, f"{mnemonic}: {sass.count(mnemonic)} occurrences"
