@@ -115,20 +115,34 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_reference_sample(B, n_diff, threads=None):
+def host_threads():
+    """All the host cores the reference arm may use.  torch.distributed.run exports OMP_NUM_THREADS=1 to every rank when
+    nproc > 1, which would leave the CPU arm single-threaded: the count is taken from the machine, not the environment."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+_CPU_STATE = {}
+
+
+def cpu_reference_sample(B, n_diff):
     """Oracle port of the reference's per-step algorithm (InterationSegmentMDM.forward + p_sample) on the host cores:
-    `n_diff` diffusion steps at batch B, arch_mdm_l.  Returns seconds per diffusion step."""
+    `n_diff` diffusion steps at batch B, arch_mdm_l, torch intra-op threads = every host core.  Returns seconds per
+    diffusion step."""
     import torch
 
     from oracle import tamf_oracle as orc
     from tamf_b200 import synth
-    if threads:
-        torch.set_num_threads(threads)
-    cfg = synth.ARCH[ARCH]
-    sd = synth.g_state_dict(cfg, seed=0)
-    batch = synth.make_batch(B, T_FRAMES, nobj=NOBJ, seed=0)
-    text = synth.text_features(batch["text"])
-    tab = orc.diffusion_tables(DIFF_STEPS)
+    if torch.get_num_threads() != host_threads():
+        torch.set_num_threads(host_threads())
+    if B not in _CPU_STATE:
+        cfg = synth.ARCH[ARCH]
+        batch = synth.make_batch(B, T_FRAMES, nobj=NOBJ, seed=0)
+        _CPU_STATE[B] = (cfg, synth.g_state_dict(cfg, seed=0), batch, synth.text_features(batch["text"]),
+                         orc.diffusion_tables(DIFF_STEPS))
+    cfg, sd, batch, text, tab = _CPU_STATE[B]
     x = torch.randn(B, 99, 1, T_FRAMES, generator=torch.Generator().manual_seed(0))
     t0 = time.perf_counter()
     with torch.no_grad():
@@ -139,34 +153,47 @@ def cpu_reference_sample(B, n_diff, threads=None):
     return (time.perf_counter() - t0) / n_diff
 
 
+def workload_config(B, world, chain_steps=DIFF_STEPS):
+    """The `config` object of BOTH arms (identical dicts: the driver compares them)."""
+    return {"workload": f"MF-MDM G {ARCH}, batch {B} synthetic sequences per GPU, T={T_FRAMES}, nobj={NOBJ}, "
+                        f"full {chain_steps}-step reverse chain (BASELINE.json configs[1])",
+            "global_batch": world * B, "sequences_per_gpu": B, "frames": T_FRAMES, "objects": NOBJ,
+            "diffusion_steps": chain_steps, "weights": "random init", "text_features": "synthetic (CLIP tower excluded)"}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU algorithm (oracle port; the Python reference cannot travel to the GPU box
-    and pytorch3d/CLIP weights are absent).  Rank 0 only; other ranks exit 0 without work."""
+    and pytorch3d/CLIP weights are absent) on every host core.  Rank 0 only; other ranks exit 0 without work.  Each timed
+    step is a bounded sample of the workload -- `n_diff` of the 1000 diffusion steps at the full batch, extrapolated
+    linearly -- sized from a first measured step so that the whole --steps/--warmup run stays within --ref-budget-s."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import torch
-    B, n_diff = args.batch, args.ref_diff_steps
-    for _ in range(args.warmup):
+    os.environ.pop("OMP_NUM_THREADS", None)
+    B = args.batch
+    first = cpu_reference_sample(B, 1)  # also the first warm-up step
+    per_call = max(args.ref_budget_s / max(1, args.steps + args.warmup), first)
+    n_diff = int(max(1, min(args.ref_diff_steps, per_call / first)))
+    for _ in range(max(0, args.warmup - 1)):
         cpu_reference_sample(B, 1)
     per = [cpu_reference_sample(B, n_diff) for _ in range(args.steps)]
     sec_per_diff = sum(per) / len(per)
     ms_per_step = sec_per_diff * DIFF_STEPS * 1e3
     value = B / (sec_per_diff * DIFF_STEPS)
-    cores = torch.get_num_threads()
-    sample = (f"{n_diff} of {DIFF_STEPS} diffusion steps at B={B} per timed step (x{args.steps} steps), extrapolated "
-              f"linearly to the full chain; CLIP text tower excluded (text feature given)")
+    cores = host_threads()
+    sample = (f"{n_diff} of {DIFF_STEPS} diffusion steps at B={B} per timed step (x{args.steps} steps, "
+              f"{sec_per_diff:.3f} s per diffusion step), extrapolated linearly to the full chain; CLIP text tower "
+              f"excluded (text feature given)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"MF-MDM G {ARCH}, batch {B} synthetic sequences per GPU, T={T_FRAMES}, nobj={NOBJ}, "
-                               f"full {DIFF_STEPS}-step reverse chain (BASELINE.json configs[1])",
-                   "global_batch": B, "parallelism": "host CPU cores (reference arm, rank 0 only)",
-                   "weights": "random init"},
+        "config": workload_config(B, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "notes": "reference arm = oracle port on the host cores, rank 0 only; ms_per_step is the linear extrapolation of "
+                 "the bounded sample to the full 1000-step chain",
     }
     print(json.dumps(line), flush=True)
 
@@ -339,7 +366,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--chain-steps", type=int, default=DIFF_STEPS, help="debug only: shorter chains are not the metric")
     ap.add_argument("--ref-diff-steps", type=int, default=24,
-                    help="diffusion steps per timed CPU sample (about 10 s of host work at B=64)")
+                    help="at most this many diffusion steps per timed CPU sample (about 10 s of host work at B=64)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0,
+                    help="wall-time budget of the whole reference-arm run; the per-step sample shrinks to fit")
     ap.add_argument("--profile-reps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -90,6 +90,11 @@ int tamf_mano_destroy(tamf_mano* h);
 /* betas [N,10]; verts [N,778,3]; joints [N,21,3] (root-centred; +tsl in TAMF_POSE_REPR mode). */
 int tamf_mano_fk(const tamf_mano* h, int pose_mode, const float* pose, const float* betas, int N, float* verts,
                  float* joints, void* stream);
+/* Same kernel with the remaining MANOOutput fields (manolayer.py:242-265): center_joint [N,3] = the root joint before
+ * the centre shift, transforms_abs [N,16,4,4] = global joint transforms G_k with the translation centre-shifted (no tsl).
+ * Either may be null. */
+int tamf_mano_fk_full(const tamf_mano* h, int pose_mode, const float* pose, const float* betas, int N, float* verts,
+                      float* joints, float* center_joint, float* transforms_abs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * MF-MDM G denoiser + ancestral DDPM sampler.

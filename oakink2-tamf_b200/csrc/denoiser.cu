@@ -357,7 +357,7 @@ static WsLayout ws_layout(const tamf_denoiser* h, int B, int T) {
       (size_t)B * h->cfg.obj_embed_dim * 4,      // 12 embmean
       (size_t)B * h->nfeat * T * 4,              // 13 xbuf
       (size_t)B * h->cfg.clip_dim * 4,           // 14 st_text
-      (size_t)B * T * 10 * 4,                    // 15 st_shape
+      (size_t)B * T * h->cfg.hand_shape_dim * 4, // 15 st_shape
       (size_t)B * MAX_NOBJ * T * 9 * 4,          // 16 st_traj
       (size_t)B * MAX_NOBJ * h->cfg.obj_embed_dim * 4,  // 17 st_emb
       (size_t)B * 4,                             // 18 st_side
@@ -595,7 +595,7 @@ extern "C" int tamf_p_sample_loop_host(tamf_denoiser* h, const float* text_feat,
   const size_t nx = (size_t)B * h->nfeat * T;
   TAMF_CUDA_CHECK(cudaMemcpyAsync(h->st_text, text_feat, (size_t)B * c.clip_dim * 4, cudaMemcpyHostToDevice, s));
   TAMF_CUDA_CHECK(cudaMemcpyAsync(h->st_side, hand_side, (size_t)B * 4, cudaMemcpyHostToDevice, s));
-  TAMF_CUDA_CHECK(cudaMemcpyAsync(h->st_shape, shape, (size_t)B * T * 10 * 4, cudaMemcpyHostToDevice, s));
+  TAMF_CUDA_CHECK(cudaMemcpyAsync(h->st_shape, shape, (size_t)B * T * c.hand_shape_dim * 4, cudaMemcpyHostToDevice, s));
   TAMF_CUDA_CHECK(cudaMemcpyAsync(h->st_traj, obj_traj, (size_t)B * nobj_max * T * 9 * 4, cudaMemcpyHostToDevice, s));
   TAMF_CUDA_CHECK(
       cudaMemcpyAsync(h->st_emb, obj_emb, (size_t)B * nobj_max * c.obj_embed_dim * 4, cudaMemcpyHostToDevice, s));

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(FK_THREADS)
     mano_fk_kernel(const float* __restrict__ blendT, const float* __restrict__ vt, const float* __restrict__ J0,
                    const float* __restrict__ JS, const float* __restrict__ wT, int is_right, int pose_mode,
                    const float* __restrict__ pose, const float* __restrict__ betas, const int* __restrict__ frame_ids,
-                   int N, float* __restrict__ verts, float* __restrict__ joints) {
+                   int N, float* __restrict__ verts, float* __restrict__ joints, float* __restrict__ center_out,
+                   float* __restrict__ transf_out) {
   __shared__ __align__(16) float sFeat[NFEAT][FK_FT];      // [feature][frame]: one LDS.128 x2 feeds 8 frames
   __shared__ float sR[FK_FT][16][9];         // local rotations
   __shared__ float sJ[FK_FT][16][3];         // rest joints J
@@ -179,6 +180,22 @@ __global__ void __launch_bounds__(FK_THREADS)
 #pragma unroll
       for (int r = 0; r < 3; ++r)
         joints[((size_t)f * 21 + slot_of[k]) * 3 + r] = g3[r] - sG[fl][0][r * 4 + 3] + sTsl[fl][r];
+      // MANOOutput.center_joint: the root joint before the centre shift (manolayer.py:242-245)
+      if (center_out && k == 0) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) center_out[(size_t)f * 3 + r] = g3[r];
+      }
+      // MANOOutput.transforms_abs [16,4,4]: global joint transforms G_k, translation centre-shifted (:251-258)
+      if (transf_out) {
+        float* o = transf_out + ((size_t)f * 16 + k) * 16;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) o[r * 4 + c] = sG[fl][k][r * 4 + c];
+          o[r * 4 + 3] = g3[r] - sG[fl][0][r * 4 + 3];
+        }
+        o[12] = 0.f, o[13] = 0.f, o[14] = 0.f, o[15] = 1.f;
+      }
     }
     __syncwarp();
 #pragma unroll
@@ -320,7 +337,8 @@ extern "C" int tamf_mano_destroy(tamf_mano* h) {
 }
 
 static int launch_fk(const tamf_mano* h, int pose_mode, const float* pose, const float* betas, const int32_t* frame_ids,
-                     int n, float* verts, float* joints, cudaStream_t stream, const char* who) {
+                     int n, float* verts, float* joints, cudaStream_t stream, const char* who,
+                     float* center_out = nullptr, float* transf_out = nullptr) {
   TAMF_REQUIRE(h, TAMF_E_BADARG, std::string(who) + ": null handle");
   TAMF_REQUIRE(pose_mode == TAMF_POSE_QUAT || pose_mode == TAMF_POSE_REPR, TAMF_E_BADARG, std::string(who) + ": bad pose_mode");
   TAMF_REQUIRE(n >= 0, TAMF_E_BADARG, std::string(who) + ": negative frame count");
@@ -328,7 +346,7 @@ static int launch_fk(const tamf_mano* h, int pose_mode, const float* pose, const
   TAMF_REQUIRE(pose && betas && verts && joints, TAMF_E_BADARG, std::string(who) + ": null pointer");
   mano_fk_kernel<<<(n + FK_FT - 1) / FK_FT, FK_THREADS, 0, stream>>>(h->d.blendT, h->d.vt, h->d.J0, h->d.JS, h->d.wT,
                                                                     h->d.is_right, pose_mode, pose, betas, frame_ids, n,
-                                                                    verts, joints);
+                                                                    verts, joints, center_out, transf_out);
   TAMF_LAUNCH_CHECK();
   return TAMF_OK;
 }
@@ -336,6 +354,12 @@ static int launch_fk(const tamf_mano* h, int pose_mode, const float* pose, const
 extern "C" int tamf_mano_fk(const tamf_mano* h, int pose_mode, const float* pose, const float* betas, int N,
                             float* verts, float* joints, void* stream) {
   return launch_fk(h, pose_mode, pose, betas, nullptr, N, verts, joints, (cudaStream_t)stream, "tamf_mano_fk");
+}
+
+extern "C" int tamf_mano_fk_full(const tamf_mano* h, int pose_mode, const float* pose, const float* betas, int N,
+                                 float* verts, float* joints, float* center_joint, float* transforms_abs, void* stream) {
+  return launch_fk(h, pose_mode, pose, betas, nullptr, N, verts, joints, (cudaStream_t)stream, "tamf_mano_fk_full",
+                   center_joint, transforms_abs);
 }
 
 extern "C" int tamf_mano_fk_select(const tamf_mano* h, int pose_mode, const float* pose, const float* betas,

@@ -21,6 +21,10 @@
 // 11 with a compare + two selects.  The argmin is recovered afterwards: per group of 16 candidates the thread notes
 // whether its running minimum dropped (strict <, so the earliest group wins ties); after each staged chunk the noted
 // group is re-evaluated with the same arithmetic and the first candidate equal to the minimum is the index.
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
 
 namespace tamf {
@@ -128,7 +132,7 @@ __device__ __forceinline__ void nn_publish(unsigned long long* packed, float bes
   }
 }
 
-// grid (N, splits); block = ceil(P1 / QPT) rounded up to a warp
+// grid (N, splits, query blocks of <= 4096); block = ceil(min(P1, 4096) / QPT) rounded up to a warp
 __global__ void __launch_bounds__(1024) nn_scan_kernel(const float* __restrict__ x, const float* __restrict__ y, int P1,
                                                        int P2, int per_split, unsigned long long* __restrict__ packed) {
   __shared__ float4 sxy[NN_CHUNK];
@@ -138,12 +142,13 @@ __global__ void __launch_bounds__(1024) nn_scan_kernel(const float* __restrict__
   const int c_end = min(P2, c_begin + per_split);
   const float* xn = x + (size_t)n * P1 * 3;
   const float* yn = y + (size_t)n * P2 * 3;
+  const int q0 = blockIdx.z * (blockDim.x * NN_QPT);  // query block (P1 > 4096: the object cloud as the query set)
 
   float qx[NN_QPT], qy[NN_QPT], qz[NN_QPT], best[NN_QPT];
   int bidx[NN_QPT];
 #pragma unroll
   for (int q = 0; q < NN_QPT; ++q) {
-    const int i = threadIdx.x + q * blockDim.x;
+    const int i = q0 + threadIdx.x + q * blockDim.x;
     const bool ok = i < P1;
     qx[q] = ok ? xn[3 * i + 0] : 0.f;
     qy[q] = ok ? xn[3 * i + 1] : 0.f;
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(1024) nn_scan_kernel(const float* __restrict__
   }
 #pragma unroll
   for (int q = 0; q < NN_QPT; ++q) {
-    const int i = threadIdx.x + q * blockDim.x;
+    const int i = q0 + threadIdx.x + q * blockDim.x;
     if (i < P1) nn_publish(packed + (size_t)n * P1 + i, best[q], bidx[q]);
   }
 }
@@ -570,6 +575,32 @@ __global__ void nn_finalize_kernel(unsigned long long* __restrict__ packed, floa
   reinterpret_cast<long long*>(packed)[i] = (long long)(unsigned int)(v & 0xffffffffull);
 }
 
+// Grow-only device scratch keyed by (device, stream, slot): the one-shot entry points stage small host tables / the
+// search index here.  Growth frees the old block (cudaFree waits for the device), steady state allocates nothing.
+static int nn_scratch(cudaStream_t stream, int slot, size_t bytes, void** out) {
+  struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+  };
+  static std::mutex mu;
+  static std::map<std::tuple<int, cudaStream_t, int>, Buf> bufs;
+  int dev = 0;
+  TAMF_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  Buf& b = bufs[std::make_tuple(dev, stream, slot)];
+  if (b.cap < bytes) {
+    if (b.p) {
+      TAMF_CUDA_CHECK(cudaDeviceSynchronize());
+      cudaFree(b.p);
+      b.p = nullptr, b.cap = 0;
+    }
+    TAMF_CUDA_CHECK(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+  }
+  *out = b.p;
+  return TAMF_OK;
+}
+
 static int pick_splits(int n_clouds, int P2) {
   // enough CTAs for >= 2 waves of 148 SMs, but never split below one shared-memory chunk
   int want = (2 * 148 + n_clouds - 1) / n_clouds;
@@ -591,19 +622,23 @@ extern "C" int tamf_nn_query(const float* x, const float* y, int N, int P1, int 
   if (N == 0 || P1 == 0) return TAMF_OK;  // empty query set: nothing to write
   TAMF_REQUIRE(P2 > 0, TAMF_E_BADARG, "tamf_nn_query: empty candidate cloud (P2 == 0) has no nearest neighbour");
   TAMF_REQUIRE(x && y && d2 && idx, TAMF_E_BADARG, "tamf_nn_query: null pointer");
-  TAMF_REQUIRE(P1 <= 1024 * NN_QPT, TAMF_E_BADARG, "tamf_nn_query: P1 > 4096 queries per cloud unsupported");
-  TAMF_REQUIRE(N <= 2147483647 / 1 && (long long)P2 < 2147483647LL, TAMF_E_BADARG, "tamf_nn_query: size overflow");
+  TAMF_REQUIRE((long long)P2 < 2147483647LL && (long long)P1 <= 65535LL * 1024 * NN_QPT, TAMF_E_BADARG,
+               "tamf_nn_query: size overflow");
   TAMF_REQUIRE(aligned16(idx), TAMF_E_ALIGN, "tamf_nn_query: idx must be 16-byte aligned");
   int rc = check_device();
   if (rc) return rc;
   const size_t total = (size_t)N * P1;
   TAMF_CUDA_CHECK(cudaMemsetAsync(idx, 0xFF, total * sizeof(int64_t), stream));
-  int threads = ((P1 + NN_QPT - 1) / NN_QPT + 31) / 32 * 32;
-  int splits = pick_splits(N, P2);
+  // queries are tiled in blocks of <= 4096 over gridDim.z: the reverse pass of ChamferDistance (chamfer_distance.py:148)
+  // queries with the nobj * 8192 object points
+  const int qblocks = (P1 + 1024 * NN_QPT - 1) / (1024 * NN_QPT);
+  const int q_per_block = (P1 + qblocks - 1) / qblocks;
+  int threads = ((q_per_block + NN_QPT - 1) / NN_QPT + 31) / 32 * 32;
+  int splits = pick_splits(N * qblocks, P2);
   int per_split = ((P2 + splits - 1) / splits + 3) / 4 * 4;
   splits = (P2 + per_split - 1) / per_split;
   // gridDim.x limit is 2^31-1; N beyond 65535 splits is fine on x
-  nn_scan_kernel<<<dim3(N, splits), threads, 0, stream>>>(x, y, P1, P2, per_split, (unsigned long long*)idx);
+  nn_scan_kernel<<<dim3(N, splits, qblocks), threads, 0, stream>>>(x, y, P1, P2, per_split, (unsigned long long*)idx);
   TAMF_LAUNCH_CHECK();
   nn_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((unsigned long long*)idx, d2, total, 0);
   TAMF_LAUNCH_CHECK();
@@ -657,14 +692,10 @@ static int h2o_dist_impl(const float* verts, const float* obj_traj, const float*
                  "tamf_h2o_dist: every sequence needs 1..nobj_max objects (empty cloud has no nearest neighbour)");
     if (n > max_nobj) max_nobj = n;
   }
-  // obj_first goes to the device through a small async copy into a grow-only per-thread buffer
-  static thread_local int* d_first = nullptr;
-  static thread_local int d_first_cap = 0;
-  if (d_first_cap < B + 1) {
-    if (d_first) cudaFree(d_first);
-    TAMF_CUDA_CHECK(cudaMalloc(&d_first, sizeof(int) * (size_t)(B + 1)));
-    d_first_cap = B + 1;
-  }
+  // obj_first goes to the device through a small async copy into a grow-only buffer owned by this (device, stream):
+  // calls on one stream are ordered, calls on different streams or devices never share the buffer
+  int* d_first = nullptr;
+  if ((rc = nn_scratch(stream, 0, sizeof(int) * (size_t)(B + 1), (void**)&d_first))) return rc;
   TAMF_CUDA_CHECK(cudaMemcpyAsync(d_first, obj_first_host, sizeof(int) * (size_t)(B + 1), cudaMemcpyHostToDevice, stream));
   const size_t total = (size_t)B * T * V;
   TAMF_CUDA_CHECK(cudaMemsetAsync(idx, 0xFF, total * sizeof(int64_t), stream));
@@ -728,23 +759,15 @@ extern "C" int tamf_h2o_dist(const float* verts, const float* obj_traj, const fl
   TAMF_REQUIRE(obj_points && obj_first_host && B > 0, TAMF_E_BADARG, "tamf_h2o_dist: null pointer");
   if (env_exhaustive || P > NNP_MAXP || P <= 0)
     return h2o_dist_impl(verts, obj_traj, obj_points, nullptr, obj_first_host, B, T, V, nobj_max, P, dist, idx, stream);
-  // one-shot form: the index lives in a grow-only per-thread device scratch and is rebuilt on every call
+  // one-shot form: the index lives in a grow-only device scratch of this (device, stream) and is rebuilt on every call
+  // (the allocation happens on first use / growth only; hot loops use tamf_h2o_index_build + tamf_h2o_dist_indexed)
   const int total_obj = obj_first_host[B];
   TAMF_REQUIRE(total_obj > 0, TAMF_E_BADARG, "tamf_h2o_dist: no objects");
   const size_t need = nnp_index_bytes(total_obj, P);
-  static thread_local void* d_scratch = nullptr;
-  static thread_local size_t d_scratch_cap = 0;
-  if (d_scratch_cap < need) {
-    if (d_scratch) {
-      TAMF_CUDA_CHECK(cudaDeviceSynchronize());
-      cudaFree(d_scratch);
-      d_scratch = nullptr, d_scratch_cap = 0;
-    }
-    TAMF_CUDA_CHECK(cudaMalloc(&d_scratch, need));
-    d_scratch_cap = need;
-  }
   int rc = check_device();
   if (rc) return rc;
+  void* d_scratch = nullptr;
+  if ((rc = nn_scratch((cudaStream_t)stream, 1, need, &d_scratch))) return rc;
   if ((rc = nnp_build(obj_points, total_obj, P, d_scratch, (cudaStream_t)stream))) return rc;
   return h2o_dist_impl(verts, obj_traj, nullptr, d_scratch, obj_first_host, B, T, V, nobj_max, P, dist, idx, stream);
 }

@@ -17,7 +17,7 @@ POSE_QUAT, POSE_REPR = 0, 1
 SYMBOLS = [
     "tamf_version", "tamf_last_error", "tamf_nn_query", "tamf_h2o_dist", "tamf_h2o_dist_exhaustive", "tamf_h2o_index_bytes",
     "tamf_h2o_index_build", "tamf_h2o_dist_indexed", "tamf_mano_create", "tamf_mano_destroy",
-    "tamf_mano_fk", "tamf_denoiser_create", "tamf_denoiser_destroy", "tamf_denoiser_workspace_bytes",
+    "tamf_mano_fk", "tamf_mano_fk_full", "tamf_denoiser_create", "tamf_denoiser_destroy", "tamf_denoiser_workspace_bytes",
     "tamf_denoiser_bind", "tamf_denoiser_set_cond", "tamf_denoiser_forward", "tamf_p_sample_step",
     "tamf_p_sample_chain", "tamf_p_sample_loop_host", "tamf_denoiser_profile_step", "tamf_kernel_launch_count", "tamf_philox_normal",
     "tamf_gemm_selftest", "tamf_refiner_create", "tamf_refiner_destroy", "tamf_refiner_workspace_bytes",
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.tamf_mano_create.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(vp)]
     L.tamf_mano_destroy.argtypes = [vp]
     L.tamf_mano_fk.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp]
+    L.tamf_mano_fk_full.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]
     L.tamf_denoiser_create.argtypes = [C.POINTER(TamfCfg), C.POINTER(TamfGWeights), C.POINTER(vp)]
     L.tamf_denoiser_destroy.argtypes = [vp]
     L.tamf_denoiser_workspace_bytes.argtypes = [vp, i32, i32]

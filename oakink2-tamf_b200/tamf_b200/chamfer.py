@@ -62,13 +62,13 @@ def point2point_signed(x, y, x_normals=None, y_normals=None):
     y2x = y - x.gather(1, ye)
     if x_normals is not None:
         y_nn = x_normals.gather(1, ye)
-        in_out = (y_nn * y2x).sum(-1).sign()
+        in_out = torch.bmm(y_nn.reshape(-1, 1, 3), y2x.reshape(-1, 3, 1)).reshape(N, -1).sign()
         y2x_signed = y2x.norm(dim=2) * in_out
     else:
         y2x_signed = y2x.norm(dim=2)
     if y_normals is not None:
         x_nn = y_normals.gather(1, xe)
-        in_out_x = (x_nn * x2y).sum(-1).sign()
+        in_out_x = torch.bmm(x_nn.reshape(-1, 1, 3), x2y.reshape(-1, 3, 1)).reshape(N, -1).sign()
         x2y_signed = x2y.norm(dim=2) * in_out_x
     else:
         x2y_signed = x2y.norm(dim=2)

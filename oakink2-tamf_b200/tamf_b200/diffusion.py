@@ -198,13 +198,14 @@ class GaussianDiffusion:
         if progress:
             from tqdm.auto import tqdm
             it = tqdm(it)
-        for i, t in enumerate(it):
-            n = torch.randn_like(img)
-            if const_noise:
-                n = n[[0]].repeat(shape[0], 1, 1, 1)
-            img = model.p_sample_step(img, t, batch, noise=n)["sample"]
-            if dump_steps is not None and i in dump_steps:
-                dump.append(img.clone())
+        with model.cond_scope(batch, shape[0], shape[3], img.device):  # conditioning once for the whole loop
+            for i, t in enumerate(it):
+                n = torch.randn_like(img)
+                if const_noise:
+                    n = n[[0]].repeat(shape[0], 1, 1, 1)
+                img = model.p_sample_step(img, t, batch, noise=n)["sample"]
+                if dump_steps is not None and i in dump_steps:
+                    dump.append(img.clone())
         return dump if dump_steps is not None else img
 
 
@@ -232,8 +233,9 @@ class GaussianDiffusion:
         if not progress:
             return model.p_sample_chain(img, t_first, 0, batch, seed=seed)
         from tqdm.auto import tqdm
-        for t in tqdm(range(t_first, -1, -1)):
-            img = model.p_sample_step(img, t, batch, noise=torch.randn_like(img))["sample"]
+        with model.cond_scope(batch, shape[0], shape[3], img.device):
+            for t in tqdm(range(t_first, -1, -1)):
+                img = model.p_sample_step(img, t, batch, noise=torch.randn_like(img))["sample"]
         return img
 
 

@@ -8,9 +8,14 @@ Reference call sites:
   * refine launcher loop + `save_dict.pkl` src/oakink2_tamf/launch/sample_refine.py:229-296
   * contact-ratio score helpers            script/compute_score/compute_score_cr.py:122-149
 
-The reference runs ONE sequence per reverse chain (collate([gt_sample]) -> B = 1).  Chains are independent, so the
-batched forms here (`extract_refined_samples`, `sample_dataset`, `refine_dataset`) stack up to `batch_size` dataset
-items that share a frame count into one chain -- same per-item result layout, ~60x fewer kernel launches per item.
+The reference runs ONE sequence per reverse chain (collate([gt_sample]) -> B = 1).  The batched forms here
+(`extract_refined_samples`, `sample_dataset`, `refine_dataset`) stack up to `batch_size` dataset items into one chain
+-- same per-item result layout, ~60x fewer kernel launches per item.  Items of one chain must share the frame count AND
+the object count: the collate zero-pads `obj_traj` / `obj_embedding` to the largest object count of the batch and the
+model averages over that padded axis (ObjectInputProcess / ObjectEmbedProcess, interaction_segment_mdm.py:243-246,
+258-261), so an item batched with a larger one would see its object features scaled by nobj / nobj_max -- which the
+B = 1 launchers never do.  Groups are therefore cut wherever T or obj_num changes, and each group draws its noise from
+its own Philox stream (seed + first sample id).
 """
 from __future__ import annotations
 
@@ -93,6 +98,9 @@ def extract_refined_samples(generation_model, diffusion, refine_model, gt_sample
                             dtype=torch.float32, seed=None) -> np.ndarray:
     """Batched `extract_refined_sample`: all items (same frame count) run as ONE G chain and ONE R pass.
     Returns refine_pose_repr [len(gt_samples), T, 99] as numpy."""
+    if len({_item_obj_num(it) for it in gt_samples}) > 1:
+        raise ValueError("extract_refined_samples: items of one batched chain must have the same object count (the "
+                         "padded object axis is averaged over; use sample_dataset / one call per object count)")
     batch = interaction_segment_collate(list(gt_samples))
     batch_device = map_copy_select_to(batch, device=device, dtype=dtype, select=SELECT_G)
     batch_device["sample_pose_repr"] = _g_chain(generation_model, diffusion, batch_device, seed)
@@ -156,19 +164,29 @@ def contact_min_cdist(hv, pc, device, dtype=torch.float32) -> List[float]:
 
 
 # ---- launcher loops ----
+def _item_obj_num(item: dict) -> int:
+    return int(np.asarray(item["obj_traj"]).shape[0])
+
+
 def _same_len_batches(dataset, ids: range, batch_size: int):
-    """Consecutive ids, cut where the frame count changes or `batch_size` is reached."""
-    cur, cur_T = [], None
+    """Consecutive ids, cut where the frame count or the object count changes or `batch_size` is reached (so that a
+    batched chain is exactly the stack of the reference's B = 1 chains: no zero-padded object rows inside a group)."""
+    cur, cur_key = [], None
     for i in ids:
         item = dataset[i]
-        T = int(np.asarray(item["pose_repr"]).shape[0])
-        if cur and (T != cur_T or len(cur) == batch_size):
+        key = (int(np.asarray(item["pose_repr"]).shape[0]), _item_obj_num(item))
+        if cur and (key != cur_key or len(cur) == batch_size):
             yield cur
             cur = []
         cur.append((i, item))
-        cur_T = T
+        cur_key = key
     if cur:
         yield cur
+
+
+def _group_seed(seed, group):
+    """A distinct Philox stream per group: with one seed for all, every group would replay the same per-step noise."""
+    return None if seed is None else int(seed) + int(group[0][0])
 
 
 def sample_dataset(model, diffusion, dataset, out_dir: Optional[str], worker_id: int = 0, num_worker: int = 1,
@@ -181,7 +199,7 @@ def sample_dataset(model, diffusion, dataset, out_dir: Optional[str], worker_id:
     for group in _same_len_batches(dataset, shard_range(len(dataset), worker_id, num_worker), batch_size):
         batch = interaction_segment_collate([it for _, it in group])
         batch_device = map_copy_select_to(batch, device=device, dtype=dtype, select=SELECT_G)
-        arr = _g_chain(model, diffusion, batch_device, seed).detach().cpu().numpy()
+        arr = _g_chain(model, diffusion, batch_device, _group_seed(seed, group)).detach().cpu().numpy()
         for (sid, _), a in zip(group, arr):
             out[sid] = a
             if commit and out_dir is not None:

@@ -37,6 +37,18 @@ def _load_assets(mano_assets_root: str, side: str) -> dict:
                 weights=g("weights"), faces=np.asarray(dd["f"]))
 
 
+def quaternion_to_axis_angle(quaternions: torch.Tensor) -> torch.Tensor:
+    """(w,x,y,z) quaternions [...,4] -> axis-angle [...,3] (manotorch/utils/geometry.py:276-300; host-side glue of
+    `MANOOutput.full_poses`, elementwise torch ops)."""
+    norms = torch.norm(quaternions[..., 1:], p=2, dim=-1, keepdim=True)
+    half = torch.atan2(norms, quaternions[..., :1])
+    ang = 2 * half
+    small = ang.abs() < 1e-6
+    safe = torch.where(small, torch.ones_like(ang), ang)
+    ratio = torch.where(small, 0.5 - (ang * ang) / 48, torch.sin(half) / safe)
+    return quaternions[..., 1:] / ratio
+
+
 class ManoLayer(torch.nn.Module):
     def __init__(self, rot_mode: str = "quat", side: str = "right", center_idx: Optional[int] = 0,
                  mano_assets_root: str = "assets/mano", use_pca: bool = False, flat_hand_mean: bool = True,
@@ -80,7 +92,7 @@ class ManoLayer(torch.nn.Module):
         except Exception:
             pass
 
-    def _fk(self, mode: int, pose: torch.Tensor, betas: torch.Tensor):
+    def _fk(self, mode: int, pose: torch.Tensor, betas: torch.Tensor, full: bool = False):
         if not pose.is_cuda:
             raise RuntimeError("tamf_b200.ManoLayer needs CUDA tensors (no CPU fallback)")
         dev = pose.device
@@ -92,22 +104,30 @@ class ManoLayer(torch.nn.Module):
         verts = torch.empty((N, 778, 3), dtype=torch.float32, device=dev)
         joints = torch.empty((N, 21, 3), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            if full:
+                center = torch.empty((N, 1, 3), dtype=torch.float32, device=dev)
+                transf = torch.empty((N, 16, 4, 4), dtype=torch.float32, device=dev)
+                _lib.check(_lib.lib().tamf_mano_fk_full(self._handle(dev), mode, _lib.ptr(pose), _lib.ptr(betas), N,
+                                                        _lib.ptr(verts), _lib.ptr(joints), _lib.ptr(center),
+                                                        _lib.ptr(transf), _lib.stream_ptr(dev)), "tamf_mano_fk_full")
+                return verts, joints, center, transf
             _lib.check(_lib.lib().tamf_mano_fk(self._handle(dev), mode, _lib.ptr(pose), _lib.ptr(betas), N,
                                                _lib.ptr(verts), _lib.ptr(joints), _lib.stream_ptr(dev)), "tamf_mano_fk")
         return verts, joints
 
     def forward(self, pose_coeffs: torch.Tensor, betas: Optional[torch.Tensor] = None, **kwargs):
-        """pose_coeffs [N,16,4] (or [N,64]) quaternions (w,x,y,z); betas [N,10] -> MANOOutput (manolayer.py:268-285).
-        `full_poses` (axis-angle) and `transforms_abs` are not produced on this path (unused by TaMF): None."""
+        """pose_coeffs [N,16,4] (or [N,64]) quaternions (w,x,y,z); betas [N,10] -> MANOOutput (manolayer.py:268-285):
+        verts / joints root-centred, `center_joint` [N,1,3] the root joint before centring, `transforms_abs`
+        [N,16,4,4] the centre-shifted global joint transforms (:251-258), `full_poses` [N,48] axis-angle (:119-126)."""
         N = pose_coeffs.shape[0]
         if pose_coeffs.numel() != N * 64:
             raise ValueError(f"pose_coeffs must be [N,16,4], got {tuple(pose_coeffs.shape)}")
         if betas is None:
             betas = self.th_betas.to(pose_coeffs.device).expand(N, 10)
-        verts, joints = self._fk(_lib.POSE_QUAT, pose_coeffs.reshape(N, 64), betas)
-        center = torch.zeros((N, 1, 3), dtype=torch.float32, device=verts.device)
-        return MANOOutput(verts=verts, joints=joints, center_idx=self.center_idx, center_joint=center, full_poses=None,
-                          betas=betas, transforms_abs=None)
+        verts, joints, center, transf = self._fk(_lib.POSE_QUAT, pose_coeffs.reshape(N, 64), betas, full=True)
+        full_poses = quaternion_to_axis_angle(pose_coeffs.reshape(N, 16, 4).to(torch.float32)).reshape(N, -1)
+        return MANOOutput(verts=verts, joints=joints, center_idx=self.center_idx, center_joint=center,
+                          full_poses=full_poses, betas=betas, transforms_abs=transf)
 
     def forward_pose_repr(self, pose_repr: torch.Tensor, betas: torch.Tensor):
         """pose_repr [N,99] (tsl + 16 x rot6d) -> world verts [N,778,3], joints [N,21,3]: the per-item body of

@@ -6,6 +6,7 @@ The torch sub-modules below are weight CONTAINERS with the reference's parameter
 util/state_util.py:22-39 load with strict=False exactly as launch/sample.py:190-196 does); they are never executed."""
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Callable, Optional
 
@@ -103,7 +104,7 @@ class InterationSegmentMDM(nn.Module):
         self._handle_dev = None
         self._ws = None
         self._bound = None
-        self._cond_key = None
+        self._cond_scope = None
         self._rule_key = None
         self._keep = []
 
@@ -145,7 +146,7 @@ class InterationSegmentMDM(nn.Module):
     def _drop_handle(self):
         if self._handle is not None:
             _lib.lib().tamf_denoiser_destroy(self._handle)
-        self._handle, self._bound, self._cond_key, self._ws, self._rule_key = None, None, None, None, None
+        self._handle, self._bound, self._cond_scope, self._ws, self._rule_key = None, None, None, None, None
 
     def __del__(self):
         try:
@@ -196,7 +197,7 @@ class InterationSegmentMDM(nn.Module):
         base = (self._ws.data_ptr() + 255) & ~255
         with torch.cuda.device(device):
             _lib.check(L.tamf_denoiser_bind(self._handle, B, T, C.c_void_p(base), nbytes), "tamf_denoiser_bind")
-        self._bound, self._cond_key = (B, T), None
+        self._bound, self._cond_scope = (B, T), None
 
     @staticmethod
     def hand_side_ids(hand_side):
@@ -211,14 +212,15 @@ class InterationSegmentMDM(nn.Module):
         return ids
 
     def set_cond(self, batch: dict, B: int, T: int, device):
-        """Conditioning is constant over the reverse chain: computed once per batch and cached (the reference
-        recomputes it, CLIP included, at every step -- interaction_segment_mdm.py:141-166)."""
+        """Conditioning is constant over a reverse chain: the fused sampler entries compute it once per chain (the
+        reference recomputes it, CLIP included, at every step -- interaction_segment_mdm.py:141-166).  There is no
+        implicit cache: tensor contents cannot be told apart by identity (a freed dict id / allocator address is reused
+        by the next item of a per-item loop), so every call recomputes unless the caller has pinned this very batch
+        object with `cond_scope(batch)`."""
         self._ensure_bound(B, T, device)
-        ts = [batch["shape"], batch["obj_traj"], batch["obj_embedding"]]
-        key = (id(batch), tuple(batch["text"]), tuple(batch["hand_side"]),
-               tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts))
-        if key == self._cond_key:
+        if self._cond_scope is not None and self._cond_scope[0] is batch and self._cond_scope[1] == (B, T, device):
             return
+        ts = [batch["shape"], batch["obj_traj"], batch["obj_embedding"]]
         shape, traj, emb = (_lib.dev_f32(t, device) for t in ts)
         if shape.shape != (B, T, self.hand_shape_feats):
             raise ValueError(f"batch['shape'] must be [B,T,{self.hand_shape_feats}], got {tuple(shape.shape)}")
@@ -231,7 +233,19 @@ class InterationSegmentMDM(nn.Module):
             _lib.check(_lib.lib().tamf_denoiser_set_cond(self._handle, _lib.ptr(text), _lib.ptr(side), _lib.ptr(shape),
                                                          _lib.ptr(traj), _lib.ptr(emb), nobj, _lib.stream_ptr(device)),
                        "tamf_denoiser_set_cond")
-        self._cond_key = key
+
+    @contextlib.contextmanager
+    def cond_scope(self, batch: dict, B: int, T: int, device):
+        """Pins `batch` as the conditioning of every step issued inside the `with` block: computed once on entry, and
+        `set_cond` of this same object (held alive here, so its identity cannot be recycled) is a no-op until exit.  The
+        step-by-step sampler loops use it; the caller must not mutate the batch tensors inside the block."""
+        self._cond_scope = None
+        self.set_cond(batch, B, T, device)
+        self._cond_scope = (batch, (B, T, device))
+        try:
+            yield self
+        finally:
+            self._cond_scope = None
 
     def forward(self, x, timesteps, batch):
         """x [B,99,1,T] fp32, timesteps [B] int -> predicted x0 [B,99,1,T] (interaction_segment_mdm.py:134-174)."""
@@ -311,5 +325,5 @@ class InterationSegmentMDM(nn.Module):
                 self._handle, _lib.ptr(text), _lib.ptr(side), _lib.ptr(shape), _lib.ptr(traj), _lib.ptr(emb),
                 traj.shape[1], _lib.ptr(xT), int(seed), _lib.ptr(out), _lib.stream_ptr(dev)),
                 "tamf_p_sample_loop_host")
-        self._cond_key = None
+        self._cond_scope = None  # the host entry installed its own conditioning
         return out

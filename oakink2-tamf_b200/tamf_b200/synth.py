@@ -224,3 +224,17 @@ def step_noise(seed: int, t: int, shape) -> torch.Tensor:
     """Counter-based per-step noise eps_t = randn(seed (+) t) shared by oracle and device path."""
     g = torch.Generator().manual_seed((seed * 1000003 + t) % (2 ** 63))
     return torch.randn(*shape, generator=g)
+
+
+def p2p_clouds(seed: int = 13, T: int = 2, nobj: int = 2, P: int = 8192):
+    """Inputs of `point2point_signed` at the reference's call shape (segment_refine_model.py:165,
+    interaction_segment_extra_loss.py:157): x = hand-sized cloud [T,778,3] with unit normals, y = nobj * P object points
+    [T, nobj*P, 3] with unit normals (numpy fp32)."""
+    rng = np.random.default_rng(seed)
+    x = (0.08 * rng.standard_normal((T, 778, 3))).astype(np.float32)
+    xn = rng.standard_normal((T, 778, 3)).astype(np.float32)
+    xn /= np.linalg.norm(xn, axis=-1, keepdims=True)
+    y = (0.1 * rng.standard_normal((T, nobj * P, 3))).astype(np.float32)
+    yn = rng.standard_normal((T, nobj * P, 3)).astype(np.float32)
+    yn /= np.linalg.norm(yn, axis=-1, keepdims=True)
+    return x, xn, y, yn

@@ -94,11 +94,79 @@ def golden_spaced(ref):
     print("wrote spaced_arch_mdm")
 
 
+def golden_g_b64(ref):
+    """The BENCHMARKED configuration (BASELINE.json configs[1]: arch_mdm_l, B=64, T=160, nobj=2) through the reference
+    module itself: forward at t = 999 / 0 and one p_sample with injected noise at t = 500.  Only sequences KEEP_B of the
+    batch are stored (the model is batch-independent; the CUDA tile layout is not), 0.25 MB per tensor."""
+    cfg = synth.ARCH["arch_mdm_l"]
+    model = ref.mdm.InterationSegmentMDM(**cfg)
+    model.eval()
+    model.load_state_dict(synth.g_state_dict(cfg, seed=0), strict=False)
+    B, T = 64, 160
+    keep = np.array([0, 21, 42, 63])
+    batch = synth.make_batch(B, T, nobj=2, seed=11)
+    x = torch.randn(B, 99, 1, T, generator=torch.Generator().manual_seed(5))
+    out = {"arch": "arch_mdm_l", "B": B, "T": T, "nobj": 2, "batch_seed": 11, "x_seed": 5, "weight_seed": 0,
+           "keep_b": keep, "noise_seed": 77}
+    diffusion = ref.diffusion_util.create_gaussian_diffusion(1000, "cosine")
+    gd = ref.gd
+    orig = gd.th.randn_like
+    with torch.no_grad():
+        for t in (999, 0):
+            out[f"x0_t{t}"] = model(x, torch.full((B,), t, dtype=torch.long), batch).numpy()[keep]
+        gd.th.randn_like = lambda z: synth.step_noise(77, 500, tuple(z.shape))
+        o = diffusion.p_sample(model, x, torch.full((B,), 500, dtype=torch.long), clip_denoised=False,
+                               model_kwargs={"batch": batch})
+        out["sample_t500"] = o["sample"].numpy()[keep]
+    gd.th.randn_like = orig
+    np.savez_compressed(os.path.join(OUT, "g_arch_mdm_l_b64.npz"), **out)
+    print("wrote g_arch_mdm_l_b64")
+
+
+def golden_mano_full(ref):
+    """Every MANOOutput field of the reference ManoLayer (manolayer.py:268-285) on the mano_fk.npz inputs."""
+    g = np.load(os.path.join(OUT, "mano_fk.npz"))
+    q, betas = torch.from_numpy(g["quat"]), torch.from_numpy(g["betas"])
+    fk = {}
+    for side in ("right", "left"):
+        layer = ref.manolayer.ManoLayer(mano_assets_root=ref.mano_root, rot_mode="quat", side=side, center_idx=0,
+                                        use_pca=False, flat_hand_mean=True)
+        o = layer(pose_coeffs=q, betas=betas)
+        fk[f"center_joint_{side}"] = o.center_joint.numpy()
+        fk[f"transforms_abs_{side}"] = o.transforms_abs.numpy()
+        fk[f"full_poses_{side}"] = o.full_poses.numpy()
+    np.savez_compressed(os.path.join(OUT, "mano_fk_full.npz"), **fk)
+    print("wrote mano_fk_full")
+
+
+def golden_p2p(ref):
+    """`point2point_signed` (model/loss/chamfer_distance.py:4-64) and `ChamferDistance.forward`
+    (chamfer_distance.py:147-162) of the reference at the reference's own call shape, both directions, with normals.
+    The nearest-neighbour arithmetic itself comes from the pytorch3d stub (PARITY UNPINNED, oracle/ref_shims.py);
+    everything around it -- gathers, signs, norms, the 4-tuple -- is the reference's code."""
+    x, xn, y, yn = synth.p2p_clouds(seed=13, T=2, nobj=2, P=8192)
+    xt, xnt, yt, ynt = (torch.from_numpy(a) for a in (x, xn, y, yn))
+    y2x, x2y, yidx = ref.p2p.point2point_signed(xt, yt, x_normals=xnt, y_normals=ynt)
+    y2x_u, x2y_u, _ = ref.p2p.point2point_signed(xt, yt)
+    cx, cy, ix, iy = ref.chd.ChamferDistance()(xt, yt)
+    np.savez_compressed(os.path.join(OUT, "p2p_signed.npz"), seed=13, T=2, nobj=2, P=8192,
+                        y2x_signed=y2x.numpy(), x2y_signed=x2y.numpy(), yidx_near=yidx.numpy().astype(np.int32),
+                        y2x_unsigned=y2x_u.numpy(), x2y_unsigned=x2y_u.numpy(), cham_x=cx.numpy(), cham_y=cy.numpy(),
+                        idx_x=ix.numpy().astype(np.int32), idx_y=iy.numpy().astype(np.int32))
+    print("wrote p2p_signed")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shims.install()
     if len(sys.argv) > 1 and sys.argv[1] == "spaced":
         return golden_spaced(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == "b64":
+        return golden_g_b64(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == "mano_full":
+        return golden_mano_full(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == "p2p":
+        return golden_p2p(ref)
 
     # ---- G forward: arch_mdm ragged objects (pins the padded-mean quirk), 4 timesteps ----
     model, sd, batch, g = golden_g(ref, "arch_mdm", B=3, T=48, nobj=3, ragged=True, steps=[999, 500, 1, 0], tag="arch_mdm")
@@ -169,6 +237,9 @@ def main():
                         **{k: ro[k].numpy() for k in keep})
     print("wrote r_arch_refine")
     golden_spaced(ref)
+    golden_mano_full(ref)
+    golden_g_b64(ref)
+    golden_p2p(ref)
 
 
 if __name__ == "__main__":

@@ -367,6 +367,26 @@ def point2point_h2o(x: torch.Tensor, y: torch.Tensor):
     return (x - near).norm(dim=2), idx_t
 
 
+def point2point_signed(x: torch.Tensor, y: torch.Tensor, x_normals=None, y_normals=None):
+    """`point2point_signed` in full (model/loss/chamfer_distance.py:4-64) over `ChamferDistance.forward`
+    (chamfer_distance.py:147-162: knn_points both ways) -> (y2x_signed [N,P2], x2y_signed [N,P1], yidx_near [N,P2])."""
+    N, P1, D = x.shape
+    P2 = y.shape[1]
+    _, ix = nn_query(x.numpy(), y.numpy())
+    _, iy = nn_query(y.numpy(), x.numpy())
+    ix, iy = torch.from_numpy(ix), torch.from_numpy(iy)
+    xe, ye = ix.view(N, P1, 1).expand(N, P1, D), iy.view(N, P2, 1).expand(N, P2, D)
+    x2y, y2x = x - y.gather(1, xe), y - x.gather(1, ye)
+    y2x_signed, x2y_signed = y2x.norm(dim=2), x2y.norm(dim=2)
+    if x_normals is not None:
+        y_nn = x_normals.gather(1, ye)
+        y2x_signed = y2x_signed * torch.bmm(y_nn.reshape(-1, 1, 3), y2x.reshape(-1, 3, 1)).reshape(N, -1).sign()
+    if y_normals is not None:
+        x_nn = y_normals.gather(1, xe)
+        x2y_signed = x2y_signed * torch.bmm(x_nn.reshape(-1, 1, 3), x2y.reshape(-1, 3, 1)).reshape(N, -1).sign()
+    return y2x_signed, x2y_signed, iy
+
+
 def obj_world_points(obj_traj: torch.Tensor, pts: torch.Tensor) -> torch.Tensor:
     """`tslrot6d_to_transf` + `transf_point_array` (src/dev_fn/transform/transform.py:148-154, 36-53):
     obj_traj [T,9], pts [P,3] -> [T,P,3] = (R_t @ p^T)^T + t_t."""

@@ -148,6 +148,79 @@ def test_philox_normal_statistics():
     assert abs(torch.corrcoef(torch.stack([out, out2]))[0, 1].item()) < 3e-3
 
 
+def test_b64_forward_and_p_sample_vs_reference_golden(golden):
+    """The BENCHMARKED configuration (BASELINE.json configs[1]: arch_mdm_l, B=64, T=160, nobj=2; M = 10 560 token rows
+    = 42 pair tiles, several tiles per persistent CTA pair) against outputs of the reference's own module
+    (tests/golden/g_arch_mdm_l_b64.npz, sequences keep_b of the batch): forward at t = 999 / 0, p_sample at t = 500."""
+    import tamf_b200
+    from tamf_b200 import synth
+    g = golden("g_arch_mdm_l_b64.npz")
+    B, T, keep = int(g["B"]), int(g["T"]), g["keep_b"]
+    m, cfg = _model(str(g["arch"]))
+    batch = _dev_batch(synth.make_batch(B, T, nobj=int(g["nobj"]), seed=int(g["batch_seed"])))
+    x = torch.randn(B, 99, 1, T, generator=torch.Generator().manual_seed(int(g["x_seed"]))).cuda()
+    for t in (999, 0):
+        o = m(x, torch.full((B,), t, dtype=torch.long, device="cuda"), batch).cpu().numpy()[keep]
+        ref = g[f"x0_t{t}"]
+        r, a = rel_l2(o, ref), float(np.abs(o - ref).max())
+        print(f"B=64 forward t={t} rel_l2={r:.3e} max_abs={a:.3e}")
+        assert r <= REL_TOL and a <= ABS_TOL
+    diffusion = tamf_b200.create_gaussian_diffusion(1000, "cosine")
+    out = diffusion.p_sample(m, x, torch.full((B,), 500, dtype=torch.long, device="cuda"), clip_denoised=False,
+                             model_kwargs={"batch": batch},
+                             noise=synth.step_noise(int(g["noise_seed"]), 500, (B, 99, 1, T)))
+    o, ref = out["sample"].cpu().numpy()[keep], g["sample_t500"]
+    r, a = rel_l2(o, ref), float(np.abs(o - ref).max())
+    print(f"B=64 p_sample t=500 rel_l2={r:.3e} max_abs={a:.3e}")
+    assert r <= REL_TOL and a <= ABS_TOL
+
+
+def test_b64_forward_and_chain_vs_live_oracle():
+    """Same configuration against the LIVE oracle over the whole batch: (a) one forward, all 64 sequences; (b) a 20-step
+    CUDA-graph chain (in-kernel Philox) == the same 20 steps issued one by one, bit for bit; (c) the oracle run free over
+    those 20 steps with the noise the kernels drew (recovered from x_{t-1} = c1 x0 + c2 x_t + sigma eps) lands on the
+    graph chain's result: rel-L2 <= 1e-2, max-abs <= 3e-2."""
+    import tamf_b200
+    from oracle import tamf_oracle as orc
+    from tamf_b200 import synth
+    m, cfg = _model("arch_mdm_l")
+    B, T = 64, 160
+    batch = synth.make_batch(B, T, nobj=2, seed=4)
+    dbatch = _dev_batch(batch)
+    sd, text, tab = synth.g_state_dict(cfg, 0), synth.text_features(batch["text"]), orc.diffusion_tables(1000)
+    x = torch.randn(B, 99, 1, T, generator=torch.Generator().manual_seed(9))
+    ts = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = orc.g_forward(sd, cfg, x, ts, batch, text)
+    out = m(x.cuda(), ts.cuda(), dbatch).cpu()
+    r, a = rel_l2(out.numpy(), ref.numpy()), float((out - ref).abs().max())
+    print(f"B=64 forward vs oracle rel_l2={r:.3e} max_abs={a:.3e}")
+    assert r <= REL_TOL and a <= ABS_TOL
+    # (b) graph chain == stepwise
+    t0, t1, seed = 519, 500, 2024
+    tamf_b200.create_gaussian_diffusion(1000, "cosine")._install(m, "ancestral")
+    chain = m.p_sample_chain(x.cuda().clone(), t0, t1, dbatch, seed=seed)
+    cur, eps = x.cuda().clone(), {}
+    for t in range(t0, t1 - 1, -1):
+        o = m.p_sample_step(cur, t, dbatch, noise=None, seed=seed)
+        c1, c2 = float(np.float32(tab["posterior_mean_coef1"][t])), float(np.float32(tab["posterior_mean_coef2"][t]))
+        sg = float(np.exp(np.float32(0.5) * np.float32(tab["posterior_log_variance_clipped"][t])))
+        eps[t] = ((o["sample"].double() - c1 * o["pred_xstart"].double() - c2 * cur.double()) / sg).float().cpu()
+        cur = o["sample"]
+    assert torch.equal(chain, cur)
+    e = torch.stack(list(eps.values()))
+    assert abs(float(e.mean())) < 5e-3 and abs(float(e.std()) - 1.0) < 5e-3  # the recovered noise is standard normal
+    # (c) oracle, free running on the same noise
+    r_x = x.clone()
+    with torch.no_grad():
+        for t in range(t0, t1 - 1, -1):
+            x0 = orc.g_forward(sd, cfg, r_x, torch.full((B,), t, dtype=torch.long), batch, text)
+            r_x = orc.p_sample_update(tab, r_x, x0, t, eps[t])
+    r, a = rel_l2(chain.cpu().numpy(), r_x.numpy()), float((chain.cpu() - r_x).abs().max())
+    print(f"B=64 20-step graph chain vs oracle rel_l2={r:.3e} max_abs={a:.3e}")
+    assert r <= REL_TOL and a <= ABS_TOL
+
+
 def test_full_size_forward_properties():
     """BASELINE size (arch_mdm_l, B=64, T=160): batch-row independence (each chain depends only on its own row) and
     agreement of row 0 with a B=1 evaluation -- size-independent properties, no oracle needed."""

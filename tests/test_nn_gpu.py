@@ -13,7 +13,7 @@ def _run(x, y):
 
 
 @pytest.mark.parametrize("N,P1,P2", [(1, 1, 1), (2, 778, 8192), (3, 7, 1000), (5, 778, 16384), (1, 4096, 37),
-                                     (64, 100, 1025)])
+                                     (64, 100, 1025), (2, 4097, 300), (3, 16384, 778), (1, 10001, 1500)])
 def test_nn_bit_exact(N, P1, P2):
     from oracle import tamf_oracle as orc
     rng = np.random.default_rng(N * 1000 + P1 + P2)
@@ -82,6 +82,42 @@ def test_chamfer_distance_api_and_point2point():
     # size-independent property: the reported distance is attained by the reported index, and no candidate is closer
     d_all = torch.cdist(xt[:1], yt[:1])[0]
     assert torch.all(d_all.min(dim=1).values + 1e-6 >= x2y[0])
+
+
+def test_chamfer_reference_call_shape_both_directions(golden):
+    """`ChamferDistance()(x[T,778,3], y[T,2*8192,3])` and `point2point_signed(..., x_normals, y_normals)` at the
+    reference's own call shape (segment_refine_model.py:165, interaction_segment_extra_loss.py:157): the reverse pass
+    queries with the 16 384 object points.  Checked against (a) outputs of the REFERENCE's code
+    (tests/golden/p2p_signed.npz: chamfer_distance.py:147-162 + model/loss/chamfer_distance.py:4-64 over the knn stub)
+    and (b) the live oracle -- indices and squared distances bit-exact."""
+    import tamf_b200
+    from oracle import tamf_oracle as orc
+    from tamf_b200 import synth
+    g = golden("p2p_signed.npz")
+    x, xn, y, yn = synth.p2p_clouds(seed=int(g["seed"]), T=int(g["T"]), nobj=int(g["nobj"]), P=int(g["P"]))
+    xt, xnt, yt, ynt = (torch.from_numpy(a).cuda() for a in (x, xn, y, yn))
+    cx, cy, ix, iy = tamf_b200.ChamferDistance()(xt, yt)
+    assert ix.dtype == torch.int64 and iy.shape == (x.shape[0], y.shape[1])
+    assert np.array_equal(ix.cpu().numpy(), g["idx_x"]) and np.array_equal(iy.cpu().numpy(), g["idx_y"])
+    assert np.array_equal(cx.cpu().numpy(), g["cham_x"]) and np.array_equal(cy.cpu().numpy(), g["cham_y"])
+    rdy, riy = orc.nn_query(y, x)
+    assert np.array_equal(iy.cpu().numpy(), riy) and np.array_equal(cy.cpu().numpy(), rdy)
+    y2x, x2y, yidx = tamf_b200.point2point_signed(xt, yt, x_normals=xnt, y_normals=ynt)
+    assert np.array_equal(yidx.cpu().numpy(), g["yidx_near"])
+    # |d| to 1e-7; the sign is that of a 3-term dot product: compare it wherever the product is not within rounding of 0
+    for ours, ref in ((y2x, g["y2x_signed"]), (x2y, g["x2y_signed"])):
+        o = ours.cpu().numpy()
+        np.testing.assert_allclose(np.abs(o), np.abs(ref), rtol=0, atol=1e-7)
+        clear = np.abs(ref) > 1e-6
+        assert np.array_equal(np.sign(o[clear]), np.sign(ref[clear]))
+    assert (g["y2x_signed"] < 0).any() and (g["y2x_signed"] > 0).any()  # the signed branch is exercised
+    y2x_u, x2y_u, _ = tamf_b200.point2point_signed(xt, yt)
+    np.testing.assert_allclose(y2x_u.cpu().numpy(), g["y2x_unsigned"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(x2y_u.cpu().numpy(), g["x2y_unsigned"], rtol=0, atol=1e-7)
+    # the oracle's full restatement agrees with the reference's code as well
+    r_y2x, r_x2y, r_idx = orc.point2point_signed(*(torch.from_numpy(a) for a in (x, y, xn, yn)))
+    assert np.array_equal(r_idx.numpy(), g["yidx_near"])
+    np.testing.assert_allclose(r_y2x.numpy(), g["y2x_signed"], rtol=0, atol=1e-7)
 
 
 def test_h2o_fused_matches_materialised():

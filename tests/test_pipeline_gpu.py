@@ -114,3 +114,35 @@ def test_sample_and_refine_dataset_write_the_reference_layout(tmp_path):
         assert s["joints"].shape == (T, 21, 3) and s["verts"].shape == (T, 778, 3) and s["faces"].shape == (1552, 3)
         assert s["refine_pose_repr"].shape == (T, 99) and s["hand_side"] == data[i]["hand_side"]
         assert np.array_equal(s["refine_pose_repr"], d["refine_pose_repr"])
+
+
+def test_batched_launcher_equals_per_item_with_ragged_object_counts(tmp_path):
+    """refine_dataset / the G forward over a dataset whose items have DIFFERENT object counts: the batched launcher
+    result equals the reference's B = 1 loop item by item (groups are cut where obj_num changes; a padded object axis
+    would scale the object token of the smaller item by nobj / nobj_max)."""
+    import tamf_b200
+    from conftest import rel_l2
+    from tamf_b200 import synth
+    from tamf_b200.extract_sample import SELECT_G, _same_len_batches, interaction_segment_collate, map_copy_select_to
+    g, r, diff = _models()
+    data = synth.make_items(7, T=T, nobj=3, seed=6, npoints=P, ragged=True)
+    assert len({it["obj_num"] for it in data}) > 1
+    batched = tamf_b200.refine_dataset(r, data, None, batch_size=4, commit=False)
+    single = tamf_b200.refine_dataset(r, data, None, batch_size=1, commit=False)
+    assert len(batched) == len(single) == 7
+    for a, b in zip(batched, single):
+        assert a["info"] == b["info"]
+        assert rel_l2(a["refine_pose_repr"], b["refine_pose_repr"]) < 1e-5
+        assert np.abs(a["verts"] - b["verts"]).max() < 1e-5
+    # G: one forward per launcher group vs one forward per item, same x_t rows
+    x = torch.randn(7, 99, 1, T, generator=torch.Generator().manual_seed(1)).cuda()
+    ts = lambda n: torch.full((n,), 400, dtype=torch.long, device="cuda")
+    for group in _same_len_batches(data, range(7), batch_size=4):
+        ids = [i for i, _ in group]
+        bd = map_copy_select_to(interaction_segment_collate([it for _, it in group]), device="cuda",
+                                dtype=torch.float32, select=SELECT_G)
+        full = g(x[ids], ts(len(ids)), bd).cpu().numpy()
+        for k, (i, it) in enumerate(group):
+            b1 = map_copy_select_to(interaction_segment_collate([it]), device="cuda", dtype=torch.float32, select=SELECT_G)
+            one = g(x[i:i + 1], ts(1), b1).cpu().numpy()
+            assert rel_l2(full[k:k + 1], one) < 1e-5

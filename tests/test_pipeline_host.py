@@ -94,3 +94,24 @@ def test_same_len_batches_and_worker_shards_cover_the_dataset():
             assert len(grp) <= 2 and len({it["pose_repr"].shape[0] for _, it in grp}) == 1
             seen += [i for i, _ in grp]
     assert seen == list(range(10))
+
+
+def test_launcher_groups_never_mix_object_counts():
+    """A batched chain must be the stack of the reference's B = 1 chains: the collate zero-pads the object axis and the
+    model averages over it, so items with different object counts (or frame counts) never share a group; one Philox
+    stream per group."""
+    from tamf_b200 import synth
+    from tamf_b200.extract_sample import _group_seed, _same_len_batches, interaction_segment_collate
+    items = synth.make_items(9, T=12, nobj=3, seed=5, npoints=16, ragged=True)
+    counts = [it["obj_num"] for it in items]
+    assert len(set(counts)) > 1  # the dataset really is ragged
+    groups = list(_same_len_batches(items, range(len(items)), batch_size=4))
+    assert [i for g in groups for i, _ in g] == list(range(9))  # order and coverage preserved
+    for g in groups:
+        assert len(g) <= 4 and len({it["obj_num"] for _, it in g}) == 1
+        b = interaction_segment_collate([it for _, it in g])
+        assert b["obj_traj"].shape[1] == g[0][1]["obj_num"]  # nothing was padded
+    assert len({_group_seed(7, g) for g in groups}) == len(groups) and _group_seed(None, groups[0]) is None
+    longer = synth.make_items(2, T=16, nobj=1, seed=1, npoints=16, ragged=False)
+    mixed = [items[0], longer[0], longer[1]]
+    assert [len(g) for g in _same_len_batches(mixed, range(3), batch_size=8)] == [1, 2]

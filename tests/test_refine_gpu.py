@@ -107,6 +107,33 @@ def test_fk_select_matches_full():
     assert bool((v[rest] == -7.0).all()) and bool((j[rest] == -7.0).all())
 
 
+def test_r_full_size_vs_oracle():
+    """BASELINE.json configs[2] size (arch_refine, B=64, T=160, one object of 8192 points, mixed hand sides) against the
+    live oracle: FK of all 10 240 frames <= 1e-5 m, sample_h2o_dist <= 2e-5, refine_pose_repr rel-L2 <= 1e-2 (and the
+    refinement delta itself <= 5e-2)."""
+    from oracle import tamf_oracle as orc
+    from tamf_b200 import synth
+    m, cfg = _model()
+    B, T = 64, 160
+    batch = synth.make_batch(B, T, nobj=1, seed=21, npoints=8192, with_pointcloud=True)
+    assert len(set(batch["hand_side"])) == 2
+    with torch.no_grad():
+        ref = orc.r_forward(synth.r_state_dict(cfg, 0), cfg, batch, synth.mano_assets("right"), synth.mano_assets("left"))
+    out = m(_dev(batch))
+    for k in ("sample_hand_verts", "sample_hand_joints", "target_hand_verts", "target_hand_joints"):
+        e = float((out[k].cpu() - ref[k]).abs().max())
+        print(f"{k}: max |d| {e:.2e} m")
+        assert e < 1e-5, k
+    for k in ("sample_h2o_dist", "target_h2o_dist"):
+        e = float((out[k].cpu() - ref[k]).abs().max())
+        print(f"{k}: max |d| {e:.2e}")
+        assert e < 2e-5, k
+    x_in = batch["sample_pose_repr"].numpy()
+    o, r = out["refine_pose_repr"].cpu().numpy(), ref["refine_pose_repr"].numpy()
+    print(f"refine_pose_repr rel_l2 {rel_l2(o, r):.3e}, delta rel_l2 {rel_l2(o - x_in, r - x_in):.3e}")
+    assert rel_l2(o, r) <= 1e-2 and rel_l2(o - x_in, r - x_in) <= 5e-2
+
+
 def test_r_full_size_properties():
     """BASELINE config 3 size (B=64, T=160, 1 object x 8192 points): finite, batch-row independence."""
     from tamf_b200 import synth
