@@ -272,6 +272,19 @@ int tamf_attn_trace(const uint16_t* qkv, uint16_t* out, int B, int S, int H, int
 int tamf_gemm_trace(int which, const uint16_t* a, const uint16_t* w, const float* bias, void* out, float* X, int M,
                     int N, int K, long long* trace, void* stream);
 
+/* Debug / self-test aid (tools/chain_trace.py, tests/test_gemm_gpu.py): ONE launch of a chain kernel (csrc/gemm_chain.cuh:
+ * two dependent GEMMs of an encoder layer in one persistent kernel) on caller data.
+ *   which 0: X = LN(X + a1 . w1^T + b1) ; c2 = gelu(Xh . w2^T + b2)     (out_proj + LN1 -> linear1 + GELU)
+ *   which 1: X = LN(...)                ; c2 = Xh . w2^T + b2           (linear2 + LN2 -> next in_proj)
+ *   which 2: X = LN(...) only
+ * a1 [M,K1], w1 [d,K1], w2 [N2,d] bf16; ln_params = [bias1 | gamma | beta] 3*d fp32; X = Xh + Xl, two bf16 planes [M,d],
+ * updated in place; c2 bf16 [M,N2]; aux: tamf_chain_aux_bytes(M, d, max(K1, N2)) bytes of device scratch; trace: null or
+ * int64 [148][64] per-CTA clock64 stamps. */
+size_t tamf_chain_aux_bytes(int M, int d, int ff);
+int tamf_chain_run(int which, const uint16_t* a1, const uint16_t* w1, const float* ln_params, uint16_t* Xh, uint16_t* Xl,
+                   const uint16_t* w2, const float* b2, uint16_t* c2, int M, int d, int K1, int N2, void* aux,
+                   size_t aux_bytes, long long* trace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

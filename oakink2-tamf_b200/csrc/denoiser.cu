@@ -151,6 +151,7 @@ struct tamf_denoiser {
   float* graph_x = nullptr;
   uint64_t graph_seed = 0;
   cudaStream_t graph_stream = nullptr;
+  int graph_kernels = 0;
 };
 
 namespace tamf {
@@ -349,7 +350,7 @@ static WsLayout ws_layout(const tamf_denoiser* h, int B, int T) {
       M * ff * 2,                                // 4 H
       Mf * KPAD * 2,                             // 5 A0
       Mf * d * 2,                                // 6 H0
-      256,                                       // 7 (unused)
+      encoder_aux_bytes((int)M, (int)d, (int)ff),  // 7 encoder aux: chain-kernel sync words, row statistics, schedules
       (size_t)B * 4 * d * 4,                     // 8 prefix
       256,                                       // 9 (unused)
       Mf * 9 * 4,                                // 10 trajmean
@@ -398,6 +399,7 @@ extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size
   h->buf.Hb = (__nv_bfloat16*)(p + L.off[4]);
   h->A0 = (__nv_bfloat16*)(p + L.off[5]);
   h->H0 = (__nv_bfloat16*)(p + L.off[6]);
+  h->buf.aux = p + L.off[7];
   h->prefix = (float*)(p + L.off[8]);
   h->trajmean = (float*)(p + L.off[10]);
   h->shapemean = (float*)(p + L.off[11]);
@@ -557,6 +559,7 @@ extern "C" int tamf_p_sample_chain(tamf_denoiser* h, float* x_io, int t_start, i
     TAMF_CUDA_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     const uint64_t before = g_launches.load();
     int rc = enqueue_step(h, x_io, h->t_dev, x_io, nullptr, nullptr, seed, cap, nullptr, false, /*advance=*/true);
+    h->graph_kernels = (int)(g_launches.load() - before);
     g_launches.store(before);  // capture records, it does not launch; replays are counted below
     cudaError_t e = cudaStreamEndCapture(cap, &g);
     if (own) cudaStreamDestroy(own);
@@ -574,7 +577,7 @@ extern "C" int tamf_p_sample_chain(tamf_denoiser* h, float* x_io, int t_start, i
     int rc0 = fill_int(h->t_dev, h->B, t_start, s);
     if (rc0) return rc0;
   }
-  const int per_step = 2 + 5 * h->L + 2;
+  const int per_step = h->graph_kernels;  // kernels of one captured step
   for (int t = t_start; t >= t_end; --t) {
     TAMF_CUDA_CHECK(cudaGraphLaunch(h->graph_exec, s));
     count_launch(per_step);

@@ -54,8 +54,20 @@ struct EncoderBuffers {
   CUtensorMap tm_QKV_st, tm_H_st;               // bf16 epilogue stores, box {64, 32}
   CUtensorMap tm_Xb_st, tm_Xlo;                 // LayerNorm epilogue: Xb / Xlo residual load + store, box {32, ln_rq} bf16
   CUtensorMap tm_att_kv, tm_att_o;    // attention: [B][S][3d] views of QKV (K/V box, Q box), [B][S][d] view of ATT
+  // ---- chain kernels (gemm_chain.cuh): out_proj+LN1 -> linear1+GELU and linear2+LN2 -> next in_proj ----
+  bool chain = false;                 // TAMF_CHAIN=0 keeps the five-kernel layer of round 1 (A/B comparisons)
+  void* aux = nullptr;                // caller-owned (workspace): sync words, row statistics, schedules
+  CUtensorMap tm_ATT128, tm_H128;     // phase-1 A operands, box {64, 128}
+  CUtensorMap tm_Xh32, tm_Xl32;       // residual planes, box {32, 32}: LayerNorm residual loads and result stores
+  unsigned *syncA = nullptr, *syncB = nullptr;  // [ready (tiles_m) | sflag (tiles_m * halves * 8)] of kernel A / B
+  int sync_words = 0, tiles_m = 0, halves = 0;
+  float* stats = nullptr;             // [tiles_m * halves * 2 * 128] float2
+  int *schedA = nullptr, *schedB = nullptr, *schedL = nullptr;  // [pairs + 1 offsets | unit codes]
+  int pairsA = 0, pairsB = 0, pairsL = 0;
   int make_maps(int d, int ff);
 };
+// bytes of EncoderBuffers::aux for an [M, d] problem (256-byte multiple)
+size_t encoder_aux_bytes(int M, int d, int ff);
 
 // Enqueue all L layers on `s`.  `marks` (profiling only): an event is recorded after every kernel.
 int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStream_t s,

@@ -171,7 +171,7 @@ static RWs r_layout(const tamf_refiner* h, int B, int T) {
       M * ff * 2,                            // 4 H
       Mf * R_K * 2,                          // 5 A0
       Mf * d * 2,                            // 6 H0
-      256,                                   // 7 (unused)
+      encoder_aux_bytes((int)M, (int)d, (int)ff),  // 7 encoder aux: chain-kernel sync words, row statistics, schedules
       (size_t)B * R_PREFIX * d * 4,          // 8 prefix
       256,                                   // 9 (unused)
       Mf * 9 * 4,                            // 10 trajmean
@@ -212,6 +212,7 @@ extern "C" int tamf_refiner_bind(tamf_refiner* h, int B, int T, void* ws, size_t
   h->buf.Hb = (__nv_bfloat16*)(p + L.off[4]);
   h->A0 = (__nv_bfloat16*)(p + L.off[5]);
   h->H0 = (__nv_bfloat16*)(p + L.off[6]);
+  h->buf.aux = p + L.off[7];
   h->prefix = (float*)(p + L.off[8]);
   h->trajmean = (float*)(p + L.off[10]);
   h->shapemean = (float*)(p + L.off[11]);

@@ -23,3 +23,45 @@ def test_gemm_matches_fp32(tile_n, cta_group, M, N, K):
     ref = a.float() @ w.float().t() + bias
     err = (c - ref).abs().max().item()
     assert err < 2e-3, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("which,M,d,K1,N2", [
+    (0, 300, 256, 256, 512), (0, 1000, 512, 512, 2048), (0, 10560, 512, 512, 2048), (1, 10560, 512, 2048, 1536),
+    (2, 777, 512, 1024, 0), (1, 10432, 256, 1024, 768), (2, 10560, 512, 2048, 0), (0, 58, 512, 512, 1024),
+    (1, 256, 512, 2048, 1536), (0, 19000, 512, 512, 2048)])
+def test_chain_kernel_matches_fp32(which, M, d, K1, N2):
+    """One launch of a chain kernel (csrc/gemm_chain.cuh): X = LayerNorm(X + A1 . W1^T + b1) in place as the bf16 hi/lo
+    pair, then C2 = act(Xh . W2^T + b2), against torch fp32 on the same bf16-rounded inputs.  Covers one and two column
+    halves (d = 256 / 512), row tiles that end inside the matrix, one unit per pair up to several rounds, no phase 2."""
+    from tamf_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + d + K1 + N2)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    a1 = rn(M, K1).to(torch.bfloat16)
+    w1 = (rn(d, K1) / K1 ** 0.5).to(torch.bfloat16)
+    lnp = torch.cat([0.1 * rn(d), 1 + 0.1 * rn(d), 0.1 * rn(d)]).contiguous()
+    x = rn(M, d)
+    xh = x.to(torch.bfloat16)
+    xl = (x - xh.float()).to(torch.bfloat16)
+    x_in = xh.float() + xl.float()
+    w2 = (rn(max(N2, 256), d) / d ** 0.5).to(torch.bfloat16)
+    b2 = 0.1 * rn(max(N2, 256))
+    c2 = torch.full((M, max(N2, 256)), float("nan"), device="cuda", dtype=torch.bfloat16)
+    nb = L.tamf_chain_aux_bytes(M, d, max(K1, N2, 3 * d))
+    aux = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    _lib.check(L.tamf_chain_run(which, _lib.ptr(a1), _lib.ptr(w1), _lib.ptr(lnp), _lib.ptr(xh), _lib.ptr(xl), _lib.ptr(w2),
+                                _lib.ptr(b2), _lib.ptr(c2), M, d, K1, N2, _lib.ptr(aux), nb, None, _lib.stream_ptr()),
+               "tamf_chain_run")
+    torch.cuda.synchronize()
+    y = x_in + a1.float() @ w1.float().t() + lnp[:d]
+    ref = torch.nn.functional.layer_norm(y, (d,), lnp[d:2 * d], lnp[2 * d:], 1e-5)
+    got = xh.float() + xl.float()
+    err = (got - ref).abs().max().item()
+    assert err < 5e-4, f"LayerNorm max abs err {err}"
+    assert torch.equal(xh, got.to(torch.bfloat16))  # the hi plane is bf16(x): it doubles as the next GEMM's operand
+    if which != 2:
+        r2 = xh.float() @ w2[:N2].float().t() + b2[:N2]
+        if which == 0:
+            r2 = torch.nn.functional.gelu(r2)
+        e2 = (c2[:, :N2].float() - r2).abs()
+        assert bool((e2 <= 1e-2 + 1e-2 * r2.abs()).all()), f"phase-2 max abs err {e2.max().item()}"

@@ -55,7 +55,6 @@ def main():
                                                       for k, v in conds[i % 2].items()}
             x = torch.empty(nb, 99, 1, T, device=dev)
             _lib.check(L.tamf_philox_normal(_lib.ptr(x), x.numel(), 7000 + ids.start, 1000, _lib.stream_ptr(dev)), "x_T")
-            model._cond_key = None
             diffusion._install(model, "ancestral")
             model.p_sample_chain(x, 999, 1000 - a.chain_steps, cb, seed=9000 + ids.start)
             out[ids.start - mine.start: ids.stop - mine.start] = x.permute(0, 3, 1, 2).squeeze(3)  # extract_sample.py:32
