@@ -281,6 +281,9 @@ int tamf_gemm_trace(int which, const uint16_t* a, const uint16_t* w, const float
  * updated in place; c2 bf16 [M,N2]; aux: tamf_chain_aux_bytes(M, d, max(K1, N2)) bytes of device scratch; trace: null or
  * int64 [148][64] per-CTA clock64 stamps. */
 size_t tamf_chain_aux_bytes(int M, int d, int ff);
+/* Debug aid (tools/chain_trace_model.py): the two chain kernels of encoder layer `layer` write per-CTA clock64 stamps
+ * (int64 [148][64] each, device) on every later launch of any handle in this process; null pointers switch it off. */
+int tamf_debug_chain_trace(long long* trace_a, long long* trace_b, int layer);
 int tamf_chain_run(int which, const uint16_t* a1, const uint16_t* w1, const float* ln_params, uint16_t* Xh, uint16_t* Xl,
                    const uint16_t* w2, const float* b2, uint16_t* c2, int M, int d, int K1, int N2, void* aux,
                    size_t aux_bytes, long long* trace, void* stream);

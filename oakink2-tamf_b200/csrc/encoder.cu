@@ -193,23 +193,24 @@ int EncoderStack::upload(DevPool& pool, const tamf_layer_weights* w, int d_, int
   return TAMF_OK;
 }
 
-// aux layout: [syncA | syncB | stats | schedA | schedB | schedL], every region 256-byte aligned
+// aux layout: [syncA | syncB | statsA | statsB | schedA | schedB | schedL], every region 256-byte aligned
 struct ChainLayout {
-  int tiles_m, halves, sync_words;
-  size_t off_syncA, off_syncB, off_stats, off_schedA, off_schedB, off_schedL, sched_bytes, total;
+  int tiles_m, halves, stats_words;
+  size_t off_syncA, off_syncB, off_statsA, off_statsB, off_schedA, off_schedB, off_schedL, sched_bytes, total;
 };
 static ChainLayout chain_layout(int M, int d, int ff) {
   ChainLayout L{};
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   L.tiles_m = (M + 255) / 256;
   L.halves = d / CH_BN;
-  L.sync_words = L.tiles_m + L.tiles_m * L.halves * 8;
+  L.stats_words = L.tiles_m * L.halves * 2 * 128;
   const int tiles_n2 = (ff > 3 * d ? ff : 3 * d) / CH_BN;
   L.sched_bytes = al(((size_t)num_sms() / 2 + 1 + (size_t)L.tiles_m * (L.halves + tiles_n2)) * 4);
   size_t o = 0;
-  L.off_syncA = o, o += al((size_t)L.sync_words * 4);
-  L.off_syncB = o, o += al((size_t)L.sync_words * 4);
-  L.off_stats = o, o += al((size_t)L.tiles_m * L.halves * 2 * 128 * 8);
+  L.off_syncA = o, o += al((size_t)L.tiles_m * 4);
+  L.off_syncB = o, o += al((size_t)L.tiles_m * 4);
+  L.off_statsA = o, o += al((size_t)L.stats_words * 8);
+  L.off_statsB = o, o += al((size_t)L.stats_words * 8);
   L.off_schedA = o, o += L.sched_bytes;
   L.off_schedB = o, o += L.sched_bytes;
   L.off_schedL = o, o += L.sched_bytes;
@@ -239,14 +240,17 @@ int EncoderBuffers::make_maps(int d, int ff) {
   if (!chain) return TAMF_OK;
   if ((rc = make_tmap_2d_bf16(&tm_ATT128, ATT, d, M, (uint64_t)d * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_H128, Hb, ff, M, (uint64_t)ff * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tm_Xh32, Xb, d, M, (uint64_t)d * 2, 32, 32))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tm_Xl32, Xlo, d, M, (uint64_t)d * 2, 32, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_Xlo128, Xlo, d, M, (uint64_t)d * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_Xh_st, Xb, d, M, (uint64_t)d * 2, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_Xl_st, Xlo, d, M, (uint64_t)d * 2, 64, 32))) return rc;
+  if ((rc = chain_identity_map(&tm_ident))) return rc;
   const ChainLayout lay = chain_layout(M, d, ff);
-  tiles_m = lay.tiles_m, halves = lay.halves, sync_words = lay.sync_words;
+  tiles_m = lay.tiles_m, halves = lay.halves, stats_words = lay.stats_words;
   uint8_t* a = static_cast<uint8_t*>(aux);
   syncA = reinterpret_cast<unsigned*>(a + lay.off_syncA);
   syncB = reinterpret_cast<unsigned*>(a + lay.off_syncB);
-  stats = reinterpret_cast<float*>(a + lay.off_stats);
+  statsA = reinterpret_cast<unsigned long long*>(a + lay.off_statsA);
+  statsB = reinterpret_cast<unsigned long long*>(a + lay.off_statsB);
   schedA = reinterpret_cast<int*>(a + lay.off_schedA);
   schedB = reinterpret_cast<int*>(a + lay.off_schedB);
   schedL = reinterpret_cast<int*>(a + lay.off_schedL);
@@ -255,12 +259,13 @@ int EncoderBuffers::make_maps(int d, int ff) {
   // epilogue FMA-pipe bound.  A unit occupies its pair for max(mainloop, epilogue); the rows of a LayerNorm unit are in L2
   // min(mainloop, epilogue) later.
   auto env_d = [](const char* k, double v) { return getenv(k) ? atof(getenv(k)) : v; };
-  const double kb = env_d("TAMF_CHAIN_KB", 540.0), e_ln = env_d("TAMF_CHAIN_EPI_LN", 9000.0);
-  const double e_gelu = env_d("TAMF_CHAIN_EPI_GELU", 4800.0), e_bias = env_d("TAMF_CHAIN_EPI_BIAS", 3000.0);
+  const double kb = env_d("TAMF_CHAIN_KB", 540.0), e_ln = env_d("TAMF_CHAIN_EPI_LN", 11000.0);
+  const double e_gelu = env_d("TAMF_CHAIN_EPI_GELU", 5000.0), e_bias = env_d("TAMF_CHAIN_EPI_BIAS", 4300.0);
   auto mx = [](double x, double y) { return x > y ? x : y; };
   auto mn = [](double x, double y) { return x < y ? x : y; };
   const int slots = num_sms() / 2;
-  const double mA = kb * d / 64, mB = kb * ff / 64, m2 = kb * d / 64;
+  const double res = env_d("TAMF_CHAIN_RES", 2000.0);  // the 4 residual ring stages of a LayerNorm unit
+  const double mA = kb * d / 64 + res, mB = kb * ff / 64 + res, m2 = kb * d / 64;
   const ChainSchedule sa = build_chain_schedule(M, d, ff, slots, mx(mA, e_ln), mn(mA, e_ln), mx(m2, e_gelu));
   const ChainSchedule sb = build_chain_schedule(M, d, 3 * d, slots, mx(mB, e_ln), mn(mB, e_ln), mx(m2, e_bias));
   const ChainSchedule sl = build_chain_schedule(M, d, 0, slots, mx(mB, e_ln), mn(mB, e_ln), 0.0);
@@ -272,8 +277,11 @@ int EncoderBuffers::make_maps(int d, int ff) {
     return TAMF_OK;
   };
   if ((rc = upload(schedA, sa)) || (rc = upload(schedB, sb)) || (rc = upload(schedL, sl))) return rc;
-  TAMF_CUDA_CHECK(cudaMemset(syncA, 0, (size_t)sync_words * 4));  // afterwards each chain kernel clears its sibling's words
-  TAMF_CUDA_CHECK(cudaMemset(syncB, 0, (size_t)sync_words * 4));
+  // afterwards each chain kernel resets its sibling's words
+  TAMF_CUDA_CHECK(cudaMemset(syncA, 0, (size_t)tiles_m * 4));
+  TAMF_CUDA_CHECK(cudaMemset(syncB, 0, (size_t)tiles_m * 4));
+  TAMF_CUDA_CHECK(cudaMemset(statsA, 0xFF, (size_t)stats_words * 8));
+  TAMF_CUDA_CHECK(cudaMemset(statsB, 0xFF, (size_t)stats_words * 8));
   return TAMF_OK;
 }
 
@@ -291,6 +299,10 @@ int configure_encoder_kernels() {
   return TAMF_OK;
 }
 
+// debug only (tools/chain_trace_model.py): per-CTA timelines of the two chain kernels of one layer inside a real step
+static long long* g_dbg_trace[2] = {nullptr, nullptr};
+static int g_dbg_trace_layer = -1;
+
 // Chain form of the stack (gemm_chain.cuh): in_proj(0), then per layer  attention | out_proj+LN1 -> linear1+GELU |
 // linear2+LN2 -> in_proj of the next layer  = 1 + 3 L kernels.
 static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& buf, cudaStream_t s,
@@ -306,9 +318,8 @@ static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& 
   }
   ChainParams base{};
   base.M = M, base.N1 = d;
-  base.stats = reinterpret_cast<float2*>(buf.stats);
   base.ready_target = (unsigned)(buf.halves * 2 * GEMM_EPI_WARPS);
-  base.zero_n = buf.sync_words;
+  base.zero_n = buf.tiles_m, base.ones_n = buf.stats_words;
   static const int dbg = getenv("TAMF_CHAIN_DBG") ? atoi(getenv("TAMF_CHAIN_DBG")) : 0;
   base.dbg = dbg;
   for (int l = 0; l < enc.L; ++l) {
@@ -326,8 +337,10 @@ static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& 
       p.K1 = d, p.N2 = ff, p.K2 = d;
       p.bias1 = w.b_out, p.gamma = w.g1, p.beta = w.be1, p.bias2 = w.b1;
       p.sched_off = buf.schedA, p.sched = buf.schedA + buf.pairsA + 1;
-      p.ready = buf.syncA, p.sflag = buf.syncA + buf.tiles_m, p.zero_ptr = buf.syncB;
-      ChainMaps tm{&buf.tm_ATT128, &w.tm_out, &buf.tm_Xb, &w.tm_w1, &buf.tm_H_st, &buf.tm_Xh32, &buf.tm_Xl32};
+      p.ready = buf.syncA, p.stats = buf.statsA, p.zero_ptr = buf.syncB, p.ones_ptr = buf.statsB;
+      if (l == g_dbg_trace_layer) p.trace = g_dbg_trace[0];
+      ChainMaps tm{&buf.tm_ATT128, &w.tm_out, &buf.tm_Xb, &buf.tm_Xlo128, &w.tm_w1, &buf.tm_H_st, &buf.tm_Xh_st,
+                   &buf.tm_Xl_st, &buf.tm_ident};
       if ((rc = launch_gemm_chain<CHAIN_GELU>(tm, p, buf.pairsA, s))) return rc;
       mark_event(marks, s);
     }
@@ -339,9 +352,10 @@ static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& 
       const int* sc = last ? buf.schedL : buf.schedB;
       const int pairs = last ? buf.pairsL : buf.pairsB;
       p.sched_off = sc, p.sched = sc + pairs + 1;
-      p.ready = buf.syncB, p.sflag = buf.syncB + buf.tiles_m, p.zero_ptr = buf.syncA;
-      ChainMaps tm{&buf.tm_H128, &w.tm_w2, &buf.tm_Xb, last ? nullptr : &enc.layers[l + 1].tm_in,
-                   last ? nullptr : &buf.tm_QKV_st, &buf.tm_Xh32, &buf.tm_Xl32};
+      p.ready = buf.syncB, p.stats = buf.statsB, p.zero_ptr = buf.syncA, p.ones_ptr = buf.statsA;
+      if (l == g_dbg_trace_layer) p.trace = g_dbg_trace[1];
+      ChainMaps tm{&buf.tm_H128, &w.tm_w2, &buf.tm_Xb, &buf.tm_Xlo128, last ? nullptr : &enc.layers[l + 1].tm_in,
+                   last ? nullptr : &buf.tm_QKV_st, &buf.tm_Xh_st, &buf.tm_Xl_st, &buf.tm_ident};
       if ((rc = launch_gemm_chain<CHAIN_BIAS>(tm, p, pairs, s))) return rc;
       mark_event(marks, s);
     }
@@ -402,6 +416,12 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
 
 // Debug / self-test aid (tools/chain_trace.py, tests/test_gemm_gpu.py): ONE launch of a chain kernel on caller data.
 // which: 0 = A (LN(X + a1 . w1^T) -> gelu(Xb . w2^T)), 1 = B (LN(...) -> Xb . w2^T + b2), 2 = LN only.
+extern "C" int tamf_debug_chain_trace(long long* trace_a, long long* trace_b, int layer) {
+  tamf::g_dbg_trace[0] = trace_a, tamf::g_dbg_trace[1] = trace_b;
+  tamf::g_dbg_trace_layer = (trace_a || trace_b) ? layer : -1;
+  return TAMF_OK;
+}
+
 extern "C" size_t tamf_chain_aux_bytes(int M, int d, int ff) { return tamf::encoder_aux_bytes(M, d, ff); }
 
 extern "C" int tamf_chain_run(int which, const uint16_t* a1, const uint16_t* w1, const float* ln_params, uint16_t* Xh,
@@ -420,21 +440,23 @@ extern "C" int tamf_chain_run(int which, const uint16_t* a1, const uint16_t* w1,
   const ChainLayout lay = chain_layout(M, d, ffmax > 3 * d ? ffmax : 3 * d);
   TAMF_REQUIRE(aux_bytes >= lay.total, TAMF_E_BADARG, "tamf_chain_run: aux too small (tamf_chain_aux_bytes(M, d, max(K1, N2)))");
   if ((rc = configure_gemm_chain<CHAIN_GELU>()) || (rc = configure_gemm_chain<CHAIN_BIAS>())) return rc;
-  CUtensorMap tA1, tB1, tA2, tB2, tC2, tXh, tXl;
+  CUtensorMap tA1, tB1, tXh, tXl, tB2, tC2, tXhs, tXls, tI;
   const uint32_t wbox = (uint32_t)gemm_b_box_rows(256, 2);
   if ((rc = make_tmap_2d_bf16(&tA1, a1, K1, M, (uint64_t)K1 * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tB1, w1, K1, d, (uint64_t)K1 * 2, 64, wbox))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tXh, Xh, d, M, (uint64_t)d * 2, 32, 32))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tXl, Xl, d, M, (uint64_t)d * 2, 32, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tXh, Xh, d, M, (uint64_t)d * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tXl, Xl, d, M, (uint64_t)d * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tXhs, Xh, d, M, (uint64_t)d * 2, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tXls, Xl, d, M, (uint64_t)d * 2, 64, 32))) return rc;
+  if ((rc = chain_identity_map(&tI))) return rc;
   if (N2) {
-    if ((rc = make_tmap_2d_bf16(&tA2, Xh, d, M, (uint64_t)d * 2, 64, 128))) return rc;
     if ((rc = make_tmap_2d_bf16(&tB2, w2, d, N2, (uint64_t)d * 2, 64, wbox))) return rc;
     if ((rc = make_tmap_2d_bf16(&tC2, c2, N2, M, (uint64_t)N2 * 2, 64, 32))) return rc;
   }
   auto env_d = [](const char* k, double v) { return getenv(k) ? atof(getenv(k)) : v; };
-  const double kb = env_d("TAMF_CHAIN_KB", 540.0), e_ln = env_d("TAMF_CHAIN_EPI_LN", 9000.0);
-  const double e2 = which == 0 ? env_d("TAMF_CHAIN_EPI_GELU", 4800.0) : env_d("TAMF_CHAIN_EPI_BIAS", 3000.0);
-  const double m1 = kb * K1 / 64, m2 = kb * d / 64;
+  const double kb = env_d("TAMF_CHAIN_KB", 540.0), e_ln = env_d("TAMF_CHAIN_EPI_LN", 11000.0);
+  const double e2 = which == 0 ? env_d("TAMF_CHAIN_EPI_GELU", 5000.0) : env_d("TAMF_CHAIN_EPI_BIAS", 4300.0);
+  const double m1 = kb * K1 / 64 + env_d("TAMF_CHAIN_RES", 2000.0), m2 = kb * d / 64;
   const ChainSchedule sc = build_chain_schedule(M, d, N2, num_sms() / 2, m1 > e_ln ? m1 : e_ln, m1 < e_ln ? m1 : e_ln,
                                                 m2 > e2 ? m2 : e2);
   uint8_t* a = static_cast<uint8_t*>(aux);
@@ -444,16 +466,19 @@ extern "C" int tamf_chain_run(int which, const uint16_t* a1, const uint16_t* w1,
   TAMF_CUDA_CHECK(cudaMemcpyAsync(sched + sc.pairs + 1, sc.units.data(), sc.units.size() * 4, cudaMemcpyHostToDevice, stream));
   TAMF_CUDA_CHECK(cudaStreamSynchronize(stream));  // the host vectors go out of scope
   unsigned* sync = reinterpret_cast<unsigned*>(a + lay.off_syncA);
-  TAMF_CUDA_CHECK(cudaMemsetAsync(sync, 0, (size_t)lay.sync_words * 4, stream));
+  unsigned long long* stats = reinterpret_cast<unsigned long long*>(a + lay.off_statsA);
+  TAMF_CUDA_CHECK(cudaMemsetAsync(sync, 0, (size_t)lay.tiles_m * 4, stream));
+  TAMF_CUDA_CHECK(cudaMemsetAsync(stats, 0xFF, (size_t)lay.stats_words * 8, stream));
   ChainParams p{};
   p.M = M, p.N1 = d, p.K1 = K1, p.N2 = N2, p.K2 = d;
   p.bias1 = ln_params, p.gamma = ln_params + d, p.beta = ln_params + 2 * d, p.bias2 = b2;
   p.sched_off = sched, p.sched = sched + sc.pairs + 1;
-  p.ready = sync, p.sflag = sync + lay.tiles_m, p.stats = reinterpret_cast<float2*>(a + lay.off_stats);
+  p.ready = sync, p.stats = stats;
   p.ready_target = (unsigned)(lay.halves * 2 * GEMM_EPI_WARPS);
-  p.zero_ptr = reinterpret_cast<unsigned*>(a + lay.off_syncB), p.zero_n = lay.sync_words;
+  p.zero_ptr = reinterpret_cast<unsigned*>(a + lay.off_syncB), p.zero_n = lay.tiles_m;
+  p.ones_ptr = reinterpret_cast<unsigned long long*>(a + lay.off_statsB), p.ones_n = lay.stats_words;
   p.trace = trace;
-  ChainMaps tm{&tA1, &tB1, N2 ? &tA2 : nullptr, N2 ? &tB2 : nullptr, N2 ? &tC2 : nullptr, &tXh, &tXl};
+  ChainMaps tm{&tA1, &tB1, &tXh, &tXl, N2 ? &tB2 : nullptr, N2 ? &tC2 : nullptr, &tXhs, &tXls, &tI};
   return which == 0 ? launch_gemm_chain<CHAIN_GELU>(tm, p, sc.pairs, stream)
                     : launch_gemm_chain<CHAIN_BIAS>(tm, p, sc.pairs, stream);
 }

@@ -58,10 +58,12 @@ struct EncoderBuffers {
   bool chain = false;                 // TAMF_CHAIN=0 keeps the five-kernel layer of round 1 (A/B comparisons)
   void* aux = nullptr;                // caller-owned (workspace): sync words, row statistics, schedules
   CUtensorMap tm_ATT128, tm_H128;     // phase-1 A operands, box {64, 128}
-  CUtensorMap tm_Xh32, tm_Xl32;       // residual planes, box {32, 32}: LayerNorm residual loads and result stores
-  unsigned *syncA = nullptr, *syncB = nullptr;  // [ready (tiles_m) | sflag (tiles_m * halves * 8)] of kernel A / B
-  int sync_words = 0, tiles_m = 0, halves = 0;
-  float* stats = nullptr;             // [tiles_m * halves * 2 * 128] float2
+  CUtensorMap tm_Xlo128;              // low residual plane, box {64, 128} (the high plane is tm_Xb)
+  CUtensorMap tm_Xh_st, tm_Xl_st;     // residual planes, box {64, 32}: LayerNorm result stores
+  CUtensorMap tm_ident;               // 64 x 64 identity (gemm_chain.cuh chain_identity_map)
+  unsigned *syncA = nullptr, *syncB = nullptr;  // ready counters [tiles_m] of kernel A / B
+  unsigned long long *statsA = nullptr, *statsB = nullptr;  // row statistics words [tiles_m * halves * 2 * 128]
+  int tiles_m = 0, halves = 0, stats_words = 0;
   int *schedA = nullptr, *schedB = nullptr, *schedL = nullptr;  // [pairs + 1 offsets | unit codes]
   int pairsA = 0, pairsB = 0, pairsL = 0;
   int make_maps(int d, int ff);

@@ -23,7 +23,7 @@ SYMBOLS = [
     "tamf_gemm_selftest", "tamf_refiner_create", "tamf_refiner_destroy", "tamf_refiner_workspace_bytes",
     "tamf_refiner_bind", "tamf_refiner_forward", "tamf_mano_fk_select", "tamf_vertex_normals", "tamf_gemm_trace",
     "tamf_attn_selftest", "tamf_attn_trace", "tamf_denoiser_set_sampler", "tamf_denoiser_sampler_steps",
-    "tamf_chain_aux_bytes", "tamf_chain_run",
+    "tamf_chain_aux_bytes", "tamf_chain_run", "tamf_debug_chain_trace",
 ]
 
 
@@ -114,6 +114,7 @@ def lib() -> C.CDLL:
     L.tamf_attn_trace.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     L.tamf_chain_aux_bytes.argtypes = [i32, i32, i32]
     L.tamf_chain_aux_bytes.restype = sz
+    L.tamf_debug_chain_trace.argtypes = [vp, vp, i32]
     L.tamf_chain_run.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp, vp]
     _lib = L
     return L
