@@ -49,8 +49,8 @@ def flops_per_seq_step(cfg, T=T_FRAMES):
 
 def kernel_classes(cfg, B, T=T_FRAMES, chain=True):
     """(name, algorithmic FLOPs per launch) in the launch order tamf_denoiser_profile_step reports.  chain=True: the
-    chain-kernel form of the encoder (csrc/gemm_chain.cuh): in_proj of layer 0, then per layer attention | out_proj+LN1 ->
-    linear1+GELU | linear2+LN2 -> in_proj of the next layer; chain=False: the five-kernel layer (TAMF_CHAIN=0)."""
+    layer-kernel form of the encoder (csrc/layer_chain.cuh): in_proj of layer 0, then per layer attention | out_proj+LN1 ->
+    linear1+GELU -> linear2+LN2 -> in_proj of the next layer in ONE kernel; chain=False: the five-kernel layer (TAMF_CHAIN=0)."""
     d, ff, L = cfg["latent_dim"], cfg["ff_size"], cfg["num_layers"]
     S = T + 5
     M, Mf = B * S, B * T
@@ -59,8 +59,7 @@ def kernel_classes(cfg, B, T=T_FRAMES, chain=True):
     if chain:
         out.append(("in_proj0", f_in))
         for l in range(L):
-            out += [("attention", f_att), ("outproj_ln1_linear1_gelu", f_out + f_l1),
-                    ("linear2_ln2_inproj", f_l2 + (f_in if l + 1 < L else 0))]
+            out += [("attention", f_att), ("layer_ln1_l1_ln2_inproj", f_out + f_l1 + f_l2 + (f_in if l + 1 < L else 0))]
     else:
         for _ in range(L):
             out += [("in_proj", f_in), ("attention", f_att), ("out_proj_ln", f_out), ("linear1_gelu", f_l1),

@@ -242,6 +242,14 @@ int tamf_vertex_normals(const float* verts, const int32_t* faces, int N, int V, 
  * ms_out [cap] HOST floats, *n_out = number of kernels (3 + 5 L + 1).  x_io is advanced one step.  Synchronous. */
 int tamf_denoiser_profile_step(tamf_denoiser* h, float* x_io, int t, uint64_t seed, float* ms_out_host, int cap,
                                int* n_out_host, void* stream);
+/* In-graph per-kernel breakdown (bench.py `roofline.kernels_in_graph`): the step is captured in a CUDA graph exactly as
+ * tamf_p_sample_chain captures it (same kernels, same programmatic dependent launches); every kernel additionally
+ * records, on the globaltimer all SMs share, its earliest CTA entry, the earliest end of a dependency wait and its latest
+ * CTA exit.  n_steps (>= 4) replays run back to back from t_start downwards; the last three are averaged.  Outputs per
+ * kernel in launch order (microseconds relative to the entry of the step's first kernel), n_out kernels, and the mean
+ * step period step_us.  x_io is advanced n_steps sampler steps. */
+int tamf_denoiser_profile_graph(tamf_denoiser* h, float* x_io, int t_start, int n_steps, uint64_t seed, double* entry_us,
+                                double* ready_us, double* exit_us, int cap, int* n_out, double* step_us, void* stream);
 
 /* Number of kernels this library launched since load (for bench.py's gpu_launches claim). */
 uint64_t tamf_kernel_launch_count(void);
@@ -272,21 +280,26 @@ int tamf_attn_trace(const uint16_t* qkv, uint16_t* out, int B, int S, int H, int
 int tamf_gemm_trace(int which, const uint16_t* a, const uint16_t* w, const float* bias, void* out, float* X, int M,
                     int N, int K, long long* trace, void* stream);
 
-/* Debug / self-test aid (tools/chain_trace.py, tests/test_gemm_gpu.py): ONE launch of a chain kernel (csrc/gemm_chain.cuh:
- * two dependent GEMMs of an encoder layer in one persistent kernel) on caller data.
- *   which 0: X = LN(X + a1 . w1^T + b1) ; c2 = gelu(Xh . w2^T + b2)     (out_proj + LN1 -> linear1 + GELU)
- *   which 1: X = LN(...)                ; c2 = Xh . w2^T + b2           (linear2 + LN2 -> next in_proj)
- *   which 2: X = LN(...) only
- * a1 [M,K1], w1 [d,K1], w2 [N2,d] bf16; ln_params = [bias1 | gamma | beta] 3*d fp32; X = Xh + Xl, two bf16 planes [M,d],
- * updated in place; c2 bf16 [M,N2]; aux: tamf_chain_aux_bytes(M, d, max(K1, N2)) bytes of device scratch; trace: null or
- * int64 [148][64] per-CTA clock64 stamps. */
-size_t tamf_chain_aux_bytes(int M, int d, int ff);
-/* Debug aid (tools/chain_trace_model.py): the two chain kernels of encoder layer `layer` write per-CTA clock64 stamps
- * (int64 [148][64] each, device) on every later launch of any handle in this process; null pointers switch it off. */
-int tamf_debug_chain_trace(long long* trace_a, long long* trace_b, int layer);
-int tamf_chain_run(int which, const uint16_t* a1, const uint16_t* w1, const float* ln_params, uint16_t* Xh, uint16_t* Xl,
-                   const uint16_t* w2, const float* b2, uint16_t* c2, int M, int d, int K1, int N2, void* aux,
-                   size_t aux_bytes, long long* trace, void* stream);
+/* Debug / self-test aid (tools/layer_trace.py, tests/test_gemm_gpu.py): ONE launch of the layer kernel
+ * (csrc/layer_chain.cuh: everything between two attention kernels of the encoder stack in one persistent kernel) on
+ * caller data:  X = LN1(X + att . w_out^T + b_out);  H = gelu(Xh . w1^T + b1);  X = LN2(X + H . w2^T + b2);
+ * qkv = Xh . w_in^T + b_in (n_inp = 3 d; n_inp = 0 skips it, as after the last layer).
+ * att [M,d], w_out [d,d], w1 [ff,d], w2 [d,ff], w_in [3d,d] bf16; ln_params = [b_out | g1 | be1 | b2 | g2 | be2] 6*d fp32;
+ * X = Xh + Xl, two bf16 planes [M,d], updated in place; Hbuf bf16 [M,ff]; qkv bf16 [M,3d]; aux: tamf_layer_aux_bytes(M, d,
+ * ff) bytes of device scratch; trace: null or int64 [148][64] per-CTA clock64 stamps. */
+size_t tamf_layer_aux_bytes(int M, int d, int ff);
+int tamf_layer_run(const uint16_t* att, const uint16_t* w_out, const uint16_t* w1, const uint16_t* w2, const uint16_t* w_in,
+                   const float* ln_params, const float* b1, const float* b_in, uint16_t* Xh, uint16_t* Xl, uint16_t* Hbuf,
+                   uint16_t* qkv, int M, int d, int ff, int n_inp, void* aux, size_t aux_bytes, long long* trace,
+                   void* stream);
+/* Debug aid (tools/chain_trace_model.py): the layer kernel of encoder layer `layer` writes per-CTA clock64 stamps (int64
+ * [148][64], device) on every later launch of any handle in this process; a null pointer switches it off. */
+int tamf_debug_chain_trace(long long* trace, int layer);
+/* Host-only (no GPU needed): the static schedule the layer kernel runs for an [M, d] problem on `slots` CTA pairs.
+ * off_out [slots + 1], units_out [cap] unit codes kind << 28 | row tile << 8 | column tile (kind 0 LN1, 1 L1, 2 LN2,
+ * 3 INP); makespan_out: the cost model's estimate in cycles.  Returns the pair count, or a negative TAMF_E_* code. */
+int tamf_layer_schedule(int M, int d, int ff, int n_inp, int slots, int* off_out, int* units_out, int cap,
+                        double* makespan_out);
 
 #ifdef __cplusplus
 }

@@ -106,7 +106,7 @@ __device__ __forceinline__ void atc_sts128(uint32_t addr, uint32_t a, uint32_t b
 template <int HD>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmO, int S, int d,
-                   int dbg, long long* trace) {
+                   int dbg, long long* trace, long long* ktime) {
   // debug only (tools/attn_trace.py): per-CTA clock64 stamps [grid][16]; null in the product path
 #define ATC_TRACE(slot)                                                                                   \
   do {                                                                                                    \
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
   const int ntile = S > 128 ? 2 : 1;
   if (threadIdx.x == 0) {
     ATC_TRACE(0);
+    ktime_entry(ktime);
     if (trace) {
       unsigned long long gt;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     // all lanes run the issue sequence (uniform descriptors / coordinates, see elect_one()); one elected lane issues
     if (elect_one()) {
       pdl_wait();  // QKV is the previous kernel's output
+      ktime_ready(ktime);
       mbar_arrive_expect_tx(&bars[0], 2 * NB * C::BLK);
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
   __syncthreads();
   if (threadIdx.x == 0) {
     ATC_TRACE(12);
+    ktime_exit(ktime);
     if (trace) {
       unsigned long long gt;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -356,7 +359,8 @@ int configure_attn_tc() {
 }
 
 template <int HD>
-int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t stream, long long* trace = nullptr) {
+int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t stream, long long* trace = nullptr,
+                   long long* ktime = nullptr) {
   TAMF_REQUIRE(S <= ATC_KP, TAMF_E_BADARG, "attention: at most 176 tokens per sequence");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(H, B);
@@ -373,7 +377,7 @@ int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t
   cfg.attrs = attr;
   cfg.numAttrs = na;
   static const int dbg = getenv("TAMF_ATTN_DBG") ? atoi(getenv("TAMF_ATTN_DBG")) : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel<HD>, m.kv, m.o, S, d, dbg, trace);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel<HD>, m.kv, m.o, S, d, dbg, trace, ktime);
   count_launch();
   if (e != cudaSuccess) {
     set_error(std::string("attention launch failed: ") + cudaGetErrorString(e));

@@ -184,6 +184,23 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem
                : "memory");
 }
 
+// In-graph kernel timing (debug, tamf_denoiser_profile_graph): kt[0] = earliest CTA entry, kt[1] = earliest end of a CTA's
+// dependency wait, kt[2] = latest CTA exit, all in globaltimer nanoseconds (one clock for every SM).  Null in product.
+__device__ __forceinline__ unsigned long long tamf_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void ktime_entry(long long* kt) {
+  if (kt) atomicMin(reinterpret_cast<unsigned long long*>(kt), tamf_globaltimer());
+}
+__device__ __forceinline__ void ktime_ready(long long* kt) {
+  if (kt) atomicMin(reinterpret_cast<unsigned long long*>(kt + 1), tamf_globaltimer());
+}
+__device__ __forceinline__ void ktime_exit(long long* kt) {
+  if (kt) atomicMax(reinterpret_cast<unsigned long long*>(kt + 2), tamf_globaltimer());
+}
+
 // Programmatic dependent launch (PDL) controls
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -75,8 +75,12 @@ __global__ void __launch_bounds__(256)
     prep_kernel(const float* __restrict__ x, int* __restrict__ t_ptr, int* __restrict__ t_cur,
                 const float* __restrict__ ttab, const float* __restrict__ pe, const float* __restrict__ prefix,
                 __nv_bfloat16* __restrict__ A0, __nv_bfloat16* __restrict__ Xlo, __nv_bfloat16* __restrict__ Xb, int T,
-                int S, int d, int nfeat) {
+                int S, int d, int nfeat, long long* ktime) {
   __shared__ float tile[KPAD][33];
+  if (threadIdx.x == 0) {
+    ktime_entry(ktime);
+    ktime_ready(ktime);
+  }
   const int b = blockIdx.y, tau0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int k = w; k < nfeat; k += 8) {
@@ -108,6 +112,8 @@ __global__ void __launch_bounds__(256)
       store_hilo(Xb, Xlo, ((size_t)b * S + s) * d + c, v);
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) ktime_exit(ktime);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -170,18 +176,21 @@ static int upload_bf16(tamf_denoiser* h, __nv_bfloat16** dst, const float* src, 
 // decrements it for the next replay.
 static int enqueue_step(tamf_denoiser* h, const float* x_t, int* t_ptr, float* x_out, float* x0_out,
                         const float* noise, uint64_t seed, cudaStream_t s, std::vector<cudaEvent_t>* marks = nullptr,
-                        bool model_level = false, bool advance = false) {
+                        bool model_level = false, bool advance = false, long long* ktime = nullptr) {
   const int d = h->d, B = h->B, T = h->T, S = h->S, M = h->M, Mf = h->Mf;
   int rc;
+  int kidx = 0;  // profiling only: 4 int64 timing slots per kernel, in launch order
+  auto kt = [&]() -> long long* { return ktime ? ktime + 4 * (kidx++) : nullptr; };
   mark_event(marks, s);
   prep_kernel<<<dim3((T + 31) / 32, B), 256, 0, s>>>(x_t, t_ptr, advance ? h->t_cur : nullptr,
                                                      model_level ? h->ttab : h->k_ttab, h->pe, h->prefix, h->A0,
-                                                     h->buf.Xlo, h->buf.Xb, T, S, d, h->nfeat);
+                                                     h->buf.Xlo, h->buf.Xb, T, S, d, h->nfeat, kt());
   TAMF_LAUNCH_CHECK();
   mark_event(marks, s);
   {  // embed-a
     GemmParams p{};
     p.M = Mf, p.N = d, p.K = KPAD, p.bias = h->merge_bias, p.out_bf16 = h->H0, p.ld_bf16 = d, p.tmC = &h->tm_H0_st;
+    p.ktime = kt();
     if ((rc = launch_gemm<256, EPI_BIAS_SILU_BF16, 2>(h->tm_A0, h->tm_wfold, p, s))) return rc;
     mark_event(marks, s);
   }
@@ -190,15 +199,17 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, int* t_ptr, float* x
     p.M = Mf, p.N = d, p.K = d, p.bias = h->b_m2, p.pe = h->pe, p.T = T, p.S = S, p.P0 = 5, p.Xlo = h->buf.Xlo,
     p.Xb = h->buf.Xb;
     p.tmC = &h->tm_tok_hi, p.tmX = &h->tm_tok_lo;
+    p.ktime = kt();
     if ((rc = launch_gemm<256, EPI_TOKEN_OUT, 2>(h->tm_H0, h->tm_wm2, p, s))) return rc;
     mark_event(marks, s);
   }
-  if ((rc = enqueue_encoder(h->enc, h->buf, s, marks))) return rc;
+  if ((rc = enqueue_encoder(h->enc, h->buf, s, marks, ktime, &kidx))) return rc;
   {  // final projection + DDPM posterior
     GemmParams p{};
     p.M = M, p.N = h->nfeat, p.K = d, p.bias = h->b_fin, p.T = T, p.S = S, p.P0 = 5, p.nfeat = h->nfeat;
     p.x_t = x_t, p.x_out = x_out, p.x0_out = x0_out, p.noise = noise, p.t_ptr = advance ? h->t_cur : t_ptr, p.c1 = h->k1, p.c2 = h->k2,
     p.sigma = h->ks, p.seed = seed;
+    p.ktime = kt();
     if ((rc = launch_gemm<128, EPI_POSTERIOR, 2>(h->tm_Xb_fin, h->tm_wfin, p, s))) return rc;
     mark_event(marks, s);
   }
@@ -538,6 +549,100 @@ extern "C" int tamf_denoiser_profile_step(tamf_denoiser* h, float* x_io, int t, 
   if (rc) return rc;
   TAMF_CUDA_CHECK(e);
   return TAMF_OK;
+}
+
+namespace tamf {
+__global__ void ktime_init_kernel(long long* kt, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    kt[4 * i + 0] = 0x7fffffffffffffffLL, kt[4 * i + 1] = 0x7fffffffffffffffLL;
+    kt[4 * i + 2] = 0, kt[4 * i + 3] = 0;
+  }
+}
+}  // namespace tamf
+
+// In-graph per-kernel breakdown: the step is captured in a CUDA graph exactly like tamf_p_sample_chain captures it (same
+// kernels, same programmatic dependent launches), but every kernel also records, on the globaltimer every SM shares, the
+// earliest CTA entry, the earliest end of a dependency wait and the latest CTA exit.  n_steps replays run back to back;
+// the figures of the last replays are averaged.  Per kernel k (launch order): entry_us[k], ready_us[k], exit_us[k] relative
+// to the first kernel's entry of the same step; step_us = mean step period.
+extern "C" int tamf_denoiser_profile_graph(tamf_denoiser* h, float* x_io, int t_start, int n_steps, uint64_t seed,
+                                           double* entry_us, double* ready_us, double* exit_us, int cap, int* n_out,
+                                           double* step_us, void* stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  TAMF_REQUIRE(h && h->bound && h->cond_set, TAMF_E_STATE, "tamf_denoiser_profile_graph: bind + set_cond first");
+  TAMF_REQUIRE(x_io && entry_us && ready_us && exit_us && n_out && step_us, TAMF_E_BADARG,
+               "tamf_denoiser_profile_graph: null pointer");
+  TAMF_REQUIRE(n_steps >= 4 && t_start < h->K && t_start - n_steps + 1 >= 0, TAMF_E_BADARG,
+               "tamf_denoiser_profile_graph: need n_steps >= 4 steps inside the schedule");
+  const int MAXK = 128, AVG = 3;  // the last AVG steps are averaged
+  long long* kt = nullptr;
+  TAMF_CUDA_CHECK(cudaMalloc(&kt, (size_t)AVG * MAXK * 4 * sizeof(long long)));
+  cudaStream_t cap_s = nullptr;
+  TAMF_CUDA_CHECK(cudaStreamCreateWithFlags(&cap_s, cudaStreamNonBlocking));
+  cudaGraphExec_t exec[AVG] = {nullptr, nullptr, nullptr};
+  int nk = 0, rc = TAMF_OK;
+  const uint64_t before = g_launches.load();
+  for (int a = 0; a < AVG && rc == TAMF_OK; ++a) {  // one graph per averaged step: each writes its own timing slots
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(cap_s, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      long long* slot = kt + (size_t)a * MAXK * 4;
+      ktime_init_kernel<<<1, MAXK, 0, cap_s>>>(slot, MAXK);
+      const uint64_t b0 = g_launches.load();
+      rc = enqueue_step(h, x_io, h->t_dev, x_io, nullptr, nullptr, seed, cap_s, nullptr, false, /*advance=*/true, slot);
+      nk = (int)(g_launches.load() - b0);
+      e = cudaStreamEndCapture(cap_s, &g);
+    }
+    if (rc == TAMF_OK && e == cudaSuccess) e = cudaGraphInstantiate(&exec[a], g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (rc == TAMF_OK && e != cudaSuccess) {
+      set_error(std::string("tamf_denoiser_profile_graph: ") + cudaGetErrorString(e));
+      rc = TAMF_E_CUDA;
+    }
+  }
+  g_launches.store(before);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  float ms = 0.f;
+  if (rc == TAMF_OK && nk <= MAXK && nk <= cap) {
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    rc = fill_int(h->t_dev, h->B, t_start, s);
+    // warm-up replays with the product graph shape (slot 0), then the timed tail: ... AVG graphs last
+    for (int i = 0; i < n_steps && rc == TAMF_OK; ++i) {
+      const int a = (i >= n_steps - AVG) ? i - (n_steps - AVG) : 0;
+      if (i == n_steps - AVG) cudaEventRecord(e0, s);
+      if (cudaGraphLaunch(exec[a], s) != cudaSuccess) rc = TAMF_E_CUDA;
+      count_launch(nk + 1);
+    }
+    cudaEventRecord(e1, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) rc = TAMF_E_CUDA;
+    if (rc == TAMF_OK) cudaEventElapsedTime(&ms, e0, e1);
+  } else if (rc == TAMF_OK) {
+    set_error("tamf_denoiser_profile_graph: output capacity too small");
+    rc = TAMF_E_BADARG;
+  }
+  if (rc == TAMF_OK) {
+    std::vector<long long> hst((size_t)AVG * MAXK * 4);
+    if (cudaMemcpy(hst.data(), kt, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) rc = TAMF_E_CUDA;
+    for (int k = 0; k < nk && rc == TAMF_OK; ++k) {
+      double en = 0, rd = 0, ex = 0;
+      for (int a = 0; a < AVG; ++a) {
+        const long long* z = hst.data() + (size_t)a * MAXK * 4;
+        const long long t0 = z[0];  // entry of the step's first kernel
+        en += (double)(z[4 * k + 0] - t0), rd += (double)(z[4 * k + 1] - t0), ex += (double)(z[4 * k + 2] - t0);
+      }
+      entry_us[k] = en / AVG * 1e-3, ready_us[k] = rd / AVG * 1e-3, exit_us[k] = ex / AVG * 1e-3;
+    }
+    *n_out = nk;
+    *step_us = (double)ms * 1e3 / AVG;
+  }
+  for (int a = 0; a < AVG; ++a)
+    if (exec[a]) cudaGraphExecDestroy(exec[a]);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaStreamDestroy(cap_s);
+  cudaFree(kt);
+  return rc;
 }
 
 extern "C" int tamf_p_sample_chain(tamf_denoiser* h, float* x_io, int t_start, int t_end, uint64_t seed,

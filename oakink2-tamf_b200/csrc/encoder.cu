@@ -3,7 +3,7 @@
 
 #include "attn_tc.cuh"
 #include "gemm.cuh"
-#include "gemm_chain.cuh"
+#include "layer_chain.cuh"
 
 namespace tamf {
 
@@ -193,29 +193,45 @@ int EncoderStack::upload(DevPool& pool, const tamf_layer_weights* w, int d_, int
   return TAMF_OK;
 }
 
-// aux layout: [syncA | syncB | statsA | statsB | schedA | schedB | schedL], every region 256-byte aligned
+// aux layout: [counters | statistics words | schedule (with next in_proj) | schedule (last layer)], 256-byte aligned
 struct ChainLayout {
-  int tiles_m, halves, stats_words;
-  size_t off_syncA, off_syncB, off_statsA, off_statsB, off_schedA, off_schedB, off_schedL, sched_bytes, total;
+  int tiles_m, halves;
+  size_t ctr_words, stats_words, off_ctr, off_stats, off_sched, off_schedL, sched_bytes, total;
 };
 static ChainLayout chain_layout(int M, int d, int ff) {
   ChainLayout L{};
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   L.tiles_m = (M + 255) / 256;
   L.halves = d / CH_BN;
-  L.stats_words = L.tiles_m * L.halves * 2 * 128;
-  const int tiles_n2 = (ff > 3 * d ? ff : 3 * d) / CH_BN;
-  L.sched_bytes = al(((size_t)num_sms() / 2 + 1 + (size_t)L.tiles_m * (L.halves + tiles_n2)) * 4);
+  L.ctr_words = (size_t)4 * L.tiles_m + 2;
+  L.stats_words = (size_t)2 * L.tiles_m * L.halves * 2 * 4 * 128;
+  L.sched_bytes = al(((size_t)num_sms() / 2 + 1 + (size_t)L.tiles_m * (2 * L.halves + (ff + 3 * d) / CH_BN)) * 4);
   size_t o = 0;
-  L.off_syncA = o, o += al((size_t)L.tiles_m * 4);
-  L.off_syncB = o, o += al((size_t)L.tiles_m * 4);
-  L.off_statsA = o, o += al((size_t)L.stats_words * 8);
-  L.off_statsB = o, o += al((size_t)L.stats_words * 8);
-  L.off_schedA = o, o += L.sched_bytes;
-  L.off_schedB = o, o += L.sched_bytes;
+  L.off_ctr = o, o += al(L.ctr_words * 4);
+  L.off_stats = o, o += al(L.stats_words * 8);
+  L.off_sched = o, o += L.sched_bytes;
   L.off_schedL = o, o += L.sched_bytes;
   L.total = o;
   return L;
+}
+
+static LayerCosts layer_costs_from_env() {
+  // unit cost estimates in cycles (profiles/r02_*_timelines.txt), overridable for schedule experiments
+  LayerCosts c;
+  auto env_d = [](const char* k, double v) { return getenv(k) ? atof(getenv(k)) : v; };
+  c.kb = env_d("TAMF_CHAIN_KB", c.kb), c.res = env_d("TAMF_CHAIN_RES", c.res);
+  c.epi_ln = env_d("TAMF_CHAIN_EPI_LN", c.epi_ln), c.ln_ready = env_d("TAMF_CHAIN_LN_READY", c.ln_ready);
+  c.epi_gelu = env_d("TAMF_CHAIN_EPI_GELU", c.epi_gelu), c.epi_bias = env_d("TAMF_CHAIN_EPI_BIAS", c.epi_bias);
+  c.signal = env_d("TAMF_CHAIN_SIGNAL", c.signal), c.slack = env_d("TAMF_CHAIN_SLACK", c.slack);
+  return c;
+}
+
+static int upload_schedule(int* dst, const LayerSchedule& sc, size_t cap_bytes, cudaStream_t stream) {
+  TAMF_REQUIRE((size_t)(sc.pairs + 1 + sc.units.size()) * 4 <= cap_bytes, TAMF_E_BADARG, "layer schedule overflow");
+  TAMF_CUDA_CHECK(cudaMemcpyAsync(dst, sc.off.data(), (size_t)(sc.pairs + 1) * 4, cudaMemcpyHostToDevice, stream));
+  TAMF_CUDA_CHECK(cudaMemcpyAsync(dst + sc.pairs + 1, sc.units.data(), sc.units.size() * 4, cudaMemcpyHostToDevice, stream));
+  TAMF_CUDA_CHECK(cudaStreamSynchronize(stream));  // the host vectors may go out of scope
+  return TAMF_OK;
 }
 
 size_t encoder_aux_bytes(int M, int d, int ff) { return chain_layout(M, d, ff).total; }
@@ -234,7 +250,7 @@ int EncoderBuffers::make_maps(int d, int ff) {
   AttnTcMaps at;
   if ((rc = make_attn_tc_maps(&at, QKV, ATT, B, S, d))) return rc;
   tm_att_kv = at.kv, tm_att_o = at.o;
-  // ---- chain kernels ----
+  // ---- layer kernel ----
   static const bool env_chain = !(getenv("TAMF_CHAIN") && getenv("TAMF_CHAIN")[0] == '0');
   chain = env_chain && aux != nullptr;
   if (!chain) return TAMF_OK;
@@ -245,46 +261,23 @@ int EncoderBuffers::make_maps(int d, int ff) {
   if ((rc = make_tmap_2d_bf16(&tm_Xl_st, Xlo, d, M, (uint64_t)d * 2, 64, 32))) return rc;
   if ((rc = chain_identity_map(&tm_ident))) return rc;
   const ChainLayout lay = chain_layout(M, d, ff);
-  tiles_m = lay.tiles_m, halves = lay.halves, stats_words = lay.stats_words;
+  tiles_m = lay.tiles_m, halves = lay.halves;
   uint8_t* a = static_cast<uint8_t*>(aux);
-  syncA = reinterpret_cast<unsigned*>(a + lay.off_syncA);
-  syncB = reinterpret_cast<unsigned*>(a + lay.off_syncB);
-  statsA = reinterpret_cast<unsigned long long*>(a + lay.off_statsA);
-  statsB = reinterpret_cast<unsigned long long*>(a + lay.off_statsB);
-  schedA = reinterpret_cast<int*>(a + lay.off_schedA);
-  schedB = reinterpret_cast<int*>(a + lay.off_schedB);
+  ctr = reinterpret_cast<unsigned*>(a + lay.off_ctr);
+  stats = reinterpret_cast<unsigned long long*>(a + lay.off_stats);
+  sched = reinterpret_cast<int*>(a + lay.off_sched);
   schedL = reinterpret_cast<int*>(a + lay.off_schedL);
-  // unit cost estimates in cycles (profiles/r02_chain_cta_timelines.txt): 512 per 64-deep k-block of a 256 x 256 pair tile
-  // at the tensor-pipe rate; the LayerNorm epilogue is store bound (4 B per element through ~32 B/clk/SM), the GELU
-  // epilogue FMA-pipe bound.  A unit occupies its pair for max(mainloop, epilogue); the rows of a LayerNorm unit are in L2
-  // min(mainloop, epilogue) later.
-  auto env_d = [](const char* k, double v) { return getenv(k) ? atof(getenv(k)) : v; };
-  const double kb = env_d("TAMF_CHAIN_KB", 540.0), e_ln = env_d("TAMF_CHAIN_EPI_LN", 11000.0);
-  const double e_gelu = env_d("TAMF_CHAIN_EPI_GELU", 5000.0), e_bias = env_d("TAMF_CHAIN_EPI_BIAS", 4300.0);
-  auto mx = [](double x, double y) { return x > y ? x : y; };
-  auto mn = [](double x, double y) { return x < y ? x : y; };
+  const LayerCosts costs = layer_costs_from_env();
   const int slots = num_sms() / 2;
-  const double res = env_d("TAMF_CHAIN_RES", 2000.0);  // the 4 residual ring stages of a LayerNorm unit
-  const double mA = kb * d / 64 + res, mB = kb * ff / 64 + res, m2 = kb * d / 64;
-  const ChainSchedule sa = build_chain_schedule(M, d, ff, slots, mx(mA, e_ln), mn(mA, e_ln), mx(m2, e_gelu));
-  const ChainSchedule sb = build_chain_schedule(M, d, 3 * d, slots, mx(mB, e_ln), mn(mB, e_ln), mx(m2, e_bias));
-  const ChainSchedule sl = build_chain_schedule(M, d, 0, slots, mx(mB, e_ln), mn(mB, e_ln), 0.0);
-  pairsA = sa.pairs, pairsB = sb.pairs, pairsL = sl.pairs;
-  auto upload = [&](int* dst, const ChainSchedule& sc) -> int {
-    TAMF_REQUIRE((size_t)(sc.pairs + 1 + sc.units.size()) * 4 <= lay.sched_bytes, TAMF_E_BADARG, "chain schedule overflow");
-    TAMF_CUDA_CHECK(cudaMemcpy(dst, sc.off.data(), (size_t)(sc.pairs + 1) * 4, cudaMemcpyHostToDevice));
-    TAMF_CUDA_CHECK(cudaMemcpy(dst + sc.pairs + 1, sc.units.data(), sc.units.size() * 4, cudaMemcpyHostToDevice));
-    return TAMF_OK;
-  };
-  if ((rc = upload(schedA, sa)) || (rc = upload(schedB, sb)) || (rc = upload(schedL, sl))) return rc;
-  // afterwards each chain kernel resets its sibling's words
-  TAMF_CUDA_CHECK(cudaMemset(syncA, 0, (size_t)tiles_m * 4));
-  TAMF_CUDA_CHECK(cudaMemset(syncB, 0, (size_t)tiles_m * 4));
-  TAMF_CUDA_CHECK(cudaMemset(statsA, 0xFF, (size_t)stats_words * 8));
-  TAMF_CUDA_CHECK(cudaMemset(statsB, 0xFF, (size_t)stats_words * 8));
+  const LayerSchedule sc = build_layer_schedule(M, d, ff, 3 * d, slots, costs);
+  const LayerSchedule sl = build_layer_schedule(M, d, ff, 0, slots, costs);
+  pairs = sc.pairs, pairsL = sl.pairs;
+  if ((rc = upload_schedule(sched, sc, lay.sched_bytes, nullptr)) || (rc = upload_schedule(schedL, sl, lay.sched_bytes, nullptr)))
+    return rc;
+  TAMF_CUDA_CHECK(cudaMemset(ctr, 0, lay.ctr_words * 4));          // counters are monotonic from here on (epoch 0)
+  TAMF_CUDA_CHECK(cudaMemset(stats, 0xFF, lay.stats_words * 8));   // "not posted"; every reader resets its word
   return TAMF_OK;
 }
-
 
 int configure_encoder_kernels() {
   int rc;
@@ -294,78 +287,75 @@ int configure_encoder_kernels() {
   if ((rc = configure_gemm<512, EPI_RES_LN, 2>())) return rc;
   if ((rc = configure_attn_tc<64>())) return rc;
   if ((rc = configure_attn_tc<128>())) return rc;
-  if ((rc = configure_gemm_chain<CHAIN_GELU>())) return rc;
-  if ((rc = configure_gemm_chain<CHAIN_BIAS>())) return rc;
+  if ((rc = configure_layer_chain())) return rc;
   return TAMF_OK;
 }
 
-// debug only (tools/chain_trace_model.py): per-CTA timelines of the two chain kernels of one layer inside a real step
-static long long* g_dbg_trace[2] = {nullptr, nullptr};
+// debug only (tools/chain_trace_model.py): per-CTA timeline of the layer kernel of one layer inside a real step
+static long long* g_dbg_trace = nullptr;
 static int g_dbg_trace_layer = -1;
 
-// Chain form of the stack (gemm_chain.cuh): in_proj(0), then per layer  attention | out_proj+LN1 -> linear1+GELU |
-// linear2+LN2 -> in_proj of the next layer  = 1 + 3 L kernels.
+static void fill_layer_params(LayerParams& p, const EncoderStack& enc, const EncoderBuffers& buf, int l) {
+  const LayerDev& w = enc.layers[l];
+  const bool last = l + 1 == enc.L;
+  p.M = buf.M, p.d = enc.d, p.ff = enc.ff, p.n_inp = last ? 0 : 3 * enc.d;
+  p.bias[CK_LN1] = w.b_out, p.bias[CK_L1] = w.b1, p.bias[CK_LN2] = w.b2;
+  p.bias[CK_INP] = last ? nullptr : enc.layers[l + 1].b_in;
+  p.gamma[0] = w.g1, p.beta[0] = w.be1, p.gamma[1] = w.g2, p.beta[1] = w.be2;
+  const int* sc = last ? buf.schedL : buf.sched;
+  const int pairs = last ? buf.pairsL : buf.pairs;
+  p.sched_off = sc, p.sched = sc + pairs + 1;
+  p.ctr = buf.ctr, p.stats = buf.stats, p.tiles_m = buf.tiles_m;
+  p.target_ln = (unsigned)(buf.halves * 2 * GEMM_EPI_WARPS);
+  p.target_h = (unsigned)((enc.ff / CH_BN) * 2 * GEMM_EPI_WARPS);
+}
+
+// Layer-kernel form of the stack (layer_chain.cuh): in_proj(0), then per layer  attention | everything up to the next
+// layer's in_proj  = 1 + 2 L kernels.
 static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& buf, cudaStream_t s,
-                                 std::vector<cudaEvent_t>* marks) {
-  const int d = enc.d, ff = enc.ff, M = buf.M;
+                                 std::vector<cudaEvent_t>* marks, long long* ktime, int* kidx) {
+  const int d = enc.d, M = buf.M;
   int rc;
+  auto kt = [&]() -> long long* { return ktime ? ktime + 4 * ((*kidx)++) : nullptr; };
   {
     const LayerDev& w = enc.layers[0];
     GemmParams p{};
     p.M = M, p.N = 3 * d, p.K = d, p.bias = w.b_in, p.out_bf16 = buf.QKV, p.ld_bf16 = 3 * d, p.tmC = &buf.tm_QKV_st;
+    p.ktime = kt();
     if ((rc = launch_gemm<256, EPI_BIAS_BF16, 2>(buf.tm_Xb, w.tm_in, p, s))) return rc;
     mark_event(marks, s);
   }
-  ChainParams base{};
-  base.M = M, base.N1 = d;
-  base.ready_target = (unsigned)(buf.halves * 2 * GEMM_EPI_WARPS);
-  base.zero_n = buf.tiles_m, base.ones_n = buf.stats_words;
   static const int dbg = getenv("TAMF_CHAIN_DBG") ? atoi(getenv("TAMF_CHAIN_DBG")) : 0;
-  base.dbg = dbg;
   for (int l = 0; l < enc.L; ++l) {
     const LayerDev& w = enc.layers[l];
     {
       AttnTcMaps at;
       at.kv = buf.tm_att_kv, at.o = buf.tm_att_o;
-      rc = (d / enc.H == 128) ? launch_attn_tc<128>(at, buf.B, buf.S, enc.H, d, s)
-                              : launch_attn_tc<64>(at, buf.B, buf.S, enc.H, d, s);
+      long long* k = kt();
+      rc = (d / enc.H == 128) ? launch_attn_tc<128>(at, buf.B, buf.S, enc.H, d, s, nullptr, k)
+                              : launch_attn_tc<64>(at, buf.B, buf.S, enc.H, d, s, nullptr, k);
       if (rc) return rc;
       mark_event(marks, s);
     }
-    {  // A: X = LN1(X + ATT . Wo^T + b) ; H = gelu(Xb . W1^T + b)
-      ChainParams p = base;
-      p.K1 = d, p.N2 = ff, p.K2 = d;
-      p.bias1 = w.b_out, p.gamma = w.g1, p.beta = w.be1, p.bias2 = w.b1;
-      p.sched_off = buf.schedA, p.sched = buf.schedA + buf.pairsA + 1;
-      p.ready = buf.syncA, p.stats = buf.statsA, p.zero_ptr = buf.syncB, p.ones_ptr = buf.statsB;
-      if (l == g_dbg_trace_layer) p.trace = g_dbg_trace[0];
-      ChainMaps tm{&buf.tm_ATT128, &w.tm_out, &buf.tm_Xb, &buf.tm_Xlo128, &w.tm_w1, &buf.tm_H_st, &buf.tm_Xh_st,
-                   &buf.tm_Xl_st, &buf.tm_ident};
-      if ((rc = launch_gemm_chain<CHAIN_GELU>(tm, p, buf.pairsA, s))) return rc;
-      mark_event(marks, s);
-    }
-    {  // B: X = LN2(X + H . W2^T + b) ; QKV(next layer) = Xb . Win^T + b
-      const bool last = l + 1 == enc.L;
-      ChainParams p = base;
-      p.K1 = ff, p.N2 = last ? 0 : 3 * d, p.K2 = d;
-      p.bias1 = w.b2, p.gamma = w.g2, p.beta = w.be2, p.bias2 = last ? nullptr : enc.layers[l + 1].b_in;
-      const int* sc = last ? buf.schedL : buf.schedB;
-      const int pairs = last ? buf.pairsL : buf.pairsB;
-      p.sched_off = sc, p.sched = sc + pairs + 1;
-      p.ready = buf.syncB, p.stats = buf.statsB, p.zero_ptr = buf.syncA, p.ones_ptr = buf.statsA;
-      if (l == g_dbg_trace_layer) p.trace = g_dbg_trace[1];
-      ChainMaps tm{&buf.tm_H128, &w.tm_w2, &buf.tm_Xb, &buf.tm_Xlo128, last ? nullptr : &enc.layers[l + 1].tm_in,
-                   last ? nullptr : &buf.tm_QKV_st, &buf.tm_Xh_st, &buf.tm_Xl_st, &buf.tm_ident};
-      if ((rc = launch_gemm_chain<CHAIN_BIAS>(tm, p, pairs, s))) return rc;
-      mark_event(marks, s);
-    }
+    const bool last = l + 1 == enc.L;
+    LayerParams p{};
+    fill_layer_params(p, enc, buf, l);
+    p.dbg = dbg;
+    p.ktime = kt();
+    if (l == g_dbg_trace_layer) p.trace = g_dbg_trace;
+    LayerMaps tm{&buf.tm_ATT128, &w.tm_out, &buf.tm_Xb, &buf.tm_Xlo128, &w.tm_w1, &buf.tm_H_st, &buf.tm_H128, &w.tm_w2,
+                 last ? nullptr : &enc.layers[l + 1].tm_in, last ? nullptr : &buf.tm_QKV_st, &buf.tm_Xh_st, &buf.tm_Xl_st,
+                 &buf.tm_ident};
+    if ((rc = launch_layer_chain(tm, p, last ? buf.pairsL : buf.pairs, s))) return rc;
+    mark_event(marks, s);
   }
   return TAMF_OK;
 }
 
 int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStream_t s,
-                    std::vector<cudaEvent_t>* marks) {
-  if (buf.chain) return enqueue_encoder_chain(enc, buf, s, marks);
+                    std::vector<cudaEvent_t>* marks, long long* ktime, int* kidx) {
+  if (buf.chain) return enqueue_encoder_chain(enc, buf, s, marks, ktime, kidx);
+  auto kt = [&]() -> long long* { return ktime ? ktime + 4 * ((*kidx)++) : nullptr; };
   const int d = enc.d, ff = enc.ff, M = buf.M;
   int rc;
   for (int l = 0; l < enc.L; ++l) {
@@ -373,14 +363,16 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     {
       GemmParams p{};
       p.M = M, p.N = 3 * d, p.K = d, p.bias = w.b_in, p.out_bf16 = buf.QKV, p.ld_bf16 = 3 * d, p.tmC = &buf.tm_QKV_st;
+      p.ktime = kt();
       if ((rc = launch_gemm<256, EPI_BIAS_BF16, 2>(buf.tm_Xb, w.tm_in, p, s))) return rc;
       mark_event(marks, s);
     }
     {
       AttnTcMaps at;
       at.kv = buf.tm_att_kv, at.o = buf.tm_att_o;
-      rc = (d / enc.H == 128) ? launch_attn_tc<128>(at, buf.B, buf.S, enc.H, d, s)
-                              : launch_attn_tc<64>(at, buf.B, buf.S, enc.H, d, s);
+      long long* k = kt();
+      rc = (d / enc.H == 128) ? launch_attn_tc<128>(at, buf.B, buf.S, enc.H, d, s, nullptr, k)
+                              : launch_attn_tc<64>(at, buf.B, buf.S, enc.H, d, s, nullptr, k);
       if (rc) return rc;
     }
     mark_event(marks, s);
@@ -388,6 +380,7 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
       GemmParams p{};
       p.M = M, p.N = d, p.K = d, p.bias = w.b_out, p.Xlo = buf.Xlo, p.Xb = buf.Xb, p.gamma = w.g1, p.beta = w.be1;
       p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_Xlo, p.ln_rq = buf.ln_rq;
+      p.ktime = kt();
       rc = (d == 512) ? launch_gemm<512, EPI_RES_LN, 2>(buf.tm_ATT, w.tm_out, p, s)
                       : launch_gemm<256, EPI_RES_LN, 2>(buf.tm_ATT, w.tm_out, p, s);
       if (rc) return rc;
@@ -396,6 +389,7 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
     {
       GemmParams p{};
       p.M = M, p.N = ff, p.K = d, p.bias = w.b1, p.out_bf16 = buf.Hb, p.ld_bf16 = ff, p.tmC = &buf.tm_H_st;
+      p.ktime = kt();
       if ((rc = launch_gemm<256, EPI_BIAS_GELU_BF16, 2>(buf.tm_Xb, w.tm_w1, p, s))) return rc;
       mark_event(marks, s);
     }
@@ -403,6 +397,7 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
       GemmParams p{};
       p.M = M, p.N = d, p.K = ff, p.bias = w.b2, p.Xlo = buf.Xlo, p.Xb = buf.Xb, p.gamma = w.g2, p.beta = w.be2;
       p.tmC = &buf.tm_Xb_st, p.tmX = &buf.tm_Xlo, p.ln_rq = buf.ln_rq;
+      p.ktime = kt();
       rc = (d == 512) ? launch_gemm<512, EPI_RES_LN, 2>(buf.tm_H, w.tm_w2, p, s)
                       : launch_gemm<256, EPI_RES_LN, 2>(buf.tm_H, w.tm_w2, p, s);
       if (rc) return rc;
@@ -414,71 +409,86 @@ int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStre
 
 }  // namespace tamf
 
-// Debug / self-test aid (tools/chain_trace.py, tests/test_gemm_gpu.py): ONE launch of a chain kernel on caller data.
-// which: 0 = A (LN(X + a1 . w1^T) -> gelu(Xb . w2^T)), 1 = B (LN(...) -> Xb . w2^T + b2), 2 = LN only.
-extern "C" int tamf_debug_chain_trace(long long* trace_a, long long* trace_b, int layer) {
-  tamf::g_dbg_trace[0] = trace_a, tamf::g_dbg_trace[1] = trace_b;
-  tamf::g_dbg_trace_layer = (trace_a || trace_b) ? layer : -1;
+// Debug aids / self-test (tools/chain_trace_model.py, tools/layer_trace.py, tests/test_gemm_gpu.py)
+extern "C" int tamf_debug_chain_trace(long long* trace, int layer) {
+  tamf::g_dbg_trace = trace;
+  tamf::g_dbg_trace_layer = trace ? layer : -1;
   return TAMF_OK;
 }
 
-extern "C" size_t tamf_chain_aux_bytes(int M, int d, int ff) { return tamf::encoder_aux_bytes(M, d, ff); }
+extern "C" size_t tamf_layer_aux_bytes(int M, int d, int ff) { return tamf::encoder_aux_bytes(M, d, ff); }
 
-extern "C" int tamf_chain_run(int which, const uint16_t* a1, const uint16_t* w1, const float* ln_params, uint16_t* Xh,
-                              uint16_t* Xl, const uint16_t* w2, const float* b2, uint16_t* c2, int M, int d, int K1, int N2,
+// ONE launch of the layer kernel on caller data: X (two bf16 planes, in place), att [M,d], weights as nn.Linear stores
+// them (bf16), ln_params = [b_out | g1 | be1 | b2 | g2 | be2] (6 d floats), b1 [ff], b_in [3d] (n_inp = 0: no INP).
+extern "C" int tamf_layer_run(const uint16_t* att, const uint16_t* w_out, const uint16_t* w1, const uint16_t* w2,
+                              const uint16_t* w_in, const float* ln_params, const float* b1, const float* b_in,
+                              uint16_t* Xh, uint16_t* Xl, uint16_t* Hbuf, uint16_t* qkv, int M, int d, int ff, int n_inp,
                               void* aux, size_t aux_bytes, long long* trace, void* stream_) {
   using namespace tamf;
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_device();
   if (rc) return rc;
-  TAMF_REQUIRE(a1 && w1 && ln_params && Xh && Xl && aux, TAMF_E_BADARG, "tamf_chain_run: null pointer");
-  TAMF_REQUIRE(which >= 0 && which <= 2 && (d == 256 || d == 512) && K1 % 64 == 0 && N2 % 256 == 0, TAMF_E_BADARG,
-               "tamf_chain_run: bad shape");
-  if (which == 2) N2 = 0;
-  TAMF_REQUIRE(N2 == 0 || (w2 && c2), TAMF_E_BADARG, "tamf_chain_run: phase 2 needs w2 / c2");
-  const int ffmax = N2 > K1 ? N2 : K1;
-  const ChainLayout lay = chain_layout(M, d, ffmax > 3 * d ? ffmax : 3 * d);
-  TAMF_REQUIRE(aux_bytes >= lay.total, TAMF_E_BADARG, "tamf_chain_run: aux too small (tamf_chain_aux_bytes(M, d, max(K1, N2)))");
-  if ((rc = configure_gemm_chain<CHAIN_GELU>()) || (rc = configure_gemm_chain<CHAIN_BIAS>())) return rc;
-  CUtensorMap tA1, tB1, tXh, tXl, tB2, tC2, tXhs, tXls, tI;
+  TAMF_REQUIRE(att && w_out && w1 && w2 && ln_params && b1 && Xh && Xl && Hbuf && aux, TAMF_E_BADARG,
+               "tamf_layer_run: null pointer");
+  TAMF_REQUIRE((d == 256 || d == 512) && ff % 256 == 0 && ff > 0 && (n_inp == 0 || n_inp == 3 * d), TAMF_E_BADARG,
+               "tamf_layer_run: bad shape");
+  TAMF_REQUIRE(n_inp == 0 || (w_in && b_in && qkv), TAMF_E_BADARG, "tamf_layer_run: the in_proj stage needs w_in / b_in / qkv");
+  const ChainLayout lay = chain_layout(M, d, ff);
+  TAMF_REQUIRE(aux_bytes >= lay.total, TAMF_E_BADARG, "tamf_layer_run: aux too small (tamf_layer_aux_bytes)");
+  if ((rc = configure_layer_chain())) return rc;
+  CUtensorMap tATT, tWo, tXh, tXl, tW1, tHst, tH, tW2, tWin, tQst, tXhs, tXls, tI;
   const uint32_t wbox = (uint32_t)gemm_b_box_rows(256, 2);
-  if ((rc = make_tmap_2d_bf16(&tA1, a1, K1, M, (uint64_t)K1 * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tB1, w1, K1, d, (uint64_t)K1 * 2, 64, wbox))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tXh, Xh, d, M, (uint64_t)d * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tXl, Xl, d, M, (uint64_t)d * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tXhs, Xh, d, M, (uint64_t)d * 2, 64, 32))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tXls, Xl, d, M, (uint64_t)d * 2, 64, 32))) return rc;
+  const uint64_t pd = (uint64_t)d * 2, pf = (uint64_t)ff * 2;
+  if ((rc = make_tmap_2d_bf16(&tATT, att, d, M, pd, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tWo, w_out, d, d, pd, 64, wbox))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tXh, Xh, d, M, pd, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tXl, Xl, d, M, pd, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tW1, w1, d, ff, pd, 64, wbox))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tHst, Hbuf, ff, M, pf, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tH, Hbuf, ff, M, pf, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tW2, w2, ff, d, pf, 64, wbox))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tXhs, Xh, d, M, pd, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tXls, Xl, d, M, pd, 64, 32))) return rc;
   if ((rc = chain_identity_map(&tI))) return rc;
-  if (N2) {
-    if ((rc = make_tmap_2d_bf16(&tB2, w2, d, N2, (uint64_t)d * 2, 64, wbox))) return rc;
-    if ((rc = make_tmap_2d_bf16(&tC2, c2, N2, M, (uint64_t)N2 * 2, 64, 32))) return rc;
+  if (n_inp) {
+    if ((rc = make_tmap_2d_bf16(&tWin, w_in, d, n_inp, pd, 64, wbox))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tQst, qkv, n_inp, M, (uint64_t)n_inp * 2, 64, 32))) return rc;
   }
-  auto env_d = [](const char* k, double v) { return getenv(k) ? atof(getenv(k)) : v; };
-  const double kb = env_d("TAMF_CHAIN_KB", 540.0), e_ln = env_d("TAMF_CHAIN_EPI_LN", 11000.0);
-  const double e2 = which == 0 ? env_d("TAMF_CHAIN_EPI_GELU", 5000.0) : env_d("TAMF_CHAIN_EPI_BIAS", 4300.0);
-  const double m1 = kb * K1 / 64 + env_d("TAMF_CHAIN_RES", 2000.0), m2 = kb * d / 64;
-  const ChainSchedule sc = build_chain_schedule(M, d, N2, num_sms() / 2, m1 > e_ln ? m1 : e_ln, m1 < e_ln ? m1 : e_ln,
-                                                m2 > e2 ? m2 : e2);
+  const LayerSchedule sc = build_layer_schedule(M, d, ff, n_inp, num_sms() / 2, layer_costs_from_env());
   uint8_t* a = static_cast<uint8_t*>(aux);
-  int* sched = reinterpret_cast<int*>(a + lay.off_schedA);
-  TAMF_REQUIRE((size_t)(sc.pairs + 1 + sc.units.size()) * 4 <= lay.sched_bytes, TAMF_E_BADARG, "chain schedule overflow");
-  TAMF_CUDA_CHECK(cudaMemcpyAsync(sched, sc.off.data(), (size_t)(sc.pairs + 1) * 4, cudaMemcpyHostToDevice, stream));
-  TAMF_CUDA_CHECK(cudaMemcpyAsync(sched + sc.pairs + 1, sc.units.data(), sc.units.size() * 4, cudaMemcpyHostToDevice, stream));
-  TAMF_CUDA_CHECK(cudaStreamSynchronize(stream));  // the host vectors go out of scope
-  unsigned* sync = reinterpret_cast<unsigned*>(a + lay.off_syncA);
-  unsigned long long* stats = reinterpret_cast<unsigned long long*>(a + lay.off_statsA);
-  TAMF_CUDA_CHECK(cudaMemsetAsync(sync, 0, (size_t)lay.tiles_m * 4, stream));
-  TAMF_CUDA_CHECK(cudaMemsetAsync(stats, 0xFF, (size_t)lay.stats_words * 8, stream));
-  ChainParams p{};
-  p.M = M, p.N1 = d, p.K1 = K1, p.N2 = N2, p.K2 = d;
-  p.bias1 = ln_params, p.gamma = ln_params + d, p.beta = ln_params + 2 * d, p.bias2 = b2;
+  int* sched = reinterpret_cast<int*>(a + lay.off_sched);
+  if ((rc = upload_schedule(sched, sc, lay.sched_bytes, stream))) return rc;
+  unsigned* ctr = reinterpret_cast<unsigned*>(a + lay.off_ctr);
+  unsigned long long* stats = reinterpret_cast<unsigned long long*>(a + lay.off_stats);
+  TAMF_CUDA_CHECK(cudaMemsetAsync(ctr, 0, lay.ctr_words * 4, stream));
+  TAMF_CUDA_CHECK(cudaMemsetAsync(stats, 0xFF, lay.stats_words * 8, stream));
+  LayerParams p{};
+  p.M = M, p.d = d, p.ff = ff, p.n_inp = n_inp;
+  p.bias[CK_LN1] = ln_params, p.gamma[0] = ln_params + d, p.beta[0] = ln_params + 2 * d;
+  p.bias[CK_LN2] = ln_params + 3 * d, p.gamma[1] = ln_params + 4 * d, p.beta[1] = ln_params + 5 * d;
+  p.bias[CK_L1] = b1, p.bias[CK_INP] = b_in;
   p.sched_off = sched, p.sched = sched + sc.pairs + 1;
-  p.ready = sync, p.stats = stats;
-  p.ready_target = (unsigned)(lay.halves * 2 * GEMM_EPI_WARPS);
-  p.zero_ptr = reinterpret_cast<unsigned*>(a + lay.off_syncB), p.zero_n = lay.tiles_m;
-  p.ones_ptr = reinterpret_cast<unsigned long long*>(a + lay.off_statsB), p.ones_n = lay.stats_words;
+  p.ctr = ctr, p.stats = stats, p.tiles_m = lay.tiles_m;
+  p.target_ln = (unsigned)(lay.halves * 2 * GEMM_EPI_WARPS), p.target_h = (unsigned)((ff / CH_BN) * 2 * GEMM_EPI_WARPS);
   p.trace = trace;
-  ChainMaps tm{&tA1, &tB1, &tXh, &tXl, N2 ? &tB2 : nullptr, N2 ? &tC2 : nullptr, &tXhs, &tXls, &tI};
-  return which == 0 ? launch_gemm_chain<CHAIN_GELU>(tm, p, sc.pairs, stream)
-                    : launch_gemm_chain<CHAIN_BIAS>(tm, p, sc.pairs, stream);
+  LayerMaps tm{&tATT, &tWo, &tXh, &tXl, &tW1, &tHst, &tH, &tW2, n_inp ? &tWin : nullptr, n_inp ? &tQst : nullptr, &tXhs,
+               &tXls, &tI};
+  return launch_layer_chain(tm, p, sc.pairs, stream);
+}
+
+// Host-only: the static schedule the layer kernel would run for an [M, d] problem on `slots` CTA pairs (no GPU needed;
+// tests/test_host_logic.py checks coverage, duo placement and the global topological order).  off_out [slots + 1],
+// units_out [cap] unit codes kind << 28 | row tile << 8 | column tile; returns the pair count (< 0: error).
+extern "C" int tamf_layer_schedule(int M, int d, int ff, int n_inp, int slots, int* off_out, int* units_out, int cap,
+                                   double* makespan_out) {
+  using namespace tamf;
+  TAMF_REQUIRE(M > 0 && (d == 256 || d == 512) && ff > 0 && ff % 256 == 0 && n_inp % 256 == 0 && slots >= 1 && off_out &&
+                   units_out,
+               TAMF_E_BADARG, "tamf_layer_schedule: bad argument");
+  const LayerSchedule sc = build_layer_schedule(M, d, ff, n_inp, slots, layer_costs_from_env());
+  TAMF_REQUIRE((int)sc.units.size() <= cap, TAMF_E_BADARG, "tamf_layer_schedule: units_out too small");
+  for (int i = 0; i <= sc.pairs; ++i) off_out[i] = sc.off[i];
+  for (size_t i = 0; i < sc.units.size(); ++i) units_out[i] = sc.units[i];
+  if (makespan_out) *makespan_out = sc.makespan;
+  return sc.pairs;
 }

@@ -54,26 +54,27 @@ struct EncoderBuffers {
   CUtensorMap tm_QKV_st, tm_H_st;               // bf16 epilogue stores, box {64, 32}
   CUtensorMap tm_Xb_st, tm_Xlo;                 // LayerNorm epilogue: Xb / Xlo residual load + store, box {32, ln_rq} bf16
   CUtensorMap tm_att_kv, tm_att_o;    // attention: [B][S][3d] views of QKV (K/V box, Q box), [B][S][d] view of ATT
-  // ---- chain kernels (gemm_chain.cuh): out_proj+LN1 -> linear1+GELU and linear2+LN2 -> next in_proj ----
+  // ---- layer kernel (layer_chain.cuh): out_proj+LN1 -> linear1+GELU -> linear2+LN2 -> next in_proj in one launch ----
   bool chain = false;                 // TAMF_CHAIN=0 keeps the five-kernel layer of round 1 (A/B comparisons)
-  void* aux = nullptr;                // caller-owned (workspace): sync words, row statistics, schedules
-  CUtensorMap tm_ATT128, tm_H128;     // phase-1 A operands, box {64, 128}
+  void* aux = nullptr;                // caller-owned (workspace): counters, row statistics, schedules
+  CUtensorMap tm_ATT128, tm_H128;     // A operands of LN1 / LN2, box {64, 128}
   CUtensorMap tm_Xlo128;              // low residual plane, box {64, 128} (the high plane is tm_Xb)
   CUtensorMap tm_Xh_st, tm_Xl_st;     // residual planes, box {64, 32}: LayerNorm result stores
-  CUtensorMap tm_ident;               // 64 x 64 identity (gemm_chain.cuh chain_identity_map)
-  unsigned *syncA = nullptr, *syncB = nullptr;  // ready counters [tiles_m] of kernel A / B
-  unsigned long long *statsA = nullptr, *statsB = nullptr;  // row statistics words [tiles_m * halves * 2 * 128]
-  int tiles_m = 0, halves = 0, stats_words = 0;
-  int *schedA = nullptr, *schedB = nullptr, *schedL = nullptr;  // [pairs + 1 offsets | unit codes]
-  int pairsA = 0, pairsB = 0, pairsL = 0;
+  CUtensorMap tm_ident;               // 64 x 64 identity (layer_chain.cuh chain_identity_map)
+  unsigned* ctr = nullptr;            // [4][tiles_m] + done + epoch
+  unsigned long long* stats = nullptr;  // [2][tiles_m][halves][2][4][128] row statistics words
+  int tiles_m = 0, halves = 0;
+  int *sched = nullptr, *schedL = nullptr;  // [pairs + 1 offsets | unit codes]: with / without the next in_proj
+  int pairs = 0, pairsL = 0;
   int make_maps(int d, int ff);
 };
 // bytes of EncoderBuffers::aux for an [M, d] problem (256-byte multiple)
 size_t encoder_aux_bytes(int M, int d, int ff);
 
 // Enqueue all L layers on `s`.  `marks` (profiling only): an event is recorded after every kernel.
+// `ktime` (profiling only): in-graph timing slots, 4 int64 per kernel in launch order starting at slot *kidx.
 int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStream_t s,
-                    std::vector<cudaEvent_t>* marks);
+                    std::vector<cudaEvent_t>* marks, long long* ktime = nullptr, int* kidx = nullptr);
 int configure_encoder_kernels();  // cudaFuncSetAttribute for every instantiation used above (once per process)
 
 // ---- small fp32 helpers (conditioning path, once per sample) ----

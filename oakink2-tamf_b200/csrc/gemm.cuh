@@ -90,6 +90,7 @@ struct GemmParams {
   const CUtensorMap* tmX;
   // debug only (tools/gemm_trace.py): per-CTA event timestamps, [grid][GEMM_TRACE_SLOTS] clock64 values; null in product
   long long* trace;
+  long long* ktime;  // debug only: in-graph timing slots of this launch (common.cuh ktime_*); null in product
   int dbg;  // debug only: 1 skip global stores, 2 skip staging, 4 skip the whole epilogue body (bf16 epilogues),
             // 16 stop streaming W after the first ring fill (probe: the mainloop rate does not change, so TMA writes
             // into shared memory are not what bounds it)
@@ -304,7 +305,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int first_tile = (blockIdx.x / CG) * per_pair;
   const int last_tile = min(num_tiles, first_tile + per_pair);
 
-  if (threadIdx.x == 0) GEMM_TRACE(0);
+  if (threadIdx.x == 0) {
+    GEMM_TRACE(0);
+    ktime_entry(p.ktime);
+  }
   if (warp == PW && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -354,7 +358,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (threadIdx.x == 0) GEMM_TRACE(1);
   pdl_launch_dependents();  // the next kernel may run its own prologue on SMs this grid has already left
   pdl_wait();               // everything the previous kernel wrote is visible from here on
-  if (threadIdx.x == 0) GEMM_TRACE(2);
+  if (threadIdx.x == 0) {
+    GEMM_TRACE(2);
+    ktime_ready(p.ktime);
+  }
 
   if (warp == PW) {
     // ===================== TMA producer (both CTAs of a pair) =====================
@@ -901,7 +908,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer may still signal our barriers / TMEM
-  if (threadIdx.x == 0) GEMM_TRACE(3);
+  if (threadIdx.x == 0) {
+    GEMM_TRACE(3);
+    ktime_exit(p.ktime);
+  }
   if (warp == PW + 1) {
     tc_fence_after();
     if constexpr (CG == 2)

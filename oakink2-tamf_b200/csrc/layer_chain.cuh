@@ -1,0 +1,876 @@
+// layer_chain.cuh -- everything between two attention kernels of the encoder stack in ONE persistent tcgen05 kernel:
+//
+//   LN1   X = LayerNorm(X + ATT . Wo^T + b)          out_proj + residual + norm1      (eps 1e-5, biased variance)
+//   L1    H = gelu(Xb . W1^T + b)                    linear1 + exact-erf GELU
+//   LN2   X = LayerNorm(X + H . W2^T + b)            linear2 + residual + norm2
+//   INP   QKV = Xb . Win'^T + b'                     in_proj of the NEXT layer (absent after the last layer)
+//
+// Reference semantics: nn.TransformerEncoderLayer, post-norm (interaction_segment_mdm.py:63-70; segment_refine_model.py
+// :88-95).  Round 1 ran these as four kernels.  M = 10 560 token rows are 41.25 row tiles of 256: an N = 512 GEMM has 84
+// pair tiles for 74 CTA pairs (two rounds, the second 14 % full), and a LayerNorm epilogue that needs the whole 512-wide
+// row filled TMEM (no overlap with a mainloop) while 84 SMs carried all its stores: 49 k cycles for 18 k of balanced
+// tensor work (profiles/r01_gemm_cta_timelines.txt).  Here
+//   * every unit of work is a 256 x 256 tile of a CTA pair (tcgen05.mma.cta_group::2, M = 256, N = 256), accumulators
+//     double-buffered in TMEM, so the epilogue of unit i overlaps the mainloop of unit i + 1 for EVERY epilogue;
+//   * the residual is added BY THE TENSOR CORE: after the K loop of a LayerNorm unit, four more ring stages multiply the
+//     unit's own 256 x 256 block of the two residual planes (Xb, Xlo) with a 64 x 64 identity that stays in shared
+//     memory (M = 256, N = 64, K = 64 per 64-column block and plane: products with 1.0 are exact, the accumulation is
+//     fp32), so the epilogue never loads the residual: no small-box TMA loads (one row per ~2 cycles of the SM's TMA unit
+//     whatever its length -- they delayed the mainloop's own loads), no staging traffic;
+//   * a 512-wide LayerNorm row is computed by TWO pairs (column halves, pairs 2k and 2k + 1): each keeps its 128 x 256
+//     slab of y = acc + b in REGISTERS (64 per thread), the halves swap per-row (sum, sum of squares) through L2 as one
+//     64-bit word per row that is its own flag (no fences: a gpu-scope fence costs 1.5 - 3 k cycles), all 148 SMs store;
+//   * the four stages form a dependency chain PER ROW TILE (LN1 -> L1 -> LN2 -> INP) and row tiles are independent, so a
+//     host-built static schedule (list scheduling of the DAG on a two-resource model of a pair: tensor pipe + epilogue
+//     warps) interleaves the units of different row tiles: the ~10 k cycles between the last MMA of a LayerNorm unit and
+//     the moment its rows are in L2 are filled with other row tiles' work instead of idling every SM twice per layer.
+//     A unit waits for a per-row-tile counter that the producing epilogue warps bump after their TMA stores have
+//     COMPLETED (relaxed update after cp.async.bulk.wait_group: the rows are in L2, where TMA loads read; the waiting
+//     scout warp acquires).  Every pair's list is a subsequence of ONE global topological order and all CTAs of the
+//     grid are co-resident (grid <= SM count, 1 CTA / SM), so the schedule cannot deadlock; every spin is bounded (trap).
+//   * self-contained sync state: a statistics word is reset by its single reader; the counters are monotonic and compared
+//     against (epoch + 1) x target, the epoch is bumped by the last CTA of every launch.
+#pragma once
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <type_traits>
+#include <vector>
+
+#include "gemm.cuh"
+
+namespace tamf {
+
+enum ChainKind { CK_LN1 = 0, CK_L1 = 1, CK_LN2 = 2, CK_INP = 3 };
+
+struct LayerParams {
+  int M, d, ff, n_inp;                // n_inp = 3 d, or 0 when there is no next layer
+  const float* bias[4];               // LN1: out_proj bias [d] | L1: linear1 bias [ff] | LN2: linear2 bias [d] | INP: [3d]
+  const float *gamma[2], *beta[2];    // norm1, norm2 [d]
+  const int* sched_off;               // [pairs + 1]
+  const int* sched;                   // unit codes: kind << 28 | row tile << 8 | column tile
+  // counters [4][tiles_m] + [2]: 0 LN1 high plane stored | 1 LN1 low plane stored | 2 H tiles stored | 3 LN2 high plane
+  // stored (each counts epilogue warps, MONOTONIC over launches: a launch waits for (epoch + 1) x target, compared
+  // modulo 2^32); then the number of CTAs of the running launch that have finished, and the epoch (bumped by the last
+  // CTA of every launch).  Nothing is ever reset, so a counter update still in flight when a launch ends is harmless.
+  unsigned* ctr;
+  int tiles_m;
+  unsigned target_ln, target_h;       // halves * 32 warps | (ff / 256) * 32 warps
+  // statistics words [2 LN][tiles_m][halves][2 ranks][4 reader copies][128 rows]: (sum | sum of squares << 32) over the
+  // CTA's 256 columns of a row; all-ones = not posted (the word is its own flag; its reader resets it)
+  unsigned long long* stats;
+  long long* trace;                   // debug only: [grid][GEMM_TRACE_SLOTS] clock64 stamps
+  long long* ktime;                   // debug only: in-graph timing slots of this launch (common.cuh ktime_*)
+  int dbg;
+};
+
+// 20 warps = 5 warpgroups: 16 epilogue warps, then one warpgroup with the TMA producer (16), the MMA issuer (17), the
+// dependency scout (18) and an idle warp, so that register reallocation (setmaxnreg) always involves whole warpgroups.
+constexpr int CH_THREADS = GEMM_EPI_THREADS + 128;
+constexpr int CH_STAGES = 4;
+constexpr int CH_BN = 256;
+constexpr int CH_A_BYTES = GEMM_BM * 64 * 2;       // 128 rows x 64 k
+constexpr int CH_B_BYTES = (CH_BN / 2) * 64 * 2;   // this CTA's half of the 256 W rows
+constexpr int CH_STAGE_BYTES = CH_A_BYTES + CH_B_BYTES;
+constexpr int CH_PIPE_BYTES = CH_STAGES * CH_STAGE_BYTES;
+constexpr int CH_STG_BYTES = GEMM_EPI_WARPS * GEMM_STG_WARP;
+constexpr int CH_IDENT_BYTES = 32 * 128;  // this CTA's 32 rows of the 64 x 64 bf16 identity (K-major, 128-byte swizzle)
+constexpr int CH_RES_KB = 4;              // residual ring stages of a LayerNorm unit: 2 planes x 2 stages, each holding
+                                          // TWO 64-column blocks (A slot, B slot) -- the ring is latency bound per stage
+constexpr int CH_CTRL_BYTES = 1024;
+// [2 LN][bias | gamma | beta] (256 floats each) | per-warp bias slice of the running L1 / INP tile [16][64] | row
+// statistics [2 buffers][sum, sq][4 column quarters][128 rows]
+constexpr int CH_PARAM_BYTES = 6 * CH_BN * 4 + GEMM_EPI_WARPS * 64 * 4 + 2 * 2 * 4 * 128 * 4;
+constexpr int CH_SMEM_BYTES = 1024 + CH_PIPE_BYTES + CH_STG_BYTES + CH_IDENT_BYTES + CH_CTRL_BYTES + CH_PARAM_BYTES;
+static_assert(CH_SMEM_BYTES <= GEMM_SMEM_MAX, "shared memory budget (227 KB) exceeded");
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Bounded mbarrier wait without printf (a call site keeps many registers alive around it; the trap alone reports the
+// protocol bug as a CUDA error).
+__device__ __forceinline__ void mbar_wait_q(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// Lane 0 polls `*flag >= target` (modulo 2^32; acquire, gpu scope) with a bounded spin; the warp leaves together.
+__device__ __forceinline__ void chain_wait_ge(const unsigned* flag, unsigned target) {
+  if (lane_id() == 0) {
+    if ((int)(ld_acquire_gpu(flag) - target) < 0) {
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_gpu(flag) - target) < 0) {
+        __nanosleep(40);
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ long long chain_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return (long long)t;
+}
+#define CHAIN_TRACE_NS(slot)                                                                                     \
+  do {                                                                                                           \
+    if (p.trace) p.trace[(size_t)blockIdx.x * GEMM_TRACE_SLOTS + (slot)] = chain_globaltimer();                  \
+  } while (0)
+#define CHAIN_TRACE(slot)                                                                                        \
+  do {                                                                                                           \
+    if (p.trace && (slot) < GEMM_TRACE_SLOTS) p.trace[(size_t)blockIdx.x * GEMM_TRACE_SLOTS + (slot)] = clock64(); \
+  } while (0)
+
+// Tensor maps.  tmATT / tmH / tmXh / tmXl: A operands [M, K] with box {64, 128} (tmXh = Xb is the A operand of L1 and INP
+// AND the high residual plane, tmXl = Xlo the low one); tmWo / tmW1 / tmW2 / tmWin: weights [N, K], box {64, 128};
+// tmHst / tmQst: bf16 outputs H / QKV, box {64, 32}; tmXh_st / tmXl_st: the residual planes with box {64, 32};
+// tmI: the 64 x 64 identity, box {64, 32}.
+__global__ void __launch_bounds__(CH_THREADS, 1)
+    layer_chain_kernel(const __grid_constant__ CUtensorMap tmATT, const __grid_constant__ CUtensorMap tmWo,
+                       const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                       const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmHst,
+                       const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW2,
+                       const __grid_constant__ CUtensorMap tmWin, const __grid_constant__ CUtensorMap tmQst,
+                       const __grid_constant__ CUtensorMap tmXh_st, const __grid_constant__ CUtensorMap tmXl_st,
+                       const __grid_constant__ CUtensorMap tmI, const LayerParams p) {
+  constexpr int STAGES = CH_STAGES, PW = GEMM_EPI_WARPS, PT = GEMM_EPI_THREADS, BN = CH_BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;  // identical in both CTAs of a pair
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * CH_A_BYTES;
+  uint8_t* s_stage = smem + CH_PIPE_BYTES;
+  uint8_t* s_ident = s_stage + CH_STG_BYTES;
+  uint8_t* ctrl = s_ident + CH_IDENT_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);  // [STAGES] (the leader's copy is the live one)
+  uint64_t* empty_bar = full_bar + STAGES;                  // [STAGES]
+  uint64_t* tfull_bar = empty_bar + STAGES;                 // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                     // [2]      (the leader's copy is the live one)
+  uint64_t* ident_bar = tempty_bar + 2;                     // [1]      identity tile landed (leader's copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_bar + 1);
+  uint32_t* s_dep = tmem_slot + 1;  // units whose dependencies the scout warp has seen satisfied
+  float* s_ln = reinterpret_cast<float*>(ctrl + CH_CTRL_BYTES);  // [2 LN][bias | gamma | beta][256]
+  float* s_bias2 = s_ln + 6 * BN;           // [16 warps][64]
+  float* s_stat = s_bias2 + PW * 64;        // [2 buffers][sum, sq][4 column quarters][128 rows]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader of the pair
+  const int pair = blockIdx.x >> 1;
+  const int halves = p.d / BN;
+  const int tiles_m = p.tiles_m;
+  const int u_begin = p.sched_off[pair], u_end = p.sched_off[pair + 1];  // host data (written at bind time)
+
+  if (threadIdx.x == 0) {
+    CHAIN_TRACE(0);
+    ktime_entry(p.ktime);
+  }
+  if (warp == PW && lane == 0) {
+    tma_prefetch_desc(&tmATT);
+    tma_prefetch_desc(&tmWo);
+    tma_prefetch_desc(&tmXh);
+    tma_prefetch_desc(&tmXl);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmHst);
+    tma_prefetch_desc(&tmH);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmXh_st);
+    tma_prefetch_desc(&tmXl_st);
+    tma_prefetch_desc(&tmI);
+    if (p.n_inp > 0) {
+      tma_prefetch_desc(&tmWin);
+      tma_prefetch_desc(&tmQst);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);  // the leader's arrive.expect_tx covers the bytes of BOTH CTAs' loads
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], PW * 2);  // one elected lane per epilogue warp of both CTAs
+    }
+    mbar_init(ident_bar, 1);
+    *s_dep = 0u;
+    fence_mbar_init();
+  }
+  if (warp == PW + 1) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == PW) {  // the identity tile (constant data): this CTA's 32 rows, credited to the leader's barrier
+    if (elect_one()) {
+      if (rank == 0) mbar_arrive_expect_tx(ident_bar, 2 * CH_IDENT_BYTES);
+      tma_load_2d_2sm(s_ident, &tmI, mapa_cluster(smem_u32(ident_bar), 0), 0, (int)rank * 32);
+    }
+    __syncwarp();
+  }
+  if (threadIdx.x == 0) CHAIN_TRACE(1);
+  pdl_launch_dependents();
+  pdl_wait();  // everything the previous kernels wrote (activations, the cleared sync words) is visible from here on
+  if (threadIdx.x == 0) {
+    CHAIN_TRACE(2);
+    CHAIN_TRACE_NS(56);  // globaltimer (ns) when the dependency wait ended: the common time base across SMs
+    ktime_ready(p.ktime);
+  }
+
+  // Registers: the block is allocated 20 warps x 96.  The producer / MMA / scout warpgroup gives up 64 per thread
+  // (128 x 64 = 8192 go back to the CTA's pool), the four epilogue warpgroups take 16 more each (512 x 16 = 8192): the
+  // LayerNorm epilogue keeps 64 accumulator values per thread over two passes.  Each setmaxnreg dominates exactly one
+  // role's code, so ptxas allocates every role under its own limit.
+  if (warp >= PW) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+   if (warp == PW) {
+    // ===================== TMA producer (both CTAs of the pair) =====================
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    const uint32_t full_leader = mapa_cluster(smem_u32(&full_bar[0]), 0);
+    for (int ui = u_begin; ui < u_end; ++ui, ++it) {
+      const int code = p.sched[ui];
+      const int kind = code >> 28, m = (code >> 8) & 0xFFFFF, n = code & 0xFF;
+      const int m0 = m * 256 + (int)rank * GEMM_BM, n0 = n * BN;
+      const CUtensorMap* ta = kind == CK_LN1 ? &tmATT : (kind == CK_LN2 ? &tmH : &tmXh);
+      const CUtensorMap* tb = kind == CK_LN1 ? &tmWo : (kind == CK_L1 ? &tmW1 : (kind == CK_LN2 ? &tmW2 : &tmWin));
+      const int num_kb = (kind == CK_LN2 ? p.ff : p.d) / 64;
+      const int total_kb = num_kb + ((kind & 1) ? 0 : CH_RES_KB);
+      if (kind != CK_LN1) {  // in-kernel dependencies: the scout warp has seen the counters of this unit
+        uint32_t seen;
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_dep)) : "memory");
+        if (seen < (uint32_t)(it + 1)) {
+          const long long t0 = clock64();
+          do {
+            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_dep)) : "memory");
+            if (clock64() - t0 > 4000000000LL) __trap();
+          } while (seen < (uint32_t)(it + 1));
+        }
+      }
+      if (lane == 0) CHAIN_TRACE(4 + 6 * it);
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait_q(&empty_bar[stage], phase ^ 1u);
+        uint8_t* a_dst = sA + stage * CH_A_BYTES;
+        uint8_t* b_dst = sB + stage * CH_B_BYTES;
+        const uint32_t bar = full_leader + stage * 8;
+        if (kb < num_kb) {
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * CH_STAGE_BYTES);
+            tma_load_2d_2sm(a_dst, ta, bar, kb * 64, m0);
+            tma_load_2d_2sm(b_dst, tb, bar, kb * 64, n0 + (int)rank * (BN / 2));
+          }
+        } else {  // residual stage: 128 rows x two 64-column blocks of plane (rb / 2) at columns n0 + 128 (rb % 2)
+          const int rb = kb - num_kb;
+          const CUtensorMap* tx = (rb >> 1) ? &tmXl : &tmXh;
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * CH_STAGE_BYTES);
+            tma_load_2d_2sm(a_dst, tx, bar, n0 + 128 * (rb & 1), m0);
+            tma_load_2d_2sm(b_dst, tx, bar, n0 + 128 * (rb & 1) + 64, m0);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) stage = 0, phase ^= 1u;
+      }
+      if (lane == 0) CHAIN_TRACE(5 + 6 * it);
+    }
+   } else if (warp == PW + 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * 2, BN);
+      constexpr uint32_t idesc_res = umma_idesc_bf16(GEMM_BM * 2, 64);
+      const uint32_t i_addr = smem_u32(s_ident);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      bool ident_ready = false;
+      int it = 0;
+      for (int ui = u_begin; ui < u_end; ++ui, ++it) {
+        const int code = p.sched[ui];
+        const int kind = code >> 28;
+        const int num_kb = (kind == CK_LN2 ? p.ff : p.d) / 64;
+        const int total_kb = num_kb + ((kind & 1) ? 0 : CH_RES_KB);
+        if (!(kind & 1) && !ident_ready) {
+          mbar_wait_q(ident_bar, 0);
+          ident_ready = true;
+        }
+        mbar_wait_q(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait_q(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0 && kb == 0) CHAIN_TRACE(6 + 6 * it);
+          const uint32_t a_addr = smem_u32(sA + stage * CH_A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * CH_B_BYTES);
+          if (kb < num_kb) {
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_2sm(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                              (kb | k) ? 1u : 0u);
+              umma_commit_2sm(&empty_bar[stage]);  // ring slot reusable in both CTAs once these MMAs have read it
+              if (kb == total_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
+            }
+          } else {  // acc[:, 64 j .. 64 j + 63] += X_plane block j . I64 for the stage's two blocks
+            const uint32_t dj = d_tmem + 128u * (uint32_t)((kb - num_kb) & 1);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_2sm(dj, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(i_addr + k * 32), idesc_res, 1u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_2sm(dj + 64u, umma_desc_k_sw128(b_addr + k * 32), umma_desc_k_sw128(i_addr + k * 32), idesc_res, 1u);
+              umma_commit_2sm(&empty_bar[stage]);
+              if (kb == total_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) stage = 0, phase ^= 1u;
+        }
+        if (lane == 0) CHAIN_TRACE(7 + 6 * it);
+        if (++acc == 2) acc = 0, acc_phase ^= 1u;
+      }
+    }
+   } else if (warp == PW + 2) {
+    // ===================== dependency scout =====================
+    // Walks the unit list ahead of the producer: waits until the inputs of the next unit are in L2 (acquire on the row
+    // tile's counters) and publishes the number of cleared units in shared memory.  The producer only reads that word:
+    // polling and fencing in the producer itself drained the ring at every unit boundary (+2 k cycles per tile,
+    // measured).  No proxy fence: a counter is bumped only after the TMA stores have COMPLETED in L2, which is where the
+    // producer's TMA loads read (no L1 in that path, nothing can be stale).
+    const unsigned epoch1 = p.ctr[4 * tiles_m + 1] + 1u;  // written by the last CTA of the previous launch
+    const unsigned t_ln = epoch1 * p.target_ln, t_h = epoch1 * p.target_h;
+    int it = 0;
+    for (int ui = u_begin; ui < u_end; ++ui, ++it) {
+      const int code = p.sched[ui];
+      const int kind = code >> 28, m = (code >> 8) & 0xFFFFF;
+      if (kind == CK_L1) {
+        chain_wait_ge(p.ctr + 0 * tiles_m + m, t_ln);  // LN1 high plane of the row tile
+      } else if (kind == CK_LN2) {
+        chain_wait_ge(p.ctr + 2 * tiles_m + m, t_h);   // every H tile of the row tile
+        chain_wait_ge(p.ctr + 1 * tiles_m + m, t_ln);  // LN1 low plane (the residual of this unit)
+      } else if (kind == CK_INP) {
+        chain_wait_ge(p.ctr + 3 * tiles_m + m, t_ln);  // LN2 high plane
+      }
+      if (kind != CK_LN1 && lane == 0 && p.trace && p.trace[(size_t)blockIdx.x * GEMM_TRACE_SLOTS + 54] == 0)
+        CHAIN_TRACE_NS(54);
+      if (lane == 0)
+        asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(s_dep)), "r"((uint32_t)(it + 1)) : "memory");
+      __syncwarp();
+    }
+   }
+  } else {
+    // ===================== epilogue (warps 0..15, both CTAs) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // LayerNorm parameters of this pair's column half for both norms (weights, constant over the chain).  LayerNorm unit
+    // (row tile, half h) always runs on a pair with pair % halves == h (host schedule).
+    {
+      const int c0 = (pair % halves) * BN;
+      for (int i = threadIdx.x; i < BN; i += PT) {
+#pragma unroll
+        for (int ln = 0; ln < 2; ++ln) {
+          const float* b = p.bias[ln ? CK_LN2 : CK_LN1];
+          s_ln[(ln * 3 + 0) * BN + i] = b ? b[c0 + i] : 0.f;
+          s_ln[(ln * 3 + 1) * BN + i] = p.gamma[ln][c0 + i];
+          s_ln[(ln * 3 + 2) * BN + i] = p.beta[ln][c0 + i];
+        }
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+    const int lq = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter (64 columns)
+    const int row_in_tile = lq * 32 + lane;
+    const uint32_t tempty_leader = mapa_cluster(smem_u32(&tempty_bar[0]), 0);
+    const uint32_t wst = smem_u32(s_stage) + warp * GEMM_STG_WARP;
+    const int cl = cq * 64;  // first column of this warp's slab inside the 256-column tile
+    uint32_t acc = 0, acc_phase = 0, ln_count = 0;
+    int staged_key = -1;
+    unsigned* pending = nullptr;  // counter to bump once this warp's TMA stores in flight have completed
+    // A warp never blocks while it owes a signal: the signal is flushed before any wait that may depend on it.
+    auto flush_pending = [&]() {
+      if (pending != nullptr) {
+        if (elect_one()) {
+          bulk_wait<0>();
+          red_relaxed_gpu_add(pending, 1u);
+        }
+        __syncwarp();
+        pending = nullptr;
+      }
+    };
+    int it = 0;
+    for (int ui = u_begin; ui < u_end; ++ui, ++it) {
+      const int code = p.sched[ui];
+      const int kind = code >> 28, m = (code >> 8) & 0xFFFFF, n = code & 0xFF;
+      const int n0 = n * BN;
+      const int grow0 = m * 256 + (int)rank * GEMM_BM + lq * 32;  // first global row of this warp
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lq * 32) << 16) + cl;
+      auto release_acc = [&]() {  // hand the drained accumulator stage back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+      };
+      if (kind & 1) {
+        const int key = kind * 256 + n;
+        if (key != staged_key) {  // this warp's 64 bias values (a private slice: no barrier between the warps)
+          const float* bsrc = p.bias[kind];
+          const int c = n0 + cl + lane;
+          __syncwarp();
+          s_bias2[warp * 64 + lane] = bsrc ? bsrc[c] : 0.f;
+          s_bias2[warp * 64 + lane + 32] = bsrc ? bsrc[c + 32] : 0.f;
+          __syncwarp();
+          staged_key = key;
+        }
+      } else {
+        flush_pending();  // a LayerNorm unit blocks on its partner's statistics: no signal may be owed while it does
+      }
+      if (!mbar_try_wait(&tfull_bar[acc], acc_phase)) {
+        flush_pending();
+        mbar_wait_q(&tfull_bar[acc], acc_phase);
+      }
+      tc_fence_after();
+      if (threadIdx.x == 0) CHAIN_TRACE(8 + 6 * it);
+      uint32_t v0[32], v1[32];
+      tmem_ld32(taddr, v0);
+      tc_wait_ld_dep(v0);
+      tmem_ld32(taddr + 32, v1);
+      if (!(kind & 1)) {
+        // ---------------- x = LayerNorm(acc + b)   (acc already holds A . W^T + residual) ----------------
+        const int ln = kind >> 1;
+        const float* s_b1 = s_ln + (ln * 3 + 0) * BN;
+        const float* s_gamma = s_ln + (ln * 3 + 1) * BN;
+        const float* s_beta = s_ln + (ln * 3 + 2) * BN;
+        const int col0 = n0 + cl;  // global column of the slab
+        // ---- pass 1: y = acc + bias stays in registers; row sum and sum of squares (packed fp32 pairs: the epilogue is
+        //      issue bound -- 16 warps on 4 schedulers) ----
+        f32x2 sa = pk2(0.f, 0.f), sb = pk2(0.f, 0.f), qa = pk2(0.f, 0.f), qb = pk2(0.f, 0.f);
+        auto pass1 = [&](uint32_t (&v)[32], int cbase) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            asm volatile("" ::: "memory");  // keep the parameter loads next to their use (64 live accumulator registers)
+            const float4 b4 = *reinterpret_cast<const float4*>(s_b1 + cbase + j * 4);
+            const f32x2 y0 = add2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), pk2(b4.x, b4.y));
+            const f32x2 y1 = add2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pk2(b4.z, b4.w));
+            sa = add2(sa, y0), sb = add2(sb, y1);
+            qa = fma2(y0, y0, qa), qb = fma2(y1, y1, qb);
+            v[4 * j] = __float_as_uint(pk_lo(y0)), v[4 * j + 1] = __float_as_uint(pk_hi(y0));
+            v[4 * j + 2] = __float_as_uint(pk_lo(y1)), v[4 * j + 3] = __float_as_uint(pk_hi(y1));
+          }
+        };
+        pass1(v0, cl);
+        tc_wait_ld_dep(v1);
+        release_acc();  // the whole accumulator slab of this warp is in registers
+        pass1(v1, cl + 32);
+        if (threadIdx.x == 0 && it == 0) CHAIN_TRACE(57);  // pass 1 done (first unit of the pair, warp 0)
+        // ---- row statistics: 4 column quarters through shared memory, the other column half through L2 ----
+        float* st = s_stat + (ln_count & 1u) * (2 * 4 * 128);
+        ++ln_count;
+        st[cq * 128 + row_in_tile] = (pk_lo(sa) + pk_hi(sa)) + (pk_lo(sb) + pk_hi(sb));
+        st[512 + cq * 128 + row_in_tile] = (pk_lo(qa) + pk_hi(qa)) + (pk_lo(qb) + pk_hi(qb));
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        float tot_s = (st[row_in_tile] + st[128 + row_in_tile]) + (st[256 + row_in_tile] + st[384 + row_in_tile]);
+        float tot_q = (st[512 + row_in_tile] + st[640 + row_in_tile]) + (st[768 + row_in_tile] + st[896 + row_in_tile]);
+        if (halves == 2) {
+          // One 64-bit word per (row, reader): the sum of squares is >= 0 (or a NaN, made positive), so a posted word
+          // never equals the all-ones "not posted" pattern and the single store is its own flag (no fence).  The warp
+          // with column quarter 0 posts four copies, one per reading quarter of the partner CTA; a reader resets its
+          // copy after reading, which leaves the state clean for the next launch.
+          const size_t base = ((size_t)(ln * tiles_m + m) * 2) * 2;
+          const size_t mine = ((base + (size_t)n * 2 + rank) * 4) * 128 + row_in_tile;
+          const size_t theirs = ((base + (size_t)(n ^ 1) * 2 + rank) * 4 + cq) * 128 + row_in_tile;
+          if (cq == 0) {
+            const unsigned long long w = (unsigned long long)__float_as_uint(tot_s) |
+                                         ((unsigned long long)(__float_as_uint(tot_q) & 0x7fffffffu) << 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) st_relaxed_gpu_u64(p.stats + mine + c * 128, w);
+          }
+          unsigned long long o = ld_relaxed_gpu_u64(p.stats + theirs);
+          if (o == ~0ull) {
+            const long long t0 = clock64();
+            while ((o = ld_relaxed_gpu_u64(p.stats + theirs)) == ~0ull) {
+              __nanosleep(20);
+              if (clock64() - t0 > 4000000000LL) __trap();
+            }
+          }
+          st_relaxed_gpu_u64(p.stats + theirs, ~0ull);  // single reader: reset for the next launch
+          tot_s += __uint_as_float((uint32_t)o), tot_q += __uint_as_float((uint32_t)(o >> 32));
+          // a + b == b + a: both halves normalise with bit-identical statistics
+        }
+        if (threadIdx.x == 0 && it == 0) CHAIN_TRACE(58);  // statistics complete (first unit of the pair)
+        const float inv_n = 1.0f / (float)p.d;
+        const float mean = tot_s * inv_n;
+        const float var = fmaxf(tot_q * inv_n - mean * mean, 0.f);  // biased variance (F.layer_norm), fp32
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const float nmr = -mean * rstd;
+        // ---- pass 2: normalise + affine, hi plane -> staging -> TMA store, then lo plane ----
+        if (pending != nullptr) {
+          flush_pending();  // (also: the previous unit's store has finished reading the staging tile)
+        } else {
+          if (elect_one()) bulk_wait_read<0>();
+          __syncwarp();
+        }
+        const f32x2 rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
+        // y = ((acc - mean) rstd) gamma + beta on packed pairs; the hi plane bf16(y) goes to the staging tile, the
+        // register pair is replaced by the lo plane's input y - bf16(y) (exact in fp32)
+        auto norm_hi = [&](uint32_t (&v)[32], int cbase, int j0) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            uint32_t hi[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              asm volatile("" ::: "memory");  // as above
+              const int c = jj * 8 + e * 2;
+              const float2 g2 = *reinterpret_cast<const float2*>(s_gamma + cbase + c);
+              const float2 be2 = *reinterpret_cast<const float2*>(s_beta + cbase + c);
+              const f32x2 y = fma2(fma2(pk2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), rstd2, nmr2), pk2(g2.x, g2.y),
+                                   pk2(be2.x, be2.y));
+              hi[e] = pack_bf16x2(pk_lo(y), pk_hi(y));
+              const f32x2 r = add2(y, pk2(-bf16lo_f32(hi[e]), -bf16hi_f32(hi[e])));
+              v[c] = __float_as_uint(pk_lo(r)), v[c + 1] = __float_as_uint(pk_hi(r));
+            }
+            sts128(wst + stg128_off(lane, j0 + jj), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+          }
+        };
+        norm_hi(v0, cl, 0);
+        norm_hi(v1, cl + 32, 4);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one() && !(p.dbg & 1)) {
+          tma_store_2d(&tmXh_st, wst, col0, grow0);  // rows past M are clipped by the tensor map
+          bulk_commit();
+        }
+        if (threadIdx.x == 0 && it == 0) CHAIN_TRACE(59);  // hi plane staged + store issued
+        if (elect_one()) bulk_wait_read<0>();  // the hi store has finished reading the tile
+        __syncwarp();
+        if (threadIdx.x == 0 && it == 0) CHAIN_TRACE(60);
+        auto stage_lo = [&](const uint32_t (&v)[32], int j0) {  // lo = bf16(y - bf16(y)), the difference is in v
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            uint32_t lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              lo[e] = pack_bf16x2(__uint_as_float(v[jj * 8 + 2 * e]), __uint_as_float(v[jj * 8 + 2 * e + 1]));
+            sts128(wst + stg128_off(lane, j0 + jj), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          }
+        };
+        stage_lo(v0, 0);
+        stage_lo(v1, 4);
+        fence_proxy_async_smem();
+        __syncwarp();
+        // The HIGH plane (the A operand of the L1 / INP units of this row tile) is complete in L2 -> bump the row tile's
+        // counter.  The update is relaxed: the store has COMPLETED, the rows are in L2 (where TMA loads read) before the
+        // update is even issued; a release would add a gpu-scope fence, 3.3 k cycles on the critical path (measured).
+        if (elect_one()) {
+          if (!(p.dbg & 1)) {
+            tma_store_2d(&tmXl_st, wst, col0, grow0);
+            bulk_commit();
+          }
+          if (threadIdx.x == 0 && it == 0) CHAIN_TRACE(61);
+          bulk_wait<1>();  // all but the newest group: the hi-plane store of this warp has completed
+          if (threadIdx.x == 0 && it == 0) {
+            CHAIN_TRACE(62);
+            CHAIN_TRACE_NS(55);
+          }
+          red_relaxed_gpu_add(p.ctr + (ln ? 3 : 0) * tiles_m + m, 1u);
+        }
+        __syncwarp();
+        // the low plane of LN1 is the residual input of this row tile's LN2 units: owed once the store has completed
+        // (LN2's low plane is only read by the next kernel and completes before this CTA retires)
+        if (ln == 0) pending = p.ctr + 1 * tiles_m + m;
+      } else {
+        // ---------------- bias (+ GELU) -> bf16: the warp's 32 x 64 slab leaves as one TMA store ----------------
+        const float* wb = s_bias2 + warp * 64;
+        if (pending != nullptr) {
+          flush_pending();
+        } else {
+          if (elect_one()) bulk_wait_read<0>();  // the previous unit's store has finished reading the staging tile
+          __syncwarp();
+        }
+        auto half = [&](const uint32_t (&vv)[32], int j0, auto gelu) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j0 + jj;
+            const uint32_t* v = vv + jj * 8;
+            uint32_t o[4];
+            if constexpr (decltype(gelu)::value) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {  // packed pairs: bias add + GELU as FADD2 / FFMA2 chains
+                const float2 b2 = *reinterpret_cast<const float2*>(wb + j * 8 + 2 * e);
+                const f32x2 y = gelu_erf2(add2(pk2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), pk2(b2.x, b2.y)));
+                o[e] = pack_bf16x2(pk_lo(y), pk_hi(y));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 b2 = *reinterpret_cast<const float2*>(wb + j * 8 + 2 * e);
+                o[e] = pack_bf16x2(__uint_as_float(v[2 * e]) + b2.x, __uint_as_float(v[2 * e + 1]) + b2.y);
+              }
+            }
+            sts128(wst + stg128_off(lane, j), make_uint4(o[0], o[1], o[2], o[3]));
+          }
+        };
+        if (kind == CK_L1) {
+          half(v0, 0, std::true_type{});
+          tc_wait_ld_dep(v1);
+          release_acc();
+          half(v1, 4, std::true_type{});
+        } else {
+          half(v0, 0, std::false_type{});
+          tc_wait_ld_dep(v1);
+          release_acc();
+          half(v1, 4, std::false_type{});
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one() && !(p.dbg & 1)) {
+          tma_store_2d(kind == CK_L1 ? &tmHst : &tmQst, wst, n0 + cl, grow0);  // rows past M are clipped
+          bulk_commit();
+        }
+        // an H tile is an input of this row tile's LN2 units: owed once the store has completed
+        if (kind == CK_L1) pending = p.ctr + 2 * tiles_m + m;
+      }
+      if (threadIdx.x == 0) CHAIN_TRACE(9 + 6 * it);
+      if (++acc == 2) acc = 0, acc_phase ^= 1u;
+    }
+    flush_pending();
+    if (elect_one()) bulk_wait<0>();  // this thread's TMA stores have been performed before the CTA retires
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still signal our barriers / read our TMEM half
+  if (threadIdx.x == 0) {
+    CHAIN_TRACE(3);
+    ktime_exit(p.ktime);
+    // every wait of this CTA is behind it: the last CTA of the grid opens the next epoch
+    unsigned* done = p.ctr + 4 * tiles_m;
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      *done = 0u;
+      p.ctr[4 * tiles_m + 1] += 1u;
+    }
+  }
+  if (warp == PW + 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+// Static schedule of one layer kernel: per CTA pair the list of unit codes (kind << 28 | row tile << 8 | column tile).
+struct LayerSchedule {
+  int pairs = 0, tiles_m = 0, halves = 0;
+  std::vector<int> off, units;
+  double makespan = 0.0;
+};
+
+// Cost estimates in cycles (profiles/r02_chain_*): mainloop time of a unit, epilogue time, the offset inside the
+// epilogue (LN: from its start; L1: from its end) at which the unit's output is usable by a dependent unit.
+struct LayerCosts {
+  double kb = 625.0;        // one 64-deep k-block of a 256 x 256 pair tile (ring-latency bound with 4 stages; 512 at the MMA rate)
+  double res = 2000.0;      // the 4 residual stages of a LayerNorm unit
+  double epi_ln = 9500.0, ln_ready = 7000.0;   // LayerNorm epilogue; high plane complete this long after its start
+  double epi_gelu = 5300.0, epi_bias = 2000.0;
+  double signal = 2500.0;   // store completion + counter update + scout poll + first TMA loads of the dependent unit
+  double slack = 8000.0;    // a unit may start this much later than on the earliest pair if that pair is less loaded
+                            // (tools/sched_sweep.py, profiles/r02_sched_sweep.txt: the step time moves by < 2 % over wide
+                            // ranges of every constant; only signal = 0 -- dependents scheduled too early -- costs 12 %)
+};
+
+// List scheduling of the per-row-tile chains LN1 -> L1 (ff / 256 tiles) -> LN2 -> INP (n_inp / 256 tiles) on `slots`
+// pairs.  A pair is modelled as two resources (tensor pipe, epilogue warps) with two accumulator stages; a LayerNorm row
+// tile is a job for a DUO of neighbouring pairs (2k, 2k + 1: the two column halves run at the same list position and
+// exchange statistics).  Units are placed in order of their simulated start time, so every pair's list is a subsequence
+// of one global topological order.
+inline LayerSchedule build_layer_schedule(int M, int d, int ff, int n_inp, int slots, const LayerCosts& c) {
+  LayerSchedule s;
+  s.tiles_m = (M + 255) / 256;
+  s.halves = d / CH_BN;
+  const int T = s.tiles_m, H = s.halves, n1 = ff / CH_BN, n3 = n_inp / CH_BN;
+  int pairs = slots;
+  const long total_units = (long)T * (2 * H + n1 + n3);
+  if ((long)pairs > total_units) pairs = (int)total_units;
+  if (H == 2) pairs &= ~1;
+  if (pairs < H) pairs = H;
+  s.pairs = pairs;
+  struct Pair {
+    double mma_free = 0, epi_free = 0, epi_prev = 0, epi_last = 0;  // epi_prev: end of the epilogue before the last one
+  };
+  std::vector<Pair> ps(pairs);
+  std::vector<std::vector<int>> lists(pairs);
+  // place a unit on pair pr with inputs ready at `r`: returns {epilogue start, epilogue end}
+  auto place = [&](int pr, double r, double mma, double epi, bool commit, double* epi_start_out) {
+    Pair q = ps[pr];
+    const double mma_start = std::max(std::max(q.mma_free, r), q.epi_prev);  // needs a free accumulator stage
+    const double mma_end = mma_start + mma;
+    const double epi_start = std::max(mma_end, q.epi_free);
+    const double epi_end = epi_start + epi;
+    if (commit) {
+      q.mma_free = mma_end, q.epi_prev = q.epi_last, q.epi_last = epi_end, q.epi_free = epi_end;
+      ps[pr] = q;
+    }
+    if (epi_start_out) *epi_start_out = epi_start;
+    return epi_end;
+  };
+  const double mma_ln1 = c.kb * d / 64 + c.res, mma_ln2 = c.kb * ff / 64 + c.res, mma_t = c.kb * d / 64;
+  // per row tile: stage (0 LN1 pending, 1 L1 tiles, 2 LN2 pending, 3 INP tiles, 4 done), tiles left, input-ready time
+  std::vector<int> stage(T, 0), next_n(T, 0);
+  std::vector<double> ready(T, 0.0), acc_ready(T, 0.0);
+  long remaining = total_units;
+  std::vector<double> load(pairs, 0.0);  // tensor-pipe work assigned to a pair so far
+  while (remaining > 0) {
+    // candidate = the next unit of each row tile; pick the row tile that can start earliest (ties: the deeper stage
+    // first -- finish chains that are under way -- then the lower row tile), and for it, among the pairs (duos) that can
+    // start within `slack` of the earliest one, the least loaded: start times stay near-optimal while the long
+    // LayerNorm units spread over all duos instead of piling up on those that happened to be idle first.
+    int best_m = -1, best_pr = -1;
+    double best_start = 1e300;
+    for (int m = 0; m < T; ++m) {
+      if (stage[m] > 3) continue;
+      const bool ln = (stage[m] == 0 || stage[m] == 2);
+      const int step = ln ? H : 1;
+      double st_min = 1e300;
+      for (int k = 0; k + step <= pairs; k += step) {
+        double st = 0;
+        for (int h = 0; h < step; ++h) {
+          const Pair& q = ps[k + h];
+          st = std::max(st, std::max(std::max(q.mma_free, ready[m]), q.epi_prev));
+        }
+        st_min = std::min(st_min, st);
+      }
+      const double key = st_min - 1e-3 * stage[m];  // deeper stage wins ties
+      if (key < best_start - 1e-9) best_start = key, best_m = m;
+    }
+    {
+      const int m = best_m;
+      const bool ln = (stage[m] == 0 || stage[m] == 2);
+      const int step = ln ? H : 1;
+      const double limit = best_start + 1e-3 * stage[m] + c.slack;
+      double best_load = 1e300;
+      for (int k = 0; k + step <= pairs; k += step) {
+        double st = 0, ld = 0;
+        for (int h = 0; h < step; ++h) {
+          const Pair& q = ps[k + h];
+          st = std::max(st, std::max(std::max(q.mma_free, ready[m]), q.epi_prev));
+          ld = std::max(ld, load[k + h]);
+        }
+        if (st <= limit && ld < best_load - 1e-9) best_load = ld, best_pr = k;
+      }
+    }
+    const int m = best_m;
+    const int st = stage[m];
+    if (st == 0 || st == 2) {
+      double done = 0, duo_start = ready[m];
+      for (int h = 0; h < H; ++h) {
+        const Pair& q = ps[best_pr + h];
+        duo_start = std::max(duo_start, std::max(q.mma_free, q.epi_prev));
+      }
+      for (int h = 0; h < H; ++h) {
+        double es = 0;
+        // both halves start together: feed the common start time as the ready time
+        place(best_pr + h, duo_start, st == 0 ? mma_ln1 : mma_ln2, c.epi_ln, true, &es);
+        done = std::max(done, es + c.ln_ready + c.signal);
+        lists[best_pr + h].push_back(((st == 0 ? CK_LN1 : CK_LN2) << 28) | (m << 8) | h);
+        load[best_pr + h] += st == 0 ? mma_ln1 : mma_ln2;
+        --remaining;
+      }
+      ready[m] = done, acc_ready[m] = 0.0;
+      stage[m] = st + 1, next_n[m] = 0;
+      if (stage[m] == 3 && n3 == 0) stage[m] = 4;
+    } else {
+      const int nt = st == 1 ? n1 : n3;
+      const double end = place(best_pr, ready[m], mma_t, st == 1 ? c.epi_gelu : c.epi_bias, true, nullptr);
+      lists[best_pr].push_back(((st == 1 ? CK_L1 : CK_INP) << 28) | (m << 8) | next_n[m]);
+      load[best_pr] += mma_t;
+      --remaining;
+      acc_ready[m] = std::max(acc_ready[m], end + c.signal);
+      if (++next_n[m] == nt) {
+        stage[m] = st + 1;
+        ready[m] = acc_ready[m];  // LN2 needs every H tile of the row tile
+      }
+    }
+  }
+  s.off.assign(pairs + 1, 0);
+  for (int pr = 0; pr < pairs; ++pr) {
+    s.off[pr + 1] = s.off[pr] + (int)lists[pr].size();
+    s.units.insert(s.units.end(), lists[pr].begin(), lists[pr].end());
+    s.makespan = std::max(s.makespan, ps[pr].epi_free);
+  }
+  return s;
+}
+
+inline int configure_layer_chain() {
+  TAMF_CUDA_CHECK(cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES));
+  return TAMF_OK;
+}
+
+struct LayerMaps {
+  const CUtensorMap *ATT, *Wo, *Xh, *Xl, *W1, *Hst, *H, *W2, *Win, *Qst, *Xh_st, *Xl_st, *I;  // Win / Qst null: no INP
+};
+
+// The 64 x 64 bf16 identity the residual blocks are multiplied with (one per device, never freed) and its tensor map.
+inline int chain_identity_map(CUtensorMap* out) {
+  static std::mutex mu;
+  static std::map<int, void*> per_dev;
+  int dev = 0;
+  TAMF_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  void*& d = per_dev[dev];
+  if (!d) {
+    std::vector<uint16_t> h(64 * 64, 0);
+    for (int i = 0; i < 64; ++i) h[i * 64 + i] = 0x3F80;  // bf16 1.0
+    TAMF_CUDA_CHECK(cudaMalloc(&d, h.size() * 2));
+    TAMF_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  }
+  return make_tmap_2d_bf16(out, d, 64, 64, 128, 64, 32);
+}
+
+inline int launch_layer_chain(const LayerMaps& tm, const LayerParams& p, int pairs, cudaStream_t stream) {
+  TAMF_REQUIRE(p.d == 256 || p.d == 512, TAMF_E_BADARG, "layer_chain: LayerNorm width must be 256 or 512");
+  TAMF_REQUIRE(p.ff > 0 && p.ff % 256 == 0 && p.n_inp % 256 == 0, TAMF_E_BADARG,
+               "layer_chain: ff and the in_proj width must be multiples of 256");
+  TAMF_REQUIRE(tm.ATT && tm.Wo && tm.Xh && tm.Xl && tm.W1 && tm.Hst && tm.H && tm.W2 && tm.Xh_st && tm.Xl_st && tm.I &&
+                   (p.n_inp == 0 || (tm.Win && tm.Qst)),
+               TAMF_E_BADARG, "layer_chain: missing tensor map");
+  TAMF_REQUIRE(pairs >= 1 && 2 * pairs <= num_sms(), TAMF_E_BADARG, "layer_chain: the grid must be co-resident");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(CH_THREADS);
+  cfg.dynamicSmemBytes = CH_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 2, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  const CUtensorMap& win = tm.Win ? *tm.Win : *tm.W1;  // unused maps are passed as copies
+  const CUtensorMap& qst = tm.Qst ? *tm.Qst : *tm.Hst;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, layer_chain_kernel, *tm.ATT, *tm.Wo, *tm.Xh, *tm.Xl, *tm.W1, *tm.Hst, *tm.H,
+                                     *tm.W2, win, qst, *tm.Xh_st, *tm.Xl_st, *tm.I, p);
+  count_launch();
+  if (e != cudaSuccess) {
+    set_error(std::string("layer_chain launch failed: ") + cudaGetErrorString(e));
+    return TAMF_E_CUDA;
+  }
+  return TAMF_OK;
+}
+
+}  // namespace tamf

@@ -19,11 +19,11 @@ SYMBOLS = [
     "tamf_h2o_index_build", "tamf_h2o_dist_indexed", "tamf_mano_create", "tamf_mano_destroy",
     "tamf_mano_fk", "tamf_mano_fk_full", "tamf_denoiser_create", "tamf_denoiser_destroy", "tamf_denoiser_workspace_bytes",
     "tamf_denoiser_bind", "tamf_denoiser_set_cond", "tamf_denoiser_forward", "tamf_p_sample_step",
-    "tamf_p_sample_chain", "tamf_p_sample_loop_host", "tamf_denoiser_profile_step", "tamf_kernel_launch_count", "tamf_philox_normal",
+    "tamf_p_sample_chain", "tamf_p_sample_loop_host", "tamf_denoiser_profile_step", "tamf_denoiser_profile_graph", "tamf_kernel_launch_count", "tamf_philox_normal",
     "tamf_gemm_selftest", "tamf_refiner_create", "tamf_refiner_destroy", "tamf_refiner_workspace_bytes",
     "tamf_refiner_bind", "tamf_refiner_forward", "tamf_mano_fk_select", "tamf_vertex_normals", "tamf_gemm_trace",
     "tamf_attn_selftest", "tamf_attn_trace", "tamf_denoiser_set_sampler", "tamf_denoiser_sampler_steps",
-    "tamf_chain_aux_bytes", "tamf_chain_run", "tamf_debug_chain_trace",
+    "tamf_layer_aux_bytes", "tamf_layer_run", "tamf_debug_chain_trace", "tamf_layer_schedule",
 ]
 
 
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     L.tamf_p_sample_chain.argtypes = [vp, vp, i32, i32, u64, vp]
     L.tamf_p_sample_loop_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, u64, vp, vp]
     L.tamf_denoiser_profile_step.argtypes = [vp, vp, i32, u64, vp, i32, vp, vp]
+    L.tamf_denoiser_profile_graph.argtypes = [vp, vp, i32, i32, u64, vp, vp, vp, i32, vp, vp, vp]
     L.tamf_philox_normal.argtypes = [vp, sz, u64, C.c_uint32, vp]
     L.tamf_gemm_selftest.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.tamf_refiner_create.argtypes = [C.POINTER(TamfCfg), C.POINTER(TamfRWeights), C.POINTER(vp)]
@@ -112,10 +113,11 @@ def lib() -> C.CDLL:
     L.tamf_denoiser_set_sampler.argtypes = [vp, i32, vp, vp, vp, vp]
     L.tamf_denoiser_sampler_steps.argtypes = [vp]
     L.tamf_attn_trace.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
-    L.tamf_chain_aux_bytes.argtypes = [i32, i32, i32]
-    L.tamf_chain_aux_bytes.restype = sz
-    L.tamf_debug_chain_trace.argtypes = [vp, vp, i32]
-    L.tamf_chain_run.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp, vp]
+    L.tamf_layer_aux_bytes.argtypes = [i32, i32, i32]
+    L.tamf_layer_aux_bytes.restype = sz
+    L.tamf_layer_run.argtypes = [vp] * 12 + [i32, i32, i32, i32, vp, sz, vp, vp]
+    L.tamf_debug_chain_trace.argtypes = [vp, i32]
+    L.tamf_layer_schedule.argtypes = [i32, i32, i32, i32, i32, vp, vp, i32, vp]
     _lib = L
     return L
 

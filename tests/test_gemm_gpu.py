@@ -25,44 +25,52 @@ def test_gemm_matches_fp32(tile_n, cta_group, M, N, K):
     assert err < 2e-3, f"max abs err {err}"
 
 
-@pytest.mark.parametrize("which,M,d,K1,N2", [
-    (0, 300, 256, 256, 512), (0, 1000, 512, 512, 2048), (0, 10560, 512, 512, 2048), (1, 10560, 512, 2048, 1536),
-    (2, 777, 512, 1024, 0), (1, 10432, 256, 1024, 768), (2, 10560, 512, 2048, 0), (0, 58, 512, 512, 1024),
-    (1, 256, 512, 2048, 1536), (0, 19000, 512, 512, 2048)])
-def test_chain_kernel_matches_fp32(which, M, d, K1, N2):
-    """One launch of a chain kernel (csrc/gemm_chain.cuh): X = LayerNorm(X + A1 . W1^T + b1) in place as the bf16 hi/lo
-    pair, then C2 = act(Xh . W2^T + b2), against torch fp32 on the same bf16-rounded inputs.  Covers one and two column
-    halves (d = 256 / 512), row tiles that end inside the matrix, one unit per pair up to several rounds, no phase 2."""
+@pytest.mark.parametrize("M,d,ff,n_inp", [
+    (300, 256, 512, 768), (1000, 512, 1024, 1536), (10560, 512, 2048, 1536), (10560, 512, 2048, 0), (777, 512, 1024, 0),
+    (10432, 256, 1024, 768), (58, 512, 1024, 1536), (256, 512, 2048, 1536), (19000, 512, 2048, 1536)])
+def test_layer_kernel_matches_fp32(M, d, ff, n_inp):
+    """One launch of the layer kernel (csrc/layer_chain.cuh): X = LN1(X + ATT . Wo^T + b), H = gelu(Xh . W1^T + b),
+    X = LN2(X + H . W2^T + b), QKV = Xh . Win^T + b -- against torch fp32 evaluated stage by stage on the kernel's own
+    bf16 intermediates (so each stage is checked at fp32-summation tolerance).  Covers one and two column halves
+    (d = 256 / 512), row tiles that end inside the matrix, fewer units than CTA pairs up to a dozen units per pair, and
+    the last-layer form without the in_proj stage.  Run twice on the same scratch: the sync state must be reusable."""
     from tamf_b200 import _lib
     L = _lib.lib()
-    g = torch.Generator(device="cuda").manual_seed(M + d + K1 + N2)
+    g = torch.Generator(device="cuda").manual_seed(M + d + ff + n_inp)
     rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
-    a1 = rn(M, K1).to(torch.bfloat16)
-    w1 = (rn(d, K1) / K1 ** 0.5).to(torch.bfloat16)
-    lnp = torch.cat([0.1 * rn(d), 1 + 0.1 * rn(d), 0.1 * rn(d)]).contiguous()
+    bf = torch.bfloat16
+    att = rn(M, d).to(bf)
+    w_out, w1 = (rn(d, d) / d ** 0.5).to(bf), (rn(ff, d) / d ** 0.5).to(bf)
+    w2, w_in = (rn(d, ff) / ff ** 0.5).to(bf), (rn(max(n_inp, 256), d) / d ** 0.5).to(bf)
+    lnp = torch.cat([0.1 * rn(d), 1 + 0.1 * rn(d), 0.1 * rn(d), 0.1 * rn(d), 1 + 0.1 * rn(d), 0.1 * rn(d)]).contiguous()
+    b1, b_in = 0.1 * rn(ff), 0.1 * rn(max(n_inp, 256))
     x = rn(M, d)
-    xh = x.to(torch.bfloat16)
-    xl = (x - xh.float()).to(torch.bfloat16)
-    x_in = xh.float() + xl.float()
-    w2 = (rn(max(N2, 256), d) / d ** 0.5).to(torch.bfloat16)
-    b2 = 0.1 * rn(max(N2, 256))
-    c2 = torch.full((M, max(N2, 256)), float("nan"), device="cuda", dtype=torch.bfloat16)
-    nb = L.tamf_chain_aux_bytes(M, d, max(K1, N2, 3 * d))
+    nb = L.tamf_layer_aux_bytes(M, d, ff)
     aux = torch.zeros(nb, dtype=torch.uint8, device="cuda")
-    _lib.check(L.tamf_chain_run(which, _lib.ptr(a1), _lib.ptr(w1), _lib.ptr(lnp), _lib.ptr(xh), _lib.ptr(xl), _lib.ptr(w2),
-                                _lib.ptr(b2), _lib.ptr(c2), M, d, K1, N2, _lib.ptr(aux), nb, None, _lib.stream_ptr()),
-               "tamf_chain_run")
-    torch.cuda.synchronize()
-    y = x_in + a1.float() @ w1.float().t() + lnp[:d]
-    ref = torch.nn.functional.layer_norm(y, (d,), lnp[d:2 * d], lnp[2 * d:], 1e-5)
-    got = xh.float() + xl.float()
-    err = (got - ref).abs().max().item()
-    assert err < 5e-4, f"LayerNorm max abs err {err}"
-    # the hi plane is bf16(x) (it doubles as the next GEMM's operand), the lo plane the rounding remainder: <= half an ulp
-    assert bool((xl.float().abs() <= 2.0 ** -8 * xh.float().abs() + 1e-30).all())
-    if which != 2:
-        r2 = xh.float() @ w2[:N2].float().t() + b2[:N2]
-        if which == 0:
-            r2 = torch.nn.functional.gelu(r2)
-        e2 = (c2[:, :N2].float() - r2).abs()
-        assert bool((e2 <= 1e-2 + 1e-2 * r2.abs()).all()), f"phase-2 max abs err {e2.max().item()}"
+    ln = torch.nn.functional.layer_norm
+    for rep in range(2):
+        xh = x.to(bf)
+        xl = (x - xh.float()).to(bf)
+        x_in = xh.float() + xl.float()
+        H = torch.full((M, ff), float("nan"), device="cuda", dtype=bf)
+        qkv = torch.full((M, max(n_inp, 256)), float("nan"), device="cuda", dtype=bf)
+        _lib.check(L.tamf_layer_run(_lib.ptr(att), _lib.ptr(w_out), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w_in), _lib.ptr(lnp),
+                                    _lib.ptr(b1), _lib.ptr(b_in), _lib.ptr(xh), _lib.ptr(xl), _lib.ptr(H), _lib.ptr(qkv), M, d,
+                                    ff, n_inp, _lib.ptr(aux), nb, None, _lib.stream_ptr()), "tamf_layer_run")
+        torch.cuda.synchronize()
+        # stage 1: LN1 (its output is only visible through H: check H against gelu(bf16(LN1) . W1^T + b1))
+        y1 = ln(x_in + att.float() @ w_out.float().t() + lnp[:d], (d,), lnp[d:2 * d], lnp[2 * d:3 * d], 1e-5)
+        h_ref = torch.nn.functional.gelu(y1.to(bf).float() @ w1.float().t() + b1)
+        eh = (H.float() - h_ref).abs()
+        # a bf16 rounding flip of a LN1 output moves an H element by ~2^-9 |w|: allow a few bf16 ulps
+        assert bool((eh <= 3e-2 + 2e-2 * h_ref.abs()).all()), f"H max abs err {eh.max().item()}"
+        # stage 3: LN2 from the kernel's own H and the fp32 LN1 output
+        y2 = ln(y1 + H.float() @ w2.float().t() + lnp[3 * d:4 * d], (d,), lnp[4 * d:5 * d], lnp[5 * d:], 1e-5)
+        got = xh.float() + xl.float()
+        err = (got - y2).abs().max().item()
+        assert err < 2e-3, f"LN2 max abs err {err}"  # y1 enters as the bf16 pair (2^-17 relative)
+        assert bool((xl.float().abs() <= 2.0 ** -8 * xh.float().abs() + 1e-30).all())  # lo = rounding remainder of hi
+        if n_inp:
+            q_ref = xh.float() @ w_in[:n_inp].float().t() + b_in[:n_inp]
+            eq = (qkv[:, :n_inp].float() - q_ref).abs()
+            assert bool((eq <= 1e-2 + 1e-2 * q_ref.abs()).all()), f"QKV max abs err {eq.max().item()}"

@@ -110,6 +110,58 @@ def test_bench_flop_model():
     import bench
     cfg = synth.ARCH["arch_mdm_l"]
     assert abs(bench.flops_per_seq_step(cfg) - 8.951e9) < 2e6  # 8 951 M
-    cls = bench.kernel_classes(cfg, 64)
-    assert len(cls) == 3 + 5 * 8 + 1
-    assert abs(sum(f for _, f in cls) / 64 - bench.flops_per_seq_step(cfg)) / 8.95e9 < 0.01
+    for chain, n in ((True, 3 + 1 + 2 * 8 + 1), (False, 3 + 5 * 8 + 1)):
+        cls = bench.kernel_classes(cfg, 64, chain=chain)
+        assert len(cls) == n
+        assert abs(sum(f for _, f in cls) / 64 - bench.flops_per_seq_step(cfg)) / 8.95e9 < 0.01
+
+
+@pytest.mark.parametrize("M,d,ff,n_inp,slots", [(10560, 512, 2048, 1536, 74), (10560, 512, 2048, 0, 74), (10432, 256, 1024, 768, 74),
+                                                (300, 512, 1024, 1536, 74), (58, 256, 512, 0, 74), (19000, 512, 2048, 1536, 66)])
+def test_layer_schedule_is_complete_and_deadlock_free(M, d, ff, n_inp, slots):
+    """The static schedule of the layer kernel (csrc/layer_chain.cuh build_layer_schedule, host code of the library, no GPU
+    needed): every unit exactly once; the two column halves of a LayerNorm row tile on neighbouring pairs 2k / 2k + 1;
+    and a replay in which a pair may only run its next unit once that unit's producers have finished completes (every
+    pair's list is a subsequence of one global topological order)."""
+    import ctypes as C
+    from tamf_b200 import _lib
+    L = _lib.lib()
+    off = np.zeros(slots + 1, np.int32)
+    units = np.zeros(1 << 16, np.int32)
+    mk = C.c_double()
+    pairs = L.tamf_layer_schedule(M, d, ff, n_inp, slots, off.ctypes.data, units.ctypes.data, len(units), C.byref(mk))
+    assert 1 <= pairs <= slots and mk.value > 0
+    T, H, n1, n3 = (M + 255) // 256, d // 256, ff // 256, n_inp // 256
+    lists = [[(int(c) >> 28, (int(c) >> 8) & 0xFFFFF, int(c) & 255) for c in units[off[p]:off[p + 1]]] for p in range(pairs)]
+    allu = [u for l in lists for u in l]
+    expect = {(0, m, h) for m in range(T) for h in range(H)} | {(1, m, n) for m in range(T) for n in range(n1)} | \
+             {(2, m, h) for m in range(T) for h in range(H)} | {(3, m, n) for m in range(T) for n in range(n3)}
+    assert len(allu) == len(expect) and set(allu) == expect
+    for p, l in enumerate(lists):
+        for k, m, n in l:
+            if k in (0, 2):
+                assert p % H == n  # the half a pair's LayerNorm parameters are staged for
+                if H == 2:
+                    assert (k, m, n ^ 1) in lists[p ^ 1]
+    # replay: done[kind][m] counts finished units; a unit may run when its producers have all finished
+    pos = [0] * pairs
+    done = {k: [0] * T for k in range(4)}
+    need = {1: (0, H), 2: (1, n1), 3: (2, H)}
+    left = len(allu)
+    while left:
+        progressed = False
+        for p in range(pairs):
+            while pos[p] < len(lists[p]):
+                k, m, n = lists[p][pos[p]]
+                if k in need and done[need[k][0]][m] < need[k][1]:
+                    break
+                if k in (0, 2) and H == 2:  # the partner half must be the partner pair's next unit, or already done
+                    q = p ^ 1
+                    ahead = lists[q][pos[q]:pos[q] + 1]
+                    if (k, m, n ^ 1) not in ahead and (k, m, n ^ 1) not in lists[q][:pos[q]]:
+                        break
+                done[k][m] += 1
+                pos[p] += 1
+                left -= 1
+                progressed = True
+        assert progressed, "the schedule deadlocks"

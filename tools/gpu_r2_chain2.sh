@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gemm_gpu.py -m gpu -x -q -k chain 2>&1 | tail -n 5 > gpurun_out/r2_chain_unit.log
-if ! grep -q "passed" gpurun_out/r2_chain_unit.log || grep -q "failed" gpurun_out/r2_chain_unit.log; then echo "chain unit test failed: stop"; tail gpurun_out/r2_chain_unit.log; exit 1; fi
+timeout 300 python -m pytest tests/test_gemm_gpu.py -m gpu -x -q -k layer 2>&1 | tail -n 5 > gpurun_out/r2_chain_unit.log
+if ! grep -q "passed" gpurun_out/r2_chain_unit.log || grep -q "failed" gpurun_out/r2_chain_unit.log; then echo "layer unit test failed: stop"; tail gpurun_out/r2_chain_unit.log; exit 1; fi
 timeout 200 python tools/chain_trace_model.py 3 > gpurun_out/r2_chain_model_timelines.txt 2>&1
 B="python bench.py --steps 2 --warmup 2 --no-cpu-baseline --profile-reps 3"
 run() { tag=$1; shift; env "$@" timeout 300 $B > gpurun_out/r2_b_$tag.json 2> gpurun_out/r2_b_$tag.err; python - <<PY
@@ -12,6 +12,6 @@ except Exception as e: print("$tag failed", e)
 PY
 }
 run default X=1
-run ln13 TAMF_CHAIN_EPI_LN=13000 TAMF_CHAIN_EPI_GELU=6200 TAMF_CHAIN_EPI_BIAS=4400
-run ln11 TAMF_CHAIN_EPI_LN=11000 TAMF_CHAIN_EPI_GELU=5600 TAMF_CHAIN_EPI_BIAS=4400
+run slack0 TAMF_CHAIN_SLACK=0
+run slack12k TAMF_CHAIN_SLACK=12000
 run nochain TAMF_CHAIN=0
