@@ -11,8 +11,12 @@ p_sample steps for B=64 synthetic sequences per GPU (BASELINE.json configs[1]). 
   value     whole-job sequences/s with every input resident in HBM when the timed region starts
   e2e       the same through the reference-facing call (InterationSegmentMDM.sample_host -> tamf_p_sample_loop_host)
             with HOST buffers: H2D of the conditioning and D2H of the samples inside the timed region
-  roofline  the dominant kernel of the step (per-kernel CUDA-event times from tamf_denoiser_profile_step, live),
-            algorithmic FLOPs per launch / mean launch duration vs the measured bf16 peak (MEASURED_PEAKS.json)
+  roofline  the dominant kernel of the step, measured live INSIDE the captured step graph (globaltimer stamps at every
+            kernel's dependency-wait end and last CTA exit, tamf_denoiser_profile_graph): algorithmic FLOPs per launch /
+            in-graph duration vs the measured sustained bf16 peak (MEASURED_PEAKS.json); `isolated` repeats it with CUDA
+            events around eager launches against the burst peak; `step` is the whole evaluation
+    --sequences S   BASELINE.json configs[3]: S sequences batch-sharded over the ranks (strong scaling)
+    --config refine BASELINE.json configs[2]: the MF-MDM R forward
   cpu_baseline  the oracle port of the reference's PyTorch algorithm on the host cores (bounded sample, extrapolated)
 
 CLIP `encode_text` is library code that stays in PyTorch and needs downloaded weights (absent offline): both arms
@@ -206,13 +210,9 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
+def _dist_setup():
     import torch
     import torch.distributed as dist
-
-    import tamf_b200
-    from tamf_b200 import _lib, synth
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -223,36 +223,106 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local, dev
+
+
+def in_graph_breakdown(model, L, x, classes, n_steps=8):
+    """Per-kernel figures INSIDE the captured step (tamf_denoiser_profile_graph: globaltimer stamps at every kernel's
+    entry / end of its dependency wait / exit, the same graph and programmatic launches as the chain).  Returns
+    {class: {"us": busy time ready->exit summed over its launches, "launches", "flops"}}, the step period and the share of
+    the period no kernel of ours was past its dependency wait (launch gaps + dependency waits)."""
+    import ctypes as C
+    from tamf_b200 import _lib
+    cap = 128
+    en, rd, ex = (C.c_double * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
+    n_out, step_us = C.c_int(0), C.c_double(0)
+    _lib.check(L.tamf_denoiser_profile_graph(model._handle, _lib.ptr(x), 700, n_steps, 11, en, rd, ex, cap, C.byref(n_out),
+                                             C.byref(step_us), _lib.stream_ptr(x.device)), "profile_graph")
+    n = n_out.value
+    assert n == len(classes), (n, len(classes))
+    per = {}
+    busy_until, covered = 0.0, 0.0
+    for k, (name, fl) in enumerate(classes):
+        c = per.setdefault(name, {"us": 0.0, "launches": 0, "flops": 0})
+        c["us"] += ex[k] - rd[k]
+        c["launches"] += 1
+        c["flops"] += fl
+        lo, hi = max(rd[k], busy_until), ex[k]
+        if hi > lo:
+            covered += hi - lo
+            busy_until = hi
+    return per, step_us.value, 1.0 - covered / max(step_us.value, 1e-9)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import tamf_b200
+    from tamf_b200 import _lib, shard, synth
+
+    world, rank, local, dev = _dist_setup()
     L = _lib.lib()
     cfg = synth.ARCH[ARCH]
     B, T = args.batch, T_FRAMES
+    strong = args.sequences > 0
     model = tamf_b200.InterationSegmentMDM(**cfg, text_encoder=synth.text_features)
     model.load_state_dict(synth.g_state_dict(cfg, seed=0), strict=False)
     model = model.eval().to(dev)
+    tamf_b200.create_gaussian_diffusion(DIFF_STEPS, "cosine")._install(model, "ancestral")
     host_batch = synth.make_batch(B, T, nobj=NOBJ, seed=100 + rank)
     pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
     dev_batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
     x = torch.empty(B, 99, 1, T, device=dev)
-    gathered = torch.empty(world * B, 99, 1, T, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
+    t_end = DIFF_STEPS - args.chain_steps
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def device_step(seed):
-        flush.zero_()  # L2 flush between timed iterations (the step's own working set, 180 MB, also exceeds L2)
-        model.set_cond(dev_batch, B, T, dev)  # conditioning: once per sample batch
-        _lib.check(L.tamf_philox_normal(_lib.ptr(x), x.numel(), seed, DIFF_STEPS, _lib.stream_ptr(dev)), "x_T")
-        model.p_sample_chain(x, DIFF_STEPS - 1, DIFF_STEPS - args.chain_steps, dev_batch, seed=seed)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, x)  # the one collective of the path: final gather of the samples
+    if strong:
+        # configs[3]: a FIXED set of sequences, contiguous index ranges per rank (launch/sample.py:198-199), chains of B
+        # on ONE x buffer (one captured graph: timestep counter and seed live in device memory), samples copied into the
+        # rank's output block, one NCCL all_gather at the end
+        mine = shard.shard_range(args.sequences, rank, world)
+        chains = list(shard.batches(mine, B))
+        if any(len(c) != B for c in chains):
+            raise SystemExit("--sequences must be a multiple of world_size * batch for the strong-scaling run")
+        out = torch.empty(len(mine), T, 99, device=dev)
+        gathered = None
+
+        def device_step(seed):
+            flush.zero_()
+            for i, ids in enumerate(chains):
+                model.set_cond(dev_batch, B, T, dev)  # conditioning: once per chain
+                _lib.check(L.tamf_philox_normal(_lib.ptr(x), x.numel(), seed * 100003 + ids.start, DIFF_STEPS,
+                                                _lib.stream_ptr(dev)), "x_T")
+                model.p_sample_chain(x, DIFF_STEPS - 1, t_end, dev_batch, seed=seed * 100003 + ids.start)
+                out[ids.start - mine.start: ids.stop - mine.start] = x.permute(0, 3, 1, 2).squeeze(3)  # extract_sample.py:32
+            return shard.gather_samples(out, args.sequences)
+        seqs_per_step = args.sequences
+    else:
+        gathered = torch.empty(world * B, 99, 1, T, device=dev) if world > 1 else None
+
+        def device_step(seed):
+            flush.zero_()  # L2 flush between timed iterations (the step's own working set, 180 MB, also exceeds L2)
+            model.set_cond(dev_batch, B, T, dev)  # conditioning: once per sample batch
+            _lib.check(L.tamf_philox_normal(_lib.ptr(x), x.numel(), seed, DIFF_STEPS, _lib.stream_ptr(dev)), "x_T")
+            model.p_sample_chain(x, DIFF_STEPS - 1, t_end, dev_batch, seed=seed)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, x)  # the one collective of the path: final gather of the samples
+        seqs_per_step = world * B
 
     # ---------------- device-resident throughput ----------------
-    for i in range(args.warmup):
-        device_step(1000 + i)
+    if strong:  # one short chain warms the graph / workspace; a warm-up "step" would be the whole job
+        model.set_cond(dev_batch, B, T, dev)
+        model.p_sample_chain(x.normal_(), DIFF_STEPS - 1, DIFF_STEPS - 10, dev_batch, seed=1)
+    else:
+        for i in range(args.warmup):
+            device_step(1000 + i)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -271,96 +341,232 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     assert torch.isfinite(x).all(), "non-finite samples"
-    value = world * B * args.steps / (ms_total * 1e-3)
+    value = seqs_per_step * args.steps / (ms_total * 1e-3)
 
     # ---------------- end to end through the host-buffer API ----------------
     h2d = sum(pinned[k].numel() * 4 for k in ("shape", "obj_traj", "obj_embedding")) + B * 512 * 4 + B * 4
     d2h = B * 99 * T * 4
-    e2e_steps = max(1, args.steps)
-    model.sample_host(pinned, seed=1)  # warm-up (graph already captured; new workspace binding is reused)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        out = model.sample_host(pinned, seed=3000 + i)
-    torch.cuda.synchronize(dev)
-    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(dt.item())
-    assert torch.isfinite(out).all()
+    e2e = None
+    if not strong:
+        e2e_steps = max(1, args.steps)
+        model.sample_host(pinned, seed=1)  # warm-up (graph already captured; the workspace binding is reused)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            out_h = model.sample_host(pinned, seed=3000 + i)
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert torch.isfinite(out_h).all()
+        e2e = {"value": world * B * e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "path": "InterationSegmentMDM.sample_host -> tamf_p_sample_loop_host: pinned host conditioning in, host samples out"}
 
-    # ---------------- per-kernel times (live, CUDA events on the launch stream) -> roofline ----------------
-    roof, per_class = None, None
+    # ---------------- roofline: in-graph per-kernel figures (live) + isolated launches ----------------
+    roof = None
     if rank == 0:
         import ctypes as C
-        classes = kernel_classes(cfg, B)
-        ms_buf = (C.c_float * 64)()
-        n_out = C.c_int(0)
-        acc = [0.0] * len(classes)
-        reps = 0
+        pk = peaks()
         model.set_cond(dev_batch, B, T, dev)
+        classes = kernel_classes(cfg, B)
+        ms_buf, n_out = (C.c_float * 64)(), C.c_int(0)
+        _lib.check(L.tamf_denoiser_profile_step(model._handle, _lib.ptr(x), 500, 7, ms_buf, 64, C.byref(n_out),
+                                                _lib.stream_ptr(dev)), "profile_step")
+        if n_out.value != len(classes):  # TAMF_CHAIN=0: the five-kernel layer of round 1
+            classes = kernel_classes(cfg, B, chain=False)
+        iso = {}
         for r in range(args.profile_reps + 2):
             _lib.check(L.tamf_denoiser_profile_step(model._handle, _lib.ptr(x), 500, 7, ms_buf, 64, C.byref(n_out),
                                                     _lib.stream_ptr(dev)), "profile_step")
-            if n_out.value != len(classes):  # TAMF_CHAIN=0: the five-kernel layer of round 1
-                classes = kernel_classes(cfg, B, chain=False)
-                acc = [0.0] * len(classes)
-            assert n_out.value == len(classes)
             if r >= 2:
-                reps += 1
-                for i in range(len(classes)):
-                    acc[i] += ms_buf[i]
-        per_class = {}
-        for (name, fl), a in zip(classes, acc):
-            c = per_class.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0})
-            c["ms"] += a / reps
-            c["launches"] += 1
-            c["flops"] += fl
-        step_ms_sum = sum(c["ms"] for c in per_class.values())
-        top = max(per_class, key=lambda k: per_class[k]["ms"])
-        c = per_class[top]
-        pk = peaks()
-        achieved = c["flops"] / (c["ms"] * 1e-3) / 1e12
+                for i, (name, _) in enumerate(classes):
+                    iso[name] = iso.get(name, 0.0) + ms_buf[i] / args.profile_reps
+        per, step_us, idle = in_graph_breakdown(model, L, x, classes)
+        top = max(per, key=lambda k: per[k]["us"])
+        c = per[top]
+        achieved = c["flops"] / (c["us"] * 1e-6) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(top)
-        roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["sustained"], "traffic": traffic, "peak_source": pk["src"] + " (sustained)",
-                "launch_ms": c["ms"] / c["launches"], "share_of_step": c["ms"] / step_ms_sum,
-                "flops_per_launch": c["flops"] / c["launches"]}
         step_fl = flops_per_seq_step(cfg) * B
-        chain_ms = ms_total / args.steps / args.chain_steps
-        roof["step"] = {"achieved": step_fl / (chain_ms * 1e-3) / 1e12, "ms_per_denoiser_eval": chain_ms,
-                        "frac": step_fl / (chain_ms * 1e-3) / 1e12 / pk["sustained"]}
-        roof["kernels_ms"] = {k: round(v["ms"], 4) for k, v in per_class.items()}
+        chain_ms = ms_total / args.steps / args.chain_steps / (len(chains) if strong else 1)
+        roof = {
+            "bound": "tensor", "kernel": top, "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["sustained"], "traffic": traffic,
+            "peak_source": pk["src"] + " (sustained: the kernel is timed inside the captured step)",
+            "launch_us_in_graph": c["us"] / c["launches"], "launches_per_step": c["launches"],
+            "flops_per_launch": c["flops"] / c["launches"], "share_of_step": c["us"] / step_us,
+            "how": "globaltimer stamps (end of dependency wait -> last CTA exit) of every launch inside the captured "
+                   "step graph, mean of 3 replays (tamf_denoiser_profile_graph)",
+            "isolated": {"launch_ms": iso[top] / c["launches"],
+                         "achieved": c["flops"] / (iso[top] * 1e-3) / 1e12, "peak": pk["burst"],
+                         "frac": c["flops"] / (iso[top] * 1e-3) / 1e12 / pk["burst"],
+                         "how": "CUDA events around each eager launch (includes ~6 us of launch gap per kernel)"},
+            "step": {"achieved": step_fl / (chain_ms * 1e-3) / 1e12, "ms_per_denoiser_eval": chain_ms,
+                     "frac": step_fl / (chain_ms * 1e-3) / 1e12 / pk["sustained"], "peak": pk["sustained"]},
+            "kernels_in_graph_us": {k: round(v["us"], 2) for k, v in per.items()},
+            "kernels_in_graph_tflops": {k: round(v["flops"] / (v["us"] * 1e-6) / 1e12, 1) for k, v in per.items() if v["flops"]},
+            "in_graph_step_us": round(step_us, 2), "in_graph_idle_frac": round(idle, 4),
+            "kernels_isolated_ms": {k: round(v, 4) for k, v in iso.items()},
+        }
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import torch as _t
         sec = cpu_reference_sample(B, args.ref_diff_steps)
-        cpu = {"value": B / (sec * DIFF_STEPS), "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+        cpu = {"value": B / (sec * DIFF_STEPS), "unit": UNIT, "cores": host_threads(), "kind": "port",
                "host_cpus": os.cpu_count(),
                "sample": f"{args.ref_diff_steps} of {DIFF_STEPS} diffusion steps at B={B} ({sec:.2f} s each), extrapolated "
                          f"linearly; CLIP text tower excluded"}
 
     if rank == 0:
+        config = workload_config(B, world, args.chain_steps)
+        if strong:
+            config["workload"] = (f"MF-MDM G {ARCH} sampling batch-sharded over {world} B200, {args.sequences} synthetic "
+                                  f"sequences in chains of {B}, T={T_FRAMES}, nobj={NOBJ}, full {args.chain_steps}-step "
+                                  "chains, NCCL gather of outputs (BASELINE.json configs[3])")
+            config["global_batch"] = args.sequences
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "measurement": {"parallelism": (f"dp{world}: contiguous sequence ranges per rank, one NCCL all_gather of the "
+                                            "samples") if world > 1 else "single GPU",
+                            "l2": "256 MB flush between timed steps; step working set 180 MB > 126 MB L2",
+                            "noise": "in-kernel Philox4x32-10", "timing": "CUDA events on the launch stream, max over ranks"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_refine(args):
+    """BASELINE.json configs[2]: MF-MDM R (arch_refine) forward with ManoLayer FK and the hand->object NN query, batch 64,
+    T=160, one object of 8192 points.  A step = one SegmentRefineModel.forward (3 FK + 3 NN + transformer) per rank."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import tamf_b200
+    from tamf_b200 import _lib, synth
+
+    world, rank, local, dev = _dist_setup()
+    L = _lib.lib()
+    B, T, P, nobj = args.batch, T_FRAMES, 8192, 1
+    cfg = synth.ARCH["arch_refine"]
+    m = tamf_b200.SegmentRefineModel("unused", **cfg, use_pc=True,
+                                     mano_assets={"right": synth.mano_assets("right"), "left": synth.mano_assets("left")})
+    m.load_state_dict(synth.r_state_dict(cfg, 0), strict=False)
+    m = m.eval().to(dev)
+    host = synth.make_batch(B, T, nobj=nobj, seed=1 + rank, npoints=P, with_pointcloud=True)
+    batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+    pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        flush.zero_()
+        return m(batch)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = L.tamf_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        out = step()
+    e1.record(stream)
+    barrier()
+    launches = L.tamf_kernel_launch_count() - n0
+    clk = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    assert all(torch.isfinite(v).all() for v in out.values())
+    value = world * B * args.steps / (ms_total * 1e-3)
+    # e2e: host tensors in (pinned), the 13-key dict back on the host
+    keys_in = ("sample_pose_repr", "pose_repr", "shape", "obj_traj", "obj_embedding")
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys_in) + B * nobj * P * 12
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o = m({k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in pinned.items()})
+        host_out = {k: v.cpu() for k, v in o.items()}
+    torch.cuda.synchronize(dev)
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    roof = None
+    if rank == 0:
+        # dominant kernel: the block-pruned hand->object search (3 calls per forward), HBM roofline on the algorithmic bytes
+        from tamf_b200.chamfer import H2OIndex
+        hv = out["sample_hand_verts"].contiguous()
+        traj = batch["obj_traj"].float().contiguous()
+        pts = [np.asarray(o_, np.float32)[: len(l)] for o_, l in zip(batch["obj_pointcloud"], batch["obj_list"])]
+        oix = H2OIndex(pts, dev)
+        dist_t = torch.empty((B, T, 778), device=dev)
+        idx_t = torch.empty((B, T, 778), dtype=torch.int64, device=dev)
+
+        def nn_q():
+            _lib.check(L.tamf_h2o_dist_indexed(_lib.ptr(hv), _lib.ptr(traj), _lib.ptr(oix.index),
+                                               _lib.C.c_void_p(oix.first.data_ptr()), B, T, 778, traj.shape[1], P,
+                                               _lib.ptr(dist_t), _lib.ptr(idx_t), _lib.stream_ptr(dev)), "h2o indexed")
+        for _ in range(3):
+            nn_q()
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a0.record(stream)
+        for _ in range(reps):
+            nn_q()
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        nn_ms = a0.elapsed_time(a1) / reps
+        N = B * T
+        nn_bytes = N * (778 * 12 + 778 * 12 + 36.0) + oix.total_obj * P * 12.0  # SURVEY 8d: 18.7 KB + 36 B per frame
+        pk = peaks()
+        ach = nn_bytes / (nn_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "h2o_pruned_kernel (+ finalize)", "achieved": ach, "peak": pk["hbm"],
+                "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                "launch_ms": nn_ms, "launches_per_step": 3, "share_of_step": 3 * nn_ms / (ms_total / args.steps),
+                "note": "exact block-pruned search: instruction bound (DESIGN.md 4.5), far from the HBM roofline by design"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import tamf_oracle as orc
+        import torch as _t
+        _t.set_num_threads(host_threads())
+        nb = 4
+        sub = {k: (v[:nb] if isinstance(v, (torch.Tensor, list)) else v) for k, v in host.items()}
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.r_forward(synth.r_state_dict(cfg, 0), cfg, sub, synth.mano_assets("right"), synth.mano_assets("left"))
+        sec = time.perf_counter() - t0
+        cpu = {"value": nb / sec, "unit": "sequences/s", "cores": host_threads(), "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": f"{nb} of {B} sequences through the oracle's r_forward ({sec:.1f} s)"}
+    if rank == 0:
+        line = {
+            "metric": "refined motion sequences/sec, SegmentRefineModel forward (3 FK + 3 NN + transformer)", "value": value,
+            "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"MF-MDM G {ARCH}, batch {B} synthetic sequences per GPU, T={T_FRAMES}, nobj={NOBJ}, "
-                                   f"full {args.chain_steps}-step reverse chain (BASELINE.json configs[1])",
-                       "global_batch": world * B, "parallelism": f"dp{world} (batch-sharded chains, NCCL all_gather of "
-                                                                 "the samples)" if world > 1 else "single GPU",
-                       "l2": "256 MB flush between timed steps; step working set 180 MB > 126 MB L2",
-                       "weights": "random init", "noise": "in-kernel Philox4x32-10"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "clocks": clk,
-            "roofline": roof,
-            "cpu_baseline": cpu,
+            "dtype": "f32 (FK, NN) / bf16 (transformer)", "data": "synthetic",
+            "config": {"workload": f"MF-MDM R arch_refine, batch {B} synthetic sequences per GPU, T={T}, {nobj} object x {P} "
+                                   "points, use_pc (BASELINE.json configs[2])", "global_batch": world * B,
+                       "weights": "random init"},
+            "measurement": {"l2": "256 MB flush between timed steps", "timing": "CUDA events on the launch stream"},
+            "e2e": {"value": world * B * args.steps / float(dt.item()), "unit": "sequences/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -370,20 +576,28 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="sample", choices=["sample", "refine"],
+                    help="sample: BASELINE.json configs[1] (the metric); refine: configs[2] (MF-MDM R forward)")
+    ap.add_argument("--sequences", type=int, default=0,
+                    help="> 0: BASELINE.json configs[3] -- a FIXED set of sequences batch-sharded over the ranks (strong scaling)")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--chain-steps", type=int, default=DIFF_STEPS, help="debug only: shorter chains are not the metric")
     ap.add_argument("--ref-diff-steps", type=int, default=24,
                     help="at most this many diffusion steps per timed CPU sample (about 10 s of host work at B=64)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0,
                     help="wall-time budget of the whole reference-arm run; the per-step sample shrinks to fit")
-    ap.add_argument("--profile-reps", type=int, default=10)
+    ap.add_argument("--profile-reps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 1 if args.sequences > 0 else (10 if args.config == "refine" else 3)
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "refine":
+        run_refine(args)
     else:
         run_ours(args)
 

@@ -106,7 +106,11 @@ __device__ __forceinline__ void atc_sts128(uint32_t addr, uint32_t a, uint32_t b
 template <int HD>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmO, int S, int d,
-                   int dbg, long long* trace, long long* ktime) {
+                   int dbg, long long* trace, long long* ktime, const unsigned* rq, unsigned rq_target, unsigned* ra) {
+  // rq / ra (layer-kernel form of the encoder, layer_chain.cuh): instead of waiting for the whole previous grid, the CTA
+  // of sequence b waits until the in_proj tiles of the row tiles its tokens lie in have been stored (rq[row tile] >=
+  // rq_target, bumped by the layer kernel's epilogue warps after their TMA stores completed), and announces its own
+  // output with ra[b] += 1 per 32-row slab (ceil(S / 32) per CTA) once the slab's store has completed.  rq == null: plain programmatic dependency (layer 0).
   // debug only (tools/attn_trace.py): per-CTA clock64 stamps [grid][16]; null in the product path
 #define ATC_TRACE(slot)                                                                                   \
   do {                                                                                                    \
@@ -160,7 +164,25 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
   if (warp == 6) {
     // all lanes run the issue sequence (uniform descriptors / coordinates, see elect_one()); one elected lane issues
     if (elect_one()) {
-      pdl_wait();  // QKV is the previous kernel's output
+      if (rq == nullptr) {
+        pdl_wait();  // QKV is the previous kernel's output
+      } else {
+        const int m0 = (b * S) >> 8, m1 = (b * S + S - 1) >> 8;
+        for (int m = m0; m <= m1; ++m) {
+          unsigned v;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(rq + m) : "memory");
+          if ((int)(v - rq_target) < 0) {
+            const long long t0 = clock64();
+            do {
+              __nanosleep(40);
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(rq + m) : "memory");
+              if (clock64() - t0 > 4000000000LL) __trap();
+            } while ((int)(v - rq_target) < 0);
+          }
+        }
+        // the rows were written by TMA stores and are read by the TMA loads below: order the two proxies behind the acquire
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
       ktime_ready(ktime);
       mbar_arrive_expect_tx(&bars[0], 2 * NB * C::BLK);
 #pragma unroll
@@ -320,7 +342,16 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < NB; ++j) tma_store_3d(&tmO, stage + j * 4096, h * HD + j * 64, row0, b);
         bulk_commit();
-        bulk_wait_read<0>();  // the staging tile must outlive the store's shared-memory reads; kernel end flushes the writes
+        if (ra) {
+          // announce the 32 rows to the layer kernel: the store has completed (its writes are visible to this thread),
+          // release at gpu scope.  One update per storing warp, ceil(S / 32) per CTA; the fence of an early warp runs
+          // under the softmax / PV work of the later ones.
+          bulk_wait<0>();
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(ra + b), "r"(1u) : "memory");
+        } else {
+          bulk_wait_read<0>();  // the staging tile must outlive the store's shared-memory reads; kernel end flushes the writes
+        }
       }
       if (lane == 0 && lq == 0) ATC_TRACE(10 + t);
     }
@@ -360,7 +391,7 @@ int configure_attn_tc() {
 
 template <int HD>
 int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t stream, long long* trace = nullptr,
-                   long long* ktime = nullptr) {
+                   long long* ktime = nullptr, const unsigned* rq = nullptr, unsigned rq_target = 0, unsigned* ra = nullptr) {
   TAMF_REQUIRE(S <= ATC_KP, TAMF_E_BADARG, "attention: at most 176 tokens per sequence");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(H, B);
@@ -377,7 +408,7 @@ int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t
   cfg.attrs = attr;
   cfg.numAttrs = na;
   static const int dbg = getenv("TAMF_ATTN_DBG") ? atoi(getenv("TAMF_ATTN_DBG")) : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel<HD>, m.kv, m.o, S, d, dbg, trace, ktime);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel<HD>, m.kv, m.o, S, d, dbg, trace, ktime, rq, rq_target, ra);
   count_launch();
   if (e != cudaSuccess) {
     set_error(std::string("attention launch failed: ") + cudaGetErrorString(e));

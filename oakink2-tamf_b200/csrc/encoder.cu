@@ -195,15 +195,16 @@ int EncoderStack::upload(DevPool& pool, const tamf_layer_weights* w, int d_, int
 
 // aux layout: [counters | statistics words | schedule (with next in_proj) | schedule (last layer)], 256-byte aligned
 struct ChainLayout {
-  int tiles_m, halves;
+  int M, tiles_m, halves;
   size_t ctr_words, stats_words, off_ctr, off_stats, off_sched, off_schedL, sched_bytes, total;
 };
 static ChainLayout chain_layout(int M, int d, int ff) {
   ChainLayout L{};
+  L.M = M;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   L.tiles_m = (M + 255) / 256;
   L.halves = d / CH_BN;
-  L.ctr_words = (size_t)4 * L.tiles_m + 2;
+  L.ctr_words = (size_t)6 * L.tiles_m + (size_t)L.tiles_m * 256 + 8;  // 6 per-row-tile counters + one word per sequence (<= rows)
   L.stats_words = (size_t)2 * L.tiles_m * L.halves * 2 * 4 * 128;
   L.sched_bytes = al(((size_t)num_sms() / 2 + 1 + (size_t)L.tiles_m * (2 * L.halves + (ff + 3 * d) / CH_BN)) * 4);
   size_t o = 0;
@@ -274,7 +275,8 @@ int EncoderBuffers::make_maps(int d, int ff) {
   pairs = sc.pairs, pairsL = sl.pairs;
   if ((rc = upload_schedule(sched, sc, lay.sched_bytes, nullptr)) || (rc = upload_schedule(schedL, sl, lay.sched_bytes, nullptr)))
     return rc;
-  TAMF_CUDA_CHECK(cudaMemset(ctr, 0, lay.ctr_words * 4));          // counters are monotonic from here on (epoch 0)
+  TAMF_CUDA_CHECK(cudaMemset(ctr, 0, lay.ctr_words * 4));          // (cleared again at the start of every evaluation)
+  ctr_bytes = lay.ctr_words * 4;
   TAMF_CUDA_CHECK(cudaMemset(stats, 0xFF, lay.stats_words * 8));   // "not posted"; every reader resets its word
   return TAMF_OK;
 }
@@ -306,8 +308,17 @@ static void fill_layer_params(LayerParams& p, const EncoderStack& enc, const Enc
   const int pairs = last ? buf.pairsL : buf.pairs;
   p.sched_off = sc, p.sched = sc + pairs + 1;
   p.ctr = buf.ctr, p.stats = buf.stats, p.tiles_m = buf.tiles_m;
+  p.launch_idx = l + 1, p.B = buf.B, p.S = buf.S, p.heads = enc.H;
   p.target_ln = (unsigned)(buf.halves * 2 * GEMM_EPI_WARPS);
   p.target_h = (unsigned)((enc.ff / CH_BN) * 2 * GEMM_EPI_WARPS);
+  p.target_att = (unsigned)(enc.H * ((buf.S + 31) / 32));
+}
+
+// The dependency counters of an evaluation start from zero.  Called ahead of the FIRST kernel of the evaluation (so that the
+// programmatic launch chain between the kernels stays unbroken); everything older has completed (stream order).
+int encoder_begin_evaluation(const EncoderBuffers& buf, cudaStream_t s) {
+  if (buf.chain) TAMF_CUDA_CHECK(cudaMemsetAsync(buf.ctr, 0, buf.ctr_bytes, s));
+  return TAMF_OK;
 }
 
 // Layer-kernel form of the stack (layer_chain.cuh): in_proj(0), then per layer  attention | everything up to the next
@@ -317,6 +328,9 @@ static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& 
   const int d = enc.d, M = buf.M;
   int rc;
   auto kt = [&]() -> long long* { return ktime ? ktime + 4 * ((*kidx)++) : nullptr; };
+  unsigned* r_q = buf.ctr + 5 * buf.tiles_m;   // QKV tiles of a row tile stored (layer kernel, INP units)
+  unsigned* r_att = buf.ctr + 6 * buf.tiles_m;  // attention CTAs of a sequence done
+  const unsigned t_q = (unsigned)((3 * d / CH_BN) * 2 * GEMM_EPI_WARPS);
   {
     const LayerDev& w = enc.layers[0];
     GemmParams p{};
@@ -326,14 +340,21 @@ static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& 
     mark_event(marks, s);
   }
   static const int dbg = getenv("TAMF_CHAIN_DBG") ? atoi(getenv("TAMF_CHAIN_DBG")) : 0;
+  // debug: TAMF_FINE bit 0 = attention waits per sequence (else for the whole previous grid), bit 1 = the layer kernel
+  // starts without a grid-wide wait
+  static const int fine = getenv("TAMF_FINE") ? atoi(getenv("TAMF_FINE")) : 3;
   for (int l = 0; l < enc.L; ++l) {
     const LayerDev& w = enc.layers[l];
     {
       AttnTcMaps at;
       at.kv = buf.tm_att_kv, at.o = buf.tm_att_o;
       long long* k = kt();
-      rc = (d / enc.H == 128) ? launch_attn_tc<128>(at, buf.B, buf.S, enc.H, d, s, nullptr, k)
-                              : launch_attn_tc<64>(at, buf.B, buf.S, enc.H, d, s, nullptr, k);
+      // layer 0 follows the plain in_proj GEMM (grid-wide dependency); later layers wait per sequence for the in_proj
+      // tiles the previous layer kernel stores (l of them per row tile so far)
+      const unsigned* rq = (l && (fine & 1)) ? r_q : nullptr;
+      const unsigned tq = (unsigned)l * t_q;
+      rc = (d / enc.H == 128) ? launch_attn_tc<128>(at, buf.B, buf.S, enc.H, d, s, nullptr, k, rq, tq, r_att)
+                              : launch_attn_tc<64>(at, buf.B, buf.S, enc.H, d, s, nullptr, k, rq, tq, r_att);
       if (rc) return rc;
       mark_event(marks, s);
     }
@@ -341,6 +362,7 @@ static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& 
     LayerParams p{};
     fill_layer_params(p, enc, buf, l);
     p.dbg = dbg;
+    p.grid_wait = !(fine & 2);
     p.ktime = kt();
     if (l == g_dbg_trace_layer) p.trace = g_dbg_trace;
     LayerMaps tm{&buf.tm_ATT128, &w.tm_out, &buf.tm_Xb, &buf.tm_Xlo128, &w.tm_w1, &buf.tm_H_st, &buf.tm_H128, &w.tm_w2,
@@ -462,14 +484,19 @@ extern "C" int tamf_layer_run(const uint16_t* att, const uint16_t* w_out, const 
   unsigned long long* stats = reinterpret_cast<unsigned long long*>(a + lay.off_stats);
   TAMF_CUDA_CHECK(cudaMemsetAsync(ctr, 0, lay.ctr_words * 4, stream));
   TAMF_CUDA_CHECK(cudaMemsetAsync(stats, 0xFF, lay.stats_words * 8, stream));
+  const unsigned one = 1u;  // the attention output is given: one "sequence" covering every row, announced by one "CTA"
+  TAMF_CUDA_CHECK(cudaMemcpyAsync(ctr + 6 * lay.tiles_m, &one, 4, cudaMemcpyHostToDevice, stream));
+  TAMF_CUDA_CHECK(cudaStreamSynchronize(stream));
   LayerParams p{};
   p.M = M, p.d = d, p.ff = ff, p.n_inp = n_inp;
+  p.launch_idx = 1, p.B = 1, p.S = M > 0 ? M : 1, p.heads = 1;
   p.bias[CK_LN1] = ln_params, p.gamma[0] = ln_params + d, p.beta[0] = ln_params + 2 * d;
   p.bias[CK_LN2] = ln_params + 3 * d, p.gamma[1] = ln_params + 4 * d, p.beta[1] = ln_params + 5 * d;
   p.bias[CK_L1] = b1, p.bias[CK_INP] = b_in;
   p.sched_off = sched, p.sched = sched + sc.pairs + 1;
   p.ctr = ctr, p.stats = stats, p.tiles_m = lay.tiles_m;
   p.target_ln = (unsigned)(lay.halves * 2 * GEMM_EPI_WARPS), p.target_h = (unsigned)((ff / CH_BN) * 2 * GEMM_EPI_WARPS);
+  p.target_att = 1u;
   p.trace = trace;
   LayerMaps tm{&tATT, &tWo, &tXh, &tXl, &tW1, &tHst, &tH, &tW2, n_inp ? &tWin : nullptr, n_inp ? &tQst : nullptr, &tXhs,
                &tXls, &tI};

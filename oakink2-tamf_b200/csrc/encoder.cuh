@@ -61,7 +61,8 @@ struct EncoderBuffers {
   CUtensorMap tm_Xlo128;              // low residual plane, box {64, 128} (the high plane is tm_Xb)
   CUtensorMap tm_Xh_st, tm_Xl_st;     // residual planes, box {64, 32}: LayerNorm result stores
   CUtensorMap tm_ident;               // 64 x 64 identity (layer_chain.cuh chain_identity_map)
-  unsigned* ctr = nullptr;            // [4][tiles_m] + done + epoch
+  unsigned* ctr = nullptr;            // [6][tiles_m] row-tile counters + [B] sequence counters (layer_chain.cuh)
+  size_t ctr_bytes = 0;
   unsigned long long* stats = nullptr;  // [2][tiles_m][halves][2][4][128] row statistics words
   int tiles_m = 0, halves = 0;
   int *sched = nullptr, *schedL = nullptr;  // [pairs + 1 offsets | unit codes]: with / without the next in_proj
@@ -75,6 +76,8 @@ size_t encoder_aux_bytes(int M, int d, int ff);
 // `ktime` (profiling only): in-graph timing slots, 4 int64 per kernel in launch order starting at slot *kidx.
 int enqueue_encoder(const EncoderStack& enc, const EncoderBuffers& buf, cudaStream_t s,
                     std::vector<cudaEvent_t>* marks, long long* ktime = nullptr, int* kidx = nullptr);
+// Clears the dependency counters of the layer kernels: enqueue ahead of the first kernel of every evaluation.
+int encoder_begin_evaluation(const EncoderBuffers& buf, cudaStream_t s);
 int configure_encoder_kernels();  // cudaFuncSetAttribute for every instantiation used above (once per process)
 
 // ---- small fp32 helpers (conditioning path, once per sample) ----

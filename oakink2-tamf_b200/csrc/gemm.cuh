@@ -82,6 +82,7 @@ struct GemmParams {
   const int* t_ptr;    // [B]
   const float *c1, *c2, *sigma;  // [num_steps] fp32
   unsigned long long seed;
+  const unsigned long long* seed_ptr;  // non-null: the Philox seed is read from device memory (one graph for every chain)
   int nfeat;
   // host pointers to the TMA-store maps (copied into kernel parameters by launch_gemm):
   //   tmC: bf16 output [M,N], box {64 cols, 32 rows} (bias/GELU/SiLU epilogues) | Xb [M,N], box {32, ln_rq} (LN)
@@ -513,7 +514,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       [[maybe_unused]] float xt[32];
       [[maybe_unused]] float post_k1 = 0.f, post_k2 = 0.f, post_sg = 0.f;
       [[maybe_unused]] int pt = 0;
+      [[maybe_unused]] unsigned long long post_seed = 0;
       if constexpr (EPI == EPI_POSTERIOR) {
+        post_seed = p.seed_ptr ? *p.seed_ptr : p.seed;
         static_assert(EPI != EPI_POSTERIOR || CHUNKS == 1, "the posterior epilogue handles one 32-column chunk per warp");
         const int c0 = n0 + cq * QW;
         const int b = row / p.S, s = row % p.S;
@@ -856,7 +859,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               for (int j = 0; j < 32; j += 4) {
                 float eps[4] = {0.f, 0.f, 0.f, 0.f};
                 if (p.x_out && !p.noise && c0 + j < p.nfeat)
-                  philox_normal4(p.seed, (uint32_t)t, frame, (uint32_t)((c0 + j) >> 2), eps);
+                  philox_normal4(post_seed, (uint32_t)t, frame, (uint32_t)((c0 + j) >> 2), eps);
 #pragma unroll
                 for (int e4 = 0; e4 < 4; ++e4) {
                   const int f = c0 + j + e4;

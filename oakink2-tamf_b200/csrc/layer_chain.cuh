@@ -28,8 +28,11 @@
 //     COMPLETED (relaxed update after cp.async.bulk.wait_group: the rows are in L2, where TMA loads read; the waiting
 //     scout warp acquires).  Every pair's list is a subsequence of ONE global topological order and all CTAs of the
 //     grid are co-resident (grid <= SM count, 1 CTA / SM), so the schedule cannot deadlock; every spin is bounded (trap).
-//   * self-contained sync state: a statistics word is reset by its single reader; the counters are monotonic and compared
-//     against (epoch + 1) x target, the epoch is bumped by the last CTA of every launch.
+//   * the same counters replace the grid-wide dependency between this kernel and the attention kernels on both sides: an LN1
+//     unit waits for the attention CTAs of the sequences overlapping its row tile, an attention CTA for the in_proj tiles
+//     of its sequence (attn_tc.cuh) -- the ragged tail of one kernel overlaps the head of the next;
+//   * sync state: a statistics word is reset by its single reader; the counters are cleared once per denoiser evaluation
+//     and launch number l waits for l x target.
 #pragma once
 #include <algorithm>
 #include <map>
@@ -49,19 +52,23 @@ struct LayerParams {
   const float *gamma[2], *beta[2];    // norm1, norm2 [d]
   const int* sched_off;               // [pairs + 1]
   const int* sched;                   // unit codes: kind << 28 | row tile << 8 | column tile
-  // counters [4][tiles_m] + [2]: 0 LN1 high plane stored | 1 LN1 low plane stored | 2 H tiles stored | 3 LN2 high plane
-  // stored (each counts epilogue warps, MONOTONIC over launches: a launch waits for (epoch + 1) x target, compared
-  // modulo 2^32); then the number of CTAs of the running launch that have finished, and the epoch (bumped by the last
-  // CTA of every launch).  Nothing is ever reset, so a counter update still in flight when a launch ends is harmless.
+  // counters [6][tiles_m] then [B]: 0 LN1 high plane stored | 1 LN1 low plane stored | 2 H tiles stored | 3 LN2 high plane
+  // stored | 4 LN2 low plane stored | 5 QKV tiles stored (each counts epilogue warps) | attention CTAs of a sequence that
+  // have stored their output.  All are cleared once per denoiser evaluation (a memset node ahead of the first kernel) and
+  // only grow afterwards: launch number `launch_idx` (1-based within the evaluation) waits for launch_idx x target.
   unsigned* ctr;
   int tiles_m;
+  int launch_idx;                     // 1-based index of this layer kernel within the evaluation
+  int B, S, heads;                    // sequences, tokens per sequence, attention CTAs per sequence
   unsigned target_ln, target_h;       // halves * 32 warps | (ff / 256) * 32 warps
   // statistics words [2 LN][tiles_m][halves][2 ranks][4 reader copies][128 rows]: (sum | sum of squares << 32) over the
   // CTA's 256 columns of a row; all-ones = not posted (the word is its own flag; its reader resets it)
   unsigned long long* stats;
   long long* trace;                   // debug only: [grid][GEMM_TRACE_SLOTS] clock64 stamps
   long long* ktime;                   // debug only: in-graph timing slots of this launch (common.cuh ktime_*)
+  unsigned target_att;  // updates of rA[b] per layer: heads x ceil(S / 32) (attn_tc.cuh, one per stored 32-row slab)
   int dbg;
+  int grid_wait;  // debug: wait for the whole previous grid instead of relying on the per-unit dependencies alone
 };
 
 // 20 warps = 5 warpgroups: 16 epilogue warps, then one warpgroup with the TMA producer (16), the MMA issuer (17), the
@@ -75,6 +82,7 @@ constexpr int CH_STAGE_BYTES = CH_A_BYTES + CH_B_BYTES;
 constexpr int CH_PIPE_BYTES = CH_STAGES * CH_STAGE_BYTES;
 constexpr int CH_STG_BYTES = GEMM_EPI_WARPS * GEMM_STG_WARP;
 constexpr int CH_IDENT_BYTES = 32 * 128;  // this CTA's 32 rows of the 64 x 64 bf16 identity (K-major, 128-byte swizzle)
+constexpr int CH_SIG_BARS = 16;           // output-signal barriers of a CTA in flight (a warp runs < 2 units = 4 signals ahead)
 constexpr int CH_RES_KB = 4;              // residual ring stages of a LayerNorm unit: 2 planes x 2 stages, each holding
                                           // TWO 64-column blocks (A slot, B slot) -- the ring is latency bound per stage
 constexpr int CH_CTRL_BYTES = 1024;
@@ -138,6 +146,11 @@ __device__ __forceinline__ long long chain_globaltimer() {
   do {                                                                                                           \
     if (p.trace && (slot) < GEMM_TRACE_SLOTS) p.trace[(size_t)blockIdx.x * GEMM_TRACE_SLOTS + (slot)] = clock64(); \
   } while (0)
+// per-unit stamps: units 0..7 of a pair own slots 4..51 (6 each); slots 52..63 are the special stamps
+#define CHAIN_TRACE_UNIT(k, it)                 \
+  do {                                          \
+    if ((it) < 8) CHAIN_TRACE(4 + (k) + 6 * (it)); \
+  } while (0)
 
 // Tensor maps.  tmATT / tmH / tmXh / tmXl: A operands [M, K] with box {64, 128} (tmXh = Xb is the A operand of L1 and INP
 // AND the high residual plane, tmXl = Xlo the low one); tmWo / tmW1 / tmW2 / tmWin: weights [N, K], box {64, 128};
@@ -168,6 +181,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   uint64_t* ident_bar = tempty_bar + 2;                     // [1]      identity tile landed (leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_bar + 1);
   uint32_t* s_dep = tmem_slot + 1;  // units whose dependencies the scout warp has seen satisfied
+  uint64_t* sig_bar = reinterpret_cast<uint64_t*>(s_dep + 1);  // [CH_SIG_BARS] output signals owed by this CTA (signal warp)
   float* s_ln = reinterpret_cast<float*>(ctrl + CH_CTRL_BYTES);  // [2 LN][bias | gamma | beta][256]
   float* s_bias2 = s_ln + 6 * BN;           // [16 warps][64]
   float* s_stat = s_bias2 + PW * 64;        // [2 buffers][sum, sq][4 column quarters][128 rows]
@@ -208,6 +222,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       mbar_init(&tempty_bar[a], PW * 2);  // one elected lane per epilogue warp of both CTAs
     }
     mbar_init(ident_bar, 1);
+    for (int i = 0; i < CH_SIG_BARS; ++i) mbar_init(&sig_bar[i], PW);  // one elected lane per epilogue warp of this CTA
     *s_dep = 0u;
     fence_mbar_init();
   }
@@ -228,7 +243,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   }
   if (threadIdx.x == 0) CHAIN_TRACE(1);
   pdl_launch_dependents();
-  pdl_wait();  // everything the previous kernels wrote (activations, the cleared sync words) is visible from here on
+  if (p.grid_wait) pdl_wait();
+  // NO grid-wide dependency wait: every unit waits for exactly the rows it reads (scout warp below).  The first units
+  // (LN1) wait for the attention CTAs of the sequences that overlap their row tile, so this kernel starts on the SMs the
+  // attention kernel has left while its last CTAs are still running; everything older is ordered transitively (an
+  // attention CTA started only after the in_proj tiles of its sequence, those after LN2 of their row tiles, ...).
   if (threadIdx.x == 0) {
     CHAIN_TRACE(2);
     CHAIN_TRACE_NS(56);  // globaltimer (ns) when the dependency wait ended: the common time base across SMs
@@ -254,18 +273,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       const CUtensorMap* tb = kind == CK_LN1 ? &tmWo : (kind == CK_L1 ? &tmW1 : (kind == CK_LN2 ? &tmW2 : &tmWin));
       const int num_kb = (kind == CK_LN2 ? p.ff : p.d) / 64;
       const int total_kb = num_kb + ((kind & 1) ? 0 : CH_RES_KB);
-      if (kind != CK_LN1) {  // in-kernel dependencies: the scout warp has seen the counters of this unit
+      {  // dependencies: the scout warp has seen the counters of this unit
         uint32_t seen;
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_dep)) : "memory");
         if (seen < (uint32_t)(it + 1)) {
           const long long t0 = clock64();
           do {
+            __nanosleep(100);  // the board runs at its power limit: a busy spin on all 148 SMs is paid for in clock
             asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_dep)) : "memory");
             if (clock64() - t0 > 4000000000LL) __trap();
           } while (seen < (uint32_t)(it + 1));
         }
       }
-      if (lane == 0) CHAIN_TRACE(4 + 6 * it);
+      if (lane == 0) CHAIN_TRACE_UNIT(0, it);
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait_q(&empty_bar[stage], phase ^ 1u);
         uint8_t* a_dst = sA + stage * CH_A_BYTES;
@@ -289,7 +309,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         __syncwarp();
         if (++stage == STAGES) stage = 0, phase ^= 1u;
       }
-      if (lane == 0) CHAIN_TRACE(5 + 6 * it);
+      if (lane == 0) CHAIN_TRACE_UNIT(1, it);
     }
    } else if (warp == PW + 1) {
     // ===================== MMA issuer (leader CTA) =====================
@@ -315,7 +335,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait_q(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0 && kb == 0) CHAIN_TRACE(6 + 6 * it);
+          if (lane == 0 && kb == 0) CHAIN_TRACE_UNIT(2, it);
           const uint32_t a_addr = smem_u32(sA + stage * CH_A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * CH_B_BYTES);
           if (kb < num_kb) {
@@ -343,7 +363,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1u;
         }
-        if (lane == 0) CHAIN_TRACE(7 + 6 * it);
+        if (lane == 0) CHAIN_TRACE_UNIT(3, it);
         if (++acc == 2) acc = 0, acc_phase ^= 1u;
       }
     }
@@ -354,25 +374,57 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     // polling and fencing in the producer itself drained the ring at every unit boundary (+2 k cycles per tile,
     // measured).  No proxy fence: a counter is bumped only after the TMA stores have COMPLETED in L2, which is where the
     // producer's TMA loads read (no L1 in that path, nothing can be stale).
-    const unsigned epoch1 = p.ctr[4 * tiles_m + 1] + 1u;  // written by the last CTA of the previous launch
-    const unsigned t_ln = epoch1 * p.target_ln, t_h = epoch1 * p.target_h;
+    const unsigned li = (unsigned)p.launch_idx;
+    const unsigned t_ln = li * p.target_ln, t_h = li * p.target_h;
+    const unsigned* r_att = p.ctr + 6 * tiles_m;
     int it = 0;
     for (int ui = u_begin; ui < u_end; ++ui, ++it) {
       const int code = p.sched[ui];
       const int kind = code >> 28, m = (code >> 8) & 0xFFFFF;
-      if (kind == CK_L1) {
+      if (kind == CK_LN1) {
+        // the attention output of every sequence that overlaps the row tile, and the previous layer's LN2 low plane
+        const int b0 = (m * 256) / p.S, b1 = min(p.B - 1, (m * 256 + 255) / p.S);
+        for (int b = b0; b <= b1; ++b) chain_wait_ge(r_att + b, li * p.target_att);
+        chain_wait_ge(p.ctr + 4 * tiles_m + m, (li - 1u) * p.target_ln);
+      } else if (kind == CK_L1) {
         chain_wait_ge(p.ctr + 0 * tiles_m + m, t_ln);  // LN1 high plane of the row tile
       } else if (kind == CK_LN2) {
         chain_wait_ge(p.ctr + 2 * tiles_m + m, t_h);   // every H tile of the row tile
         chain_wait_ge(p.ctr + 1 * tiles_m + m, t_ln);  // LN1 low plane (the residual of this unit)
-      } else if (kind == CK_INP) {
+      } else {
         chain_wait_ge(p.ctr + 3 * tiles_m + m, t_ln);  // LN2 high plane
       }
-      if (kind != CK_LN1 && lane == 0 && p.trace && p.trace[(size_t)blockIdx.x * GEMM_TRACE_SLOTS + 54] == 0)
+      if (kind == CK_L1 && lane == 0 && p.trace && p.trace[(size_t)blockIdx.x * GEMM_TRACE_SLOTS + 54] == 0)
         CHAIN_TRACE_NS(54);
-      if (lane == 0)
+      if (lane == 0) {
+        // the unit's inputs were written through the async proxy (TMA stores) and will be read through it (TMA loads of
+        // the producer warp): the acquire above orders generic accesses only
+        asm volatile("fence.proxy.async;" ::: "memory");
         asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(s_dep)), "r"((uint32_t)(it + 1)) : "memory");
+      }
       __syncwarp();
+    }
+   } else {
+    // ===================== signal warp =====================
+    // Walks the unit list behind the epilogue warps: per output signal (LN unit: high plane, then low plane; L1 / INP
+    // unit: its tile) waits until all 16 epilogue warps of this CTA have seen their TMA stores complete
+    // (cp.async.bulk.wait_group: the writes are visible to the waiting thread; its barrier arrival releases that to this
+    // warp), then publishes with a gpu-scope release: fence + counter update (cumulative over the 16 warps' stores).
+    // Without the fence the dependents occasionally read stale rows (1 evaluation in ~300 at the production shape).
+    uint32_t seq = 0;
+    for (int ui = u_begin; ui < u_end; ++ui) {
+      const int code = p.sched[ui];
+      const int kind = code >> 28, m = (code >> 8) & 0xFFFFF;
+      const int nsig = (kind & 1) ? 1 : 2;
+      for (int j = 0; j < nsig; ++j, ++seq) {
+        const int c = kind == CK_LN1 ? j : (kind == CK_L1 ? 2 : (kind == CK_LN2 ? 3 + j : 5));
+        mbar_wait_q(&sig_bar[seq & (CH_SIG_BARS - 1)], (seq / CH_SIG_BARS) & 1u);
+        if (lane == 0) {
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          red_relaxed_gpu_add(p.ctr + c * tiles_m + m, (unsigned)PW);
+        }
+        __syncwarp();
+      }
     }
    }
   } else {
@@ -400,16 +452,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     const int cl = cq * 64;  // first column of this warp's slab inside the 256-column tile
     uint32_t acc = 0, acc_phase = 0, ln_count = 0;
     int staged_key = -1;
-    unsigned* pending = nullptr;  // counter to bump once this warp's TMA stores in flight have completed
+    // Output signals.  Every output of a unit (LN: high plane, low plane; L1 / INP: the tile) is announced to the units
+    // that read it by a counter update with RELEASE semantics at gpu scope -- a gpu-scope fence takes 1.5-3 k cycles
+    // here, so the epilogue warps do not execute it: the elected lane of a warp waits for ITS TMA stores to complete and
+    // arrives on the CTA's barrier of that signal (numbered in unit order, the same in all 16 warps); the signal warp
+    // collects the 16 arrivals, fences and bumps the counter (below).  `pending`: a signal whose stores are still in
+    // flight; it is handed over before the warp blocks on anything that may depend on it.
+    bool pending = false;
+    uint32_t sig_seq = 0, pending_seq = 0;
     // A warp never blocks while it owes a signal: the signal is flushed before any wait that may depend on it.
     auto flush_pending = [&]() {
-      if (pending != nullptr) {
+      if (pending) {
         if (elect_one()) {
           bulk_wait<0>();
-          red_relaxed_gpu_add(pending, 1u);
+          mbar_arrive(&sig_bar[pending_seq & (CH_SIG_BARS - 1)]);
         }
         __syncwarp();
-        pending = nullptr;
+        pending = false;
       }
     };
     int it = 0;
@@ -443,7 +502,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         mbar_wait_q(&tfull_bar[acc], acc_phase);
       }
       tc_fence_after();
-      if (threadIdx.x == 0) CHAIN_TRACE(8 + 6 * it);
+      if (threadIdx.x == 0) CHAIN_TRACE_UNIT(4, it);
       uint32_t v0[32], v1[32];
       tmem_ld32(taddr, v0);
       tc_wait_ld_dep(v0);
@@ -517,7 +576,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         const float nmr = -mean * rstd;
         // ---- pass 2: normalise + affine, hi plane -> staging -> TMA store, then lo plane ----
-        if (pending != nullptr) {
+        if (pending) {
           flush_pending();  // (also: the previous unit's store has finished reading the staging tile)
         } else {
           if (elect_one()) bulk_wait_read<0>();
@@ -585,16 +644,20 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
             CHAIN_TRACE(62);
             CHAIN_TRACE_NS(55);
           }
-          red_relaxed_gpu_add(p.ctr + (ln ? 3 : 0) * tiles_m + m, 1u);
+          if (p.trace && it == 0)  // latest warp of this CTA to have its hi plane complete (ns)
+            atomicMax(reinterpret_cast<unsigned long long*>(p.trace + (size_t)blockIdx.x * GEMM_TRACE_SLOTS + 53),
+                      (unsigned long long)chain_globaltimer());
+          mbar_arrive(&sig_bar[sig_seq & (CH_SIG_BARS - 1)]);
         }
         __syncwarp();
-        // the low plane of LN1 is the residual input of this row tile's LN2 units: owed once the store has completed
-        // (LN2's low plane is only read by the next kernel and completes before this CTA retires)
-        if (ln == 0) pending = p.ctr + 1 * tiles_m + m;
+        // the low plane is the residual input of the next LayerNorm of this row tile (LN2 here, LN1 of the next layer
+        // kernel): owed once the store has completed
+        pending = true, pending_seq = sig_seq + 1;
+        sig_seq += 2;
       } else {
         // ---------------- bias (+ GELU) -> bf16: the warp's 32 x 64 slab leaves as one TMA store ----------------
         const float* wb = s_bias2 + warp * 64;
-        if (pending != nullptr) {
+        if (pending) {
           flush_pending();
         } else {
           if (elect_one()) bulk_wait_read<0>();  // the previous unit's store has finished reading the staging tile
@@ -640,10 +703,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           tma_store_2d(kind == CK_L1 ? &tmHst : &tmQst, wst, n0 + cl, grow0);  // rows past M are clipped
           bulk_commit();
         }
-        // an H tile is an input of this row tile's LN2 units: owed once the store has completed
-        if (kind == CK_L1) pending = p.ctr + 2 * tiles_m + m;
+        // an H tile is an input of this row tile's LN2 units, a QKV tile of the attention CTAs of the next layer: owed
+        // once the store has completed
+        pending = true, pending_seq = sig_seq;
+        sig_seq += 1;
       }
-      if (threadIdx.x == 0) CHAIN_TRACE(9 + 6 * it);
+      if (threadIdx.x == 0) CHAIN_TRACE_UNIT(5, it);
       if (++acc == 2) acc = 0, acc_phase ^= 1u;
     }
     flush_pending();
@@ -654,12 +719,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   if (threadIdx.x == 0) {
     CHAIN_TRACE(3);
     ktime_exit(p.ktime);
-    // every wait of this CTA is behind it: the last CTA of the grid opens the next epoch
-    unsigned* done = p.ctr + 4 * tiles_m;
-    if (atomicAdd(done, 1u) == gridDim.x - 1) {
-      *done = 0u;
-      p.ctr[4 * tiles_m + 1] += 1u;
-    }
   }
   if (warp == PW + 1) {
     tc_fence_after();

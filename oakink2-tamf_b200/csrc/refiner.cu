@@ -238,6 +238,7 @@ extern "C" int tamf_refiner_forward(tamf_refiner* h, const float* sample_pose_re
   const int d = h->d, B = h->B, T = h->T, S = h->S, M = h->M, Mf = h->Mf;
   const tamf_cfg& c = h->cfg;
   int rc;
+  if ((rc = encoder_begin_evaluation(h->buf, s))) return rc;
   // ---- conditioning (hand_shape_process :300-301, obj_embed_process :260-261, obj_input_process :243-246) ----
   if ((rc = mean_axis(shape, h->shapemean, B, T, c.hand_shape_dim, s))) return rc;
   if ((rc = mean_axis(obj_emb, h->embmean, B, nobj_max, c.obj_embed_dim, s))) return rc;

@@ -38,9 +38,11 @@ for name, z in zip(("layer kernel: LN1 -> L1 -> LN2 -> INP",), tr):
     done = live[:, 55][live[:, 55] != 0] - t0
     seen = live[:, 54][live[:, 54] != 0] - t0
     if len(done) and len(seen):
+        last = live[:, 53][live[:, 53] != 0] - t0
         print(f"   globaltimer ns after the earliest dependency-wait end: pdl-wait end spread {int((live[:, 56] - t0).max())}; "
               f"first-LN hi plane complete (warp 0) min/median/max {int(done.min())}/{int(np.median(done))}/{int(done.max())}; "
-              f"first phase-2 ready seen min/median/max {int(seen.min())}/{int(np.median(seen))}/{int(seen.max())}")
+              f"(slowest warp of a CTA) min/median/max {int(last.min())}/{int(np.median(last))}/{int(last.max())}; "
+              f"first dependent unit cleared by the scout min/median/max {int(seen.min())}/{int(np.median(seen))}/{int(seen.max())}")
     for cta in (0, 1, 2, 18, 20, 21, 72, 146, 147):
         r = t[cta]
         if r[0] == 0:

@@ -12,6 +12,6 @@ except Exception as e: print("$tag failed", e)
 PY
 }
 run default X=1
-run slack0 TAMF_CHAIN_SLACK=0
-run slack12k TAMF_CHAIN_SLACK=12000
+run pdl0 TAMF_PDL=0
+
 run nochain TAMF_CHAIN=0
