@@ -474,6 +474,8 @@ def run_refine(args):
     def step():
         flush.zero_()
         return m(batch)
+    # the first forwards of a process pay allocator growth and lazy kernel loading (36 ms, then 16 ms: tools/diag_refine.py)
+    args.warmup = max(args.warmup, 5)
     for _ in range(args.warmup):
         step()
     barrier()
