@@ -542,7 +542,7 @@ def run_refine(args):
         roof = {"bound": "hbm", "kernel": "h2o_pruned_kernel (+ finalize)", "achieved": ach, "peak": pk["hbm"],
                 "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
                 "launch_ms": nn_ms, "launches_per_step": 3, "share_of_step": 3 * nn_ms / (ms_total / args.steps),
-                "note": "exact block-pruned search: instruction bound (DESIGN.md 4.5), far from the HBM roofline by design"}
+                "note": "exact block-pruned search: instruction bound (DESIGN.md 4.6), far from the HBM roofline by design"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import tamf_oracle as orc

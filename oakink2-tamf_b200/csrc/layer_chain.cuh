@@ -19,14 +19,19 @@
 //     whatever its length -- they delayed the mainloop's own loads), no staging traffic;
 //   * a 512-wide LayerNorm row is computed by TWO pairs (column halves, pairs 2k and 2k + 1): each keeps its 128 x 256
 //     slab of y = acc + b in REGISTERS (64 per thread), the halves swap per-row (sum, sum of squares) through L2 as one
-//     64-bit word per row that is its own flag (no fences: a gpu-scope fence costs 1.5 - 3 k cycles), all 148 SMs store;
+//     64-bit word per row that carries the data AND is its own flag (relaxed 64-bit accesses, nothing else to order: a
+//     gpu-scope fence costs 1.5 - 3 k cycles), all 148 SMs store;
 //   * the four stages form a dependency chain PER ROW TILE (LN1 -> L1 -> LN2 -> INP) and row tiles are independent, so a
 //     host-built static schedule (list scheduling of the DAG on a two-resource model of a pair: tensor pipe + epilogue
 //     warps) interleaves the units of different row tiles: the ~10 k cycles between the last MMA of a LayerNorm unit and
 //     the moment its rows are in L2 are filled with other row tiles' work instead of idling every SM twice per layer.
-//     A unit waits for a per-row-tile counter that the producing epilogue warps bump after their TMA stores have
-//     COMPLETED (relaxed update after cp.async.bulk.wait_group: the rows are in L2, where TMA loads read; the waiting
-//     scout warp acquires).  Every pair's list is a subsequence of ONE global topological order and all CTAs of the
+//     A unit waits for a per-row-tile counter.  Publishing: an epilogue warp's elected lane waits for ITS TMA stores
+//     (cp.async.bulk.wait_group: the writes are then visible to that thread) and arrives on a CTA-local mbarrier; the
+//     signal warp collects the 16 arrivals and performs ONE gpu-scope release (fence.acq_rel.gpu + counter update).
+//     Consuming: the scout warp polls with ld.acquire.gpu, issues fence.proxy.async (the data is read by TMA = async
+//     proxy) and clears the unit for the TMA producer warp through shared memory.  (A relaxed update without the fence
+//     let 1 evaluation in ~270 read stale rows at the production shape: profiles/r02_exp_release_signals.txt.)
+//     Every pair's list is a subsequence of ONE global topological order and all CTAs of the
 //     grid are co-resident (grid <= SM count, 1 CTA / SM), so the schedule cannot deadlock; every spin is bounded (trap).
 //   * the same counters replace the grid-wide dependency between this kernel and the attention kernels on both sides: an LN1
 //     unit waits for the attention CTAs of the sequences overlapping its row tile, an attention CTA for the in_proj tiles
@@ -53,8 +58,8 @@ struct LayerParams {
   const int* sched_off;               // [pairs + 1]
   const int* sched;                   // unit codes: kind << 28 | row tile << 8 | column tile
   // counters [6][tiles_m] then [B]: 0 LN1 high plane stored | 1 LN1 low plane stored | 2 H tiles stored | 3 LN2 high plane
-  // stored | 4 LN2 low plane stored | 5 QKV tiles stored (each counts epilogue warps) | attention CTAs of a sequence that
-  // have stored their output.  All are cleared once per denoiser evaluation (a memset node ahead of the first kernel) and
+  // stored | 4 LN2 low plane stored | 5 QKV tiles stored (each counts epilogue warps) | rA[b]: 32-row slabs of sequence
+  // b the attention kernel has stored.  All are cleared once per denoiser evaluation (a memset node ahead of the first kernel) and
   // only grow afterwards: launch number `launch_idx` (1-based within the evaluation) waits for launch_idx x target.
   unsigned* ctr;
   int tiles_m;
@@ -72,7 +77,7 @@ struct LayerParams {
 };
 
 // 20 warps = 5 warpgroups: 16 epilogue warps, then one warpgroup with the TMA producer (16), the MMA issuer (17), the
-// dependency scout (18) and an idle warp, so that register reallocation (setmaxnreg) always involves whole warpgroups.
+// dependency scout (18) and the signal warp (19); register reallocation (setmaxnreg) always involves whole warpgroups.
 constexpr int CH_THREADS = GEMM_EPI_THREADS + 128;
 constexpr int CH_STAGES = 4;
 constexpr int CH_BN = 256;

@@ -64,6 +64,16 @@ def betas_for_alpha_bar(num_diffusion_timesteps, alpha_bar, max_beta=0.999):
     return np.array([min(1 - alpha_bar((i + 1) / n) / alpha_bar(i / n), max_beta) for i in range(n)])
 
 
+def _x_T(shape, device, seed):
+    """x_T = th.randn(*shape) (gaussian_diffusion.py:604): torch's global generator like the reference, or -- when the
+    caller passes a chain seed -- a generator seeded with it, so that a seeded chain is reproducible end to end."""
+    if seed is None:
+        return torch.randn(*shape, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed) & 0x7FFFFFFFFFFFFFFF)
+    return torch.randn(*shape, device=device, generator=g)
+
+
 class GaussianDiffusion:
     """Schedule tables in float64 exactly as GaussianDiffusion.__init__ (gaussian_diffusion.py:116-161), after the
     respacing SpacedDiffusion applies (respace.py:69-83): `use_timesteps` = the original steps to keep (None = all)."""
@@ -182,7 +192,7 @@ class GaussianDiffusion:
         if device is None:
             device = next(model.parameters()).device
         assert isinstance(shape, (tuple, list))
-        img = noise.to(device) if noise is not None else torch.randn(*shape, device=device)
+        img = noise.to(device) if noise is not None else _x_T(shape, device, seed)
         if skip_timesteps and init_image is None:
             init_image = torch.zeros_like(img)
         t_first = self.num_timesteps - skip_timesteps - 1
@@ -221,7 +231,7 @@ class GaussianDiffusion:
         if device is None:
             device = next(model.parameters()).device
         assert isinstance(shape, (tuple, list))
-        img = noise.to(device) if noise is not None else torch.randn(*shape, device=device)
+        img = noise.to(device) if noise is not None else _x_T(shape, device, seed)
         if skip_timesteps and init_image is None:
             init_image = torch.zeros_like(img)
         t_first = self.num_timesteps - skip_timesteps - 1

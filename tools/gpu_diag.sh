@@ -1,8 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for mode in default fine0 fine1 fine2 nochain default; do
-  case $mode in default) E="";; fine0) E="TAMF_FINE=0";; fine1) E="TAMF_FINE=1";; fine2) E="TAMF_FINE=2";; nochain) E="TAMF_CHAIN=0";; esac
-  echo "== $mode" >> gpurun_out/diag.log
-  env $E timeout 300 python tools/diag_refine.py >> gpurun_out/diag.log 2>&1
+for cfg in "arch_mdm 5 24" "arch_mdm 1 171" "arch_mdm 64 160" "arch_mdm_l 3 40"; do
+  set -- $cfg
+  for E in "" "TAMF_CHAIN=0"; do
+    echo "== $cfg $E" >> gpurun_out/diag.log
+    env $E DIAG_ARCH=$1 DIAG_B=$2 DIAG_T=$3 DIAG_N=3000 timeout 300 python tools/diag_repeat.py 2>&1 | tail -3 >> gpurun_out/diag.log
+  done
 done
 cat gpurun_out/diag.log
