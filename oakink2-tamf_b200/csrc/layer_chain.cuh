@@ -277,33 +277,39 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       const CUtensorMap* ta = kind == CK_LN1 ? &tmATT : (kind == CK_LN2 ? &tmH : &tmXh);
       const CUtensorMap* tb = kind == CK_LN1 ? &tmWo : (kind == CK_L1 ? &tmW1 : (kind == CK_LN2 ? &tmW2 : &tmWin));
       const int num_kb = (kind == CK_LN2 ? p.ff : p.d) / 64;
-      const int total_kb = num_kb + ((kind & 1) ? 0 : CH_RES_KB);
-      {  // dependencies: the scout warp has seen the counters of this unit
+      const int res_kb = (kind & 1) ? 0 : CH_RES_KB;  // LayerNorm units: the residual stages come FIRST
+      const int total_kb = num_kb + res_kb;
+      // dependencies: the scout warp publishes two phases per unit (2 it + 1: the residual planes of a LayerNorm unit
+      // are in L2; 2 it + 2: all inputs are)
+      auto wait_dep = [&](uint32_t need) {
         uint32_t seen;
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_dep)) : "memory");
-        if (seen < (uint32_t)(it + 1)) {
+        if (seen < need) {
           const long long t0 = clock64();
           do {
             __nanosleep(100);  // the board runs at its power limit: a busy spin on all 148 SMs is paid for in clock
             asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_dep)) : "memory");
             if (clock64() - t0 > 4000000000LL) __trap();
-          } while (seen < (uint32_t)(it + 1));
+          } while (seen < need);
         }
-      }
+      };
+      wait_dep((uint32_t)(2 * it + (res_kb ? 1 : 2)));
       if (lane == 0) CHAIN_TRACE_UNIT(0, it);
-      for (int kb = 0; kb < total_kb; ++kb) {
+      for (int kk = 0; kk < total_kb; ++kk) {
+        if (res_kb && kk == res_kb) wait_dep((uint32_t)(2 * it + 2));
         mbar_wait_q(&empty_bar[stage], phase ^ 1u);
         uint8_t* a_dst = sA + stage * CH_A_BYTES;
         uint8_t* b_dst = sB + stage * CH_B_BYTES;
         const uint32_t bar = full_leader + stage * 8;
-        if (kb < num_kb) {
+        if (kk >= res_kb) {
+          const int kb = kk - res_kb;
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * CH_STAGE_BYTES);
             tma_load_2d_2sm(a_dst, ta, bar, kb * 64, m0);
             tma_load_2d_2sm(b_dst, tb, bar, kb * 64, n0 + (int)rank * (BN / 2));
           }
         } else {  // residual stage: 128 rows x two 64-column blocks of plane (rb / 2) at columns n0 + 128 (rb % 2)
-          const int rb = kb - num_kb;
+          const int rb = kk;
           const CUtensorMap* tx = (rb >> 1) ? &tmXl : &tmXh;
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * CH_STAGE_BYTES);
@@ -329,7 +335,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         const int code = p.sched[ui];
         const int kind = code >> 28;
         const int num_kb = (kind == CK_LN2 ? p.ff : p.d) / 64;
-        const int total_kb = num_kb + ((kind & 1) ? 0 : CH_RES_KB);
+        const int res_kb = (kind & 1) ? 0 : CH_RES_KB;
+        const int total_kb = num_kb + res_kb;
         if (!(kind & 1) && !ident_ready) {
           mbar_wait_q(ident_bar, 0);
           ident_ready = true;
@@ -337,32 +344,36 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         mbar_wait_q(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < total_kb; ++kb) {
+        for (int kk = 0; kk < total_kb; ++kk) {
           mbar_wait_q(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0 && kb == 0) CHAIN_TRACE_UNIT(2, it);
+          if (lane == 0 && kk == 0) CHAIN_TRACE_UNIT(2, it);
           const uint32_t a_addr = smem_u32(sA + stage * CH_A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * CH_B_BYTES);
-          if (kb < num_kb) {
+          if (kk >= res_kb) {
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16_2sm(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                              (kb | k) ? 1u : 0u);
+                              (kk | k) ? 1u : 0u);
               umma_commit_2sm(&empty_bar[stage]);  // ring slot reusable in both CTAs once these MMAs have read it
-              if (kb == total_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
+              if (kk == total_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
             }
-          } else {  // acc[:, 64 j .. 64 j + 63] += X_plane block j . I64 for the stage's two blocks
-            const uint32_t dj = d_tmem + 128u * (uint32_t)((kb - num_kb) & 1);
+          } else {
+            // residual stages open the accumulator: acc[:, 64 j .. 64 j + 63] (+)= X_plane block j . I64 for the stage's
+            // two blocks; the high plane (stages 0, 1) initialises its columns, the low plane (2, 3) accumulates
+            const uint32_t dj = d_tmem + 128u * (uint32_t)(kk & 1);
+            const bool first_plane = kk < 2;
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16_2sm(dj, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(i_addr + k * 32), idesc_res, 1u);
+                umma_bf16_2sm(dj, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(i_addr + k * 32), idesc_res,
+                              (first_plane && k == 0) ? 0u : 1u);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16_2sm(dj + 64u, umma_desc_k_sw128(b_addr + k * 32), umma_desc_k_sw128(i_addr + k * 32), idesc_res, 1u);
+                umma_bf16_2sm(dj + 64u, umma_desc_k_sw128(b_addr + k * 32), umma_desc_k_sw128(i_addr + k * 32), idesc_res,
+                              (first_plane && k == 0) ? 0u : 1u);
               umma_commit_2sm(&empty_bar[stage]);
-              if (kb == total_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
             }
           }
           __syncwarp();
@@ -386,28 +397,38 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     for (int ui = u_begin; ui < u_end; ++ui, ++it) {
       const int code = p.sched[ui];
       const int kind = code >> 28, m = (code >> 8) & 0xFFFFF;
+      auto publish = [&](uint32_t v) {
+        if (lane == 0) {
+          // the inputs were written through the async proxy (TMA stores) and will be read through it (TMA loads of the
+          // producer warp): the acquire of the poll orders generic accesses only
+          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(s_dep)), "r"(v) : "memory");
+        }
+        __syncwarp();
+      };
       if (kind == CK_LN1) {
-        // the attention output of every sequence that overlaps the row tile, and the previous layer's LN2 low plane
+        // residual: the previous layer's LN2 planes of the row tile (low plane counter: a CTA announces it after both of
+        // its stores).  In the first layer the planes come from the embed kernels, ordered only through the attention
+        // kernel's grid-wide wait, so there the attention counters are waited for first.
         const int b0 = (m * 256) / p.S, b1 = min(p.B - 1, (m * 256 + 255) / p.S);
-        for (int b = b0; b <= b1; ++b) chain_wait_ge(r_att + b, li * p.target_att);
+        if (li == 1u)
+          for (int b = b0; b <= b1; ++b) chain_wait_ge(r_att + b, li * p.target_att);
         chain_wait_ge(p.ctr + 4 * tiles_m + m, (li - 1u) * p.target_ln);
+        publish((uint32_t)(2 * it + 1));
+        // the attention output of every sequence that overlaps the row tile
+        for (int b = b0; b <= b1; ++b) chain_wait_ge(r_att + b, li * p.target_att);
       } else if (kind == CK_L1) {
         chain_wait_ge(p.ctr + 0 * tiles_m + m, t_ln);  // LN1 high plane of the row tile
       } else if (kind == CK_LN2) {
-        chain_wait_ge(p.ctr + 2 * tiles_m + m, t_h);   // every H tile of the row tile
         chain_wait_ge(p.ctr + 1 * tiles_m + m, t_ln);  // LN1 low plane (the residual of this unit)
+        publish((uint32_t)(2 * it + 1));
+        chain_wait_ge(p.ctr + 2 * tiles_m + m, t_h);   // every H tile of the row tile
       } else {
         chain_wait_ge(p.ctr + 3 * tiles_m + m, t_ln);  // LN2 high plane
       }
       if (kind == CK_L1 && lane == 0 && p.trace && p.trace[(size_t)blockIdx.x * GEMM_TRACE_SLOTS + 54] == 0)
         CHAIN_TRACE_NS(54);
-      if (lane == 0) {
-        // the unit's inputs were written through the async proxy (TMA stores) and will be read through it (TMA loads of
-        // the producer warp): the acquire above orders generic accesses only
-        asm volatile("fence.proxy.async;" ::: "memory");
-        asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(s_dep)), "r"((uint32_t)(it + 1)) : "memory");
-      }
-      __syncwarp();
+      publish((uint32_t)(2 * it + 2));
     }
    } else {
     // ===================== signal warp =====================

@@ -165,3 +165,43 @@ def test_layer_schedule_is_complete_and_deadlock_free(M, d, ff, n_inp, slots):
                 left -= 1
                 progressed = True
         assert progressed, "the schedule deadlocks"
+
+
+def test_encode_text_clip_branch(monkeypatch):
+    """InterationSegmentMDM.encode_text without a `text_encoder`: loads the `clip` package like load_and_freeze_clip
+    (interaction_segment_mdm.py:84-97: clip.load(version, device='cpu', jit=False), convert_weights, eval), tokenises
+    with context_length 22 + truncate and zero-pads the tokens to 77 columns before encode_text (:111-132)."""
+    import sys
+    import types
+
+    import torch
+
+    import tamf_b200
+    calls = {}
+
+    class FakeClipModel(torch.nn.Module):
+        def encode_text(self, tokens):
+            calls["tokens"] = tokens.clone()
+            return tokens[:, :4].to(torch.float16) * 0.5
+
+    def load(version, device="cuda", jit=True):
+        calls["load"] = (version, device, jit)
+        return FakeClipModel(), None
+
+    def tokenize(texts, context_length=77, truncate=False):
+        calls["tokenize"] = (list(texts), context_length, truncate)
+        return torch.arange(len(texts) * context_length, dtype=torch.int32).reshape(len(texts), context_length) + 1
+
+    fake = types.ModuleType("clip")
+    fake.load, fake.tokenize = load, tokenize
+    fake.model = types.SimpleNamespace(convert_weights=lambda m: calls.setdefault("converted", True))
+    monkeypatch.setitem(sys.modules, "clip", fake)
+    m = tamf_b200.InterationSegmentMDM(latent_dim=256, ff_size=1024, num_layers=8, num_heads=4)
+    out = m.encode_text(["pick up the cup", "pour"])
+    assert calls["load"] == ("ViT-B/32", "cpu", False) and calls["converted"]
+    assert calls["tokenize"] == (["pick up the cup", "pour"], 22, True)
+    tok = calls["tokens"]
+    assert tok.shape == (2, 77) and bool((tok[:, 22:] == 0).all()) and bool((tok[:, :22] > 0).all())
+    assert out.dtype == torch.float32 and out.shape == (2, 4) and float(out[0, 0]) == 0.5
+    m.encode_text(["again"])
+    assert calls["tokenize"][0] == ["again"]  # the tower is loaded once
