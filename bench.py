@@ -2,7 +2,7 @@
 """bench.py -- sampled motion sequences/sec, full 1000-step reverse chain, MF-MDM G arch_mdm_l (BASELINE.json).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (libtamf_b200.so, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port), rank 0 only
+    python bench.py --impl reference --gpus N --steps K ...  # the reference on the host cores (oracle/_ref, else the oracle port), rank 0 only
     torchrun --nproc-per-node N ... bench.py --gpus N ...    # N > 1: one rank per GPU, batch-sharded, NCCL gather
 
 A "step" is one pass of the hot path over one batch: conditioning (once per sample) + x_T ~ N(0,I) + the 1000
@@ -139,16 +139,71 @@ def host_threads():
 _CPU_STATE = {}
 
 
-def cpu_reference_sample(B, n_diff):
-    """Oracle port of the reference's per-step algorithm (InterationSegmentMDM.forward + p_sample) on the host cores:
-    `n_diff` diffusion steps at batch B, arch_mdm_l, torch intra-op threads = every host core.  Returns seconds per
-    diffusion step."""
+_KIND_NOTE = {
+    "reference": "the reference's own InterationSegmentMDM + GaussianDiffusion.p_sample from oracle/_ref, CLIP text tower "
+                 "(random init) evaluated every step as the reference does",
+    "port": "oracle port of the reference (oracle/tamf_oracle.py), CLIP text tower excluded (text feature given)",
+}
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")  # private copy of the reference's modules (oracle/make_ref.py), git-ignored
+
+
+def reference_kind():
+    """"reference": oracle/_ref holds the reference's own modules (built by oracle/make_ref.py where /root/reference
+    exists; travels to the GPU box) -> the CPU arm runs them unmodified.  "port": only the oracle restatement is there."""
+    return "reference" if os.path.isdir(os.path.join(REF_DIR, "src", "oakink2_tamf")) else "port"
+
+
+def _reference_sample(B, n_diff):
+    """The reference itself on the host cores: its InterationSegmentMDM (arch_mdm_l, the bench's random-init weights) and
+    its GaussianDiffusion.p_sample (gaussian_diffusion.py:412-460), called as launch/sample.py:216-228 does -- including
+    the CLIP text tower the reference evaluates at every step (random-init ViT-B/32 from oracle/ref_shims.py: the trained
+    weights are a network download)."""
     import torch
+    if "ref" not in _CPU_STATE:
+        os.environ["TAMF_REFERENCE_ROOT"] = REF_DIR
+        import warnings
+
+        from oracle import ref_shims
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ns = ref_shims.install()
+        _CPU_STATE["ref"] = ns
+    ns = _CPU_STATE["ref"]
+    from tamf_b200 import synth
+    key = ("ref", B)
+    if key not in _CPU_STATE:
+        import warnings
+        cfg = synth.ARCH[ARCH]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model = ns.mdm.InterationSegmentMDM(**cfg)
+        missing, unexpected = model.load_state_dict(synth.g_state_dict(cfg, seed=0), strict=False)
+        assert not unexpected and all(k.startswith("clip_model") for k in missing), (missing[:4], unexpected[:4])
+        model.eval()
+        diffusion = ns.diffusion_util.create_gaussian_diffusion(diffusion_steps=DIFF_STEPS, noise_schedule="cosine")
+        _CPU_STATE[key] = (model, diffusion, synth.make_batch(B, T_FRAMES, nobj=NOBJ, seed=0))
+    model, diffusion, batch = _CPU_STATE[key]
+    x = torch.randn(B, 99, 1, T_FRAMES, generator=torch.Generator().manual_seed(0))
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for i in range(n_diff):
+            t = torch.full((B,), DIFF_STEPS - 1 - i, dtype=torch.long)
+            x = diffusion.p_sample(model, x, t, clip_denoised=False, model_kwargs={"batch": batch})["sample"]
+    return (time.perf_counter() - t0) / n_diff
+
+
+def cpu_reference_sample(B, n_diff):
+    """The reference's per-step algorithm (InterationSegmentMDM.forward + p_sample) on the host cores: `n_diff` diffusion
+    steps at batch B, arch_mdm_l, torch intra-op threads = every host core.  Runs the reference's own modules from
+    oracle/_ref when they are there (reference_kind()), else the oracle port.  Returns seconds per diffusion step."""
+    import torch
+    if torch.get_num_threads() != host_threads():
+        torch.set_num_threads(host_threads())
+    if reference_kind() == "reference":
+        return _reference_sample(B, n_diff)
 
     from oracle import tamf_oracle as orc
     from tamf_b200 import synth
-    if torch.get_num_threads() != host_threads():
-        torch.set_num_threads(host_threads())
     if B not in _CPU_STATE:
         cfg = synth.ARCH[ARCH]
         batch = synth.make_batch(B, T_FRAMES, nobj=NOBJ, seed=0)
@@ -170,14 +225,18 @@ def workload_config(B, world, chain_steps=DIFF_STEPS):
     return {"workload": f"MF-MDM G {ARCH}, batch {B} synthetic sequences per GPU, T={T_FRAMES}, nobj={NOBJ}, "
                         f"full {chain_steps}-step reverse chain (BASELINE.json configs[1])",
             "global_batch": world * B, "sequences_per_gpu": B, "frames": T_FRAMES, "objects": NOBJ,
-            "diffusion_steps": chain_steps, "weights": "random init", "text_features": "synthetic (CLIP tower excluded)"}
+            "diffusion_steps": chain_steps, "weights": "random init",
+            "text_features": "synthetic prompts; trained CLIP weights are not available offline (GPU arm: hash features, "
+                             "evaluated once per batch; reference arm: whatever oracle/_ref or the port does, see its "
+                             "cpu_baseline.sample)"}
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU algorithm (oracle port; the Python reference cannot travel to the GPU box
-    and pytorch3d/CLIP weights are absent) on every host core.  Rank 0 only; other ranks exit 0 without work.  Each timed
-    step is a bounded sample of the workload -- `n_diff` of the 1000 diffusion steps at the full batch, extrapolated
-    linearly -- sized from a first measured step so that the whole --steps/--warmup run stays within --ref-budget-s."""
+    """`--impl reference`: the reference on every host core -- its own modules from oracle/_ref when the snapshot carries
+    them (oracle/make_ref.py, built where /root/reference exists), else the oracle port.  Rank 0 only; other ranks exit 0
+    without work.  Each timed step is a bounded sample of the workload -- `n_diff` of the 1000 diffusion steps at the full
+    batch, extrapolated linearly -- sized from a first measured step so that the whole --steps/--warmup run stays within
+    --ref-budget-s."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     os.environ.pop("OMP_NUM_THREADS", None)
@@ -192,20 +251,20 @@ def run_reference(args):
     ms_per_step = sec_per_diff * DIFF_STEPS * 1e3
     value = B / (sec_per_diff * DIFF_STEPS)
     cores = host_threads()
+    kind = reference_kind()
     sample = (f"{n_diff} of {DIFF_STEPS} diffusion steps at B={B} per timed step (x{args.steps} steps, "
-              f"{sec_per_diff:.3f} s per diffusion step), extrapolated linearly to the full chain; CLIP text tower "
-              f"excluded (text feature given)")
+              f"{sec_per_diff:.3f} s per diffusion step), extrapolated linearly to the full chain; " + _KIND_NOTE[kind])
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(B, max(1, args.gpus)),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "notes": "reference arm = oracle port on the host cores, rank 0 only; ms_per_step is the linear extrapolation of "
-                 "the bounded sample to the full 1000-step chain",
+        "notes": "reference arm on the host cores, rank 0 only (kind: see cpu_baseline); ms_per_step is the linear "
+                 "extrapolation of the bounded sample to the full 1000-step chain",
     }
     print(json.dumps(line), flush=True)
 
@@ -415,10 +474,10 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec = cpu_reference_sample(B, args.ref_diff_steps)
-        cpu = {"value": B / (sec * DIFF_STEPS), "unit": UNIT, "cores": host_threads(), "kind": "port",
+        cpu = {"value": B / (sec * DIFF_STEPS), "unit": UNIT, "cores": host_threads(), "kind": reference_kind(),
                "host_cpus": os.cpu_count(),
                "sample": f"{args.ref_diff_steps} of {DIFF_STEPS} diffusion steps at B={B} ({sec:.2f} s each), extrapolated "
-                         f"linearly; CLIP text tower excluded"}
+                         f"linearly; " + _KIND_NOTE[reference_kind()]}
 
     if rank == 0:
         config = workload_config(B, world, args.chain_steps)
