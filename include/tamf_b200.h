@@ -56,7 +56,10 @@ int tamf_nn_query(const float* x, const float* y, int N, int P1, int P2, float* 
  *   obj_points[sum_b nobj_b, P, 3] canonical clouds, packed in batch order
  *   obj_first [B+1] int32          prefix sums of nobj_b (host pointer)
  *   dist      [B,T,V] fp32         |v - nearest|  (sqrt of the squared distance)
- *   idx       [B,T,V] int64        index into the concatenated cloud of that sequence (scratch + output) */
+ *   idx       [B,T,V] int64        index into the concatenated cloud of that sequence (scratch + output)
+ * Device scratch: the B+1 prefix sums (and, for tamf_nn_query with more than 4096 queries per cloud, the packed
+ * per-query minima) live in a grow-only buffer the library keeps per (device, stream): the FIRST call on a stream, or
+ * a call that needs more than any earlier one, allocates (cudaMalloc); steady-state calls do not. */
 int tamf_h2o_dist(const float* verts, const float* obj_traj, const float* obj_points, const int32_t* obj_first_host,
                   int B, int T, int V, int nobj_max, int P, float* dist, int64_t* idx, void* stream);
 /* Two-step form for callers that query the same objects several times (SegmentRefineModel.forward runs the query for

@@ -374,16 +374,23 @@ extern "C" int tamf_mano_fk_select(const tamf_mano* h, int pose_mode, const floa
 // area-weighted normal), normalize(eps 1e-6)  -- oracle/tamf_oracle.py:vertex_normals.
 // ------------------------------------------------------------------------------------------------
 namespace tamf {
+// The per-vertex sums are accumulated in 2^-44 fixed point with 64-bit integer atomics: every fp32 contribution converts
+// exactly (|x| < 2^19), integer addition is associative, so the result does not depend on the order in which the faces
+// arrive -- bit-identical from run to run (fp32 atomics were not) and rounded to fp32 once.  A non-finite contribution
+// marks its vertex, whose normal becomes NaN as it would in floating point.
+constexpr float VN_SCALE = 17592186044416.0f;  // 2^44
 __global__ void __launch_bounds__(256)
     vertex_normals_kernel(const float* __restrict__ verts, const int* __restrict__ faces, int V, int F,
                           float* __restrict__ normals) {
-  extern __shared__ float sN[];  // [V*3] accumulators, then [V*3] vertex cache
-  float* sV = sN + V * 3;
+  extern __shared__ unsigned long long sAcc[];  // [V*3] fixed-point accumulators, then float [V*3] vertices, int [V] flags
+  float* sV = reinterpret_cast<float*>(sAcc + V * 3);
+  int* sBad = reinterpret_cast<int*>(sV + V * 3);
   const float* v = verts + (size_t)blockIdx.x * V * 3;
   for (int i = threadIdx.x; i < V * 3; i += blockDim.x) {
-    sN[i] = 0.f;
+    sAcc[i] = 0ull;
     sV[i] = v[i];
   }
+  for (int i = threadIdx.x; i < V; i += blockDim.x) sBad[i] = 0;
   __syncthreads();
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
     const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
@@ -393,9 +400,14 @@ __global__ void __launch_bounds__(256)
     auto cross_add = [&](const float* p, const float* q, const float* o, int dst) {  // cross(p-o, q-o) -> dst
       const float ux = p[0] - o[0], uy = p[1] - o[1], uz = p[2] - o[2];
       const float wx = q[0] - o[0], wy = q[1] - o[1], wz = q[2] - o[2];
-      atomicAdd(&sN[3 * dst + 0], uy * wz - uz * wy);
-      atomicAdd(&sN[3 * dst + 1], uz * wx - ux * wz);
-      atomicAdd(&sN[3 * dst + 2], ux * wy - uy * wx);
+      const float n[3] = {uy * wz - uz * wy, uz * wx - ux * wz, ux * wy - uy * wx};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (fabsf(n[k]) < 524288.f)  // false for NaN / inf as well
+          atomicAdd(&sAcc[3 * dst + k], (unsigned long long)__float2ll_rn(n[k] * VN_SCALE));
+        else
+          atomicOr(&sBad[dst], 1);
+      }
     };
     cross_add(c, a, b, i1);
     cross_add(a, b, c, i2);
@@ -404,7 +416,10 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   float* out = normals + (size_t)blockIdx.x * V * 3;
   for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float x = sN[3 * i], y = sN[3 * i + 1], z = sN[3 * i + 2];
+    const float inv_s = 1.0f / VN_SCALE;
+    float x = (float)(long long)sAcc[3 * i] * inv_s, y = (float)(long long)sAcc[3 * i + 1] * inv_s,
+          z = (float)(long long)sAcc[3 * i + 2] * inv_s;
+    if (sBad[i]) x = y = z = __int_as_float(0x7fc00000);
     const float inv = 1.0f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-6f);
     out[3 * i] = x * inv, out[3 * i + 1] = y * inv, out[3 * i + 2] = z * inv;
   }
@@ -416,10 +431,10 @@ extern "C" int tamf_vertex_normals(const float* verts, const int32_t* faces, int
   TAMF_REQUIRE(N >= 0 && V > 0 && F >= 0, TAMF_E_BADARG, "tamf_vertex_normals: bad size");
   if (N == 0) return TAMF_OK;
   TAMF_REQUIRE(verts && faces && normals, TAMF_E_BADARG, "tamf_vertex_normals: null pointer");
-  TAMF_REQUIRE((size_t)V * 24 <= 48 * 1024, TAMF_E_BADARG, "tamf_vertex_normals: V too large for one CTA");
+  TAMF_REQUIRE((size_t)V * 40 <= 48 * 1024, TAMF_E_BADARG, "tamf_vertex_normals: V too large for one CTA");
   int rc = check_device();
   if (rc) return rc;
-  vertex_normals_kernel<<<N, 256, (size_t)V * 24, (cudaStream_t)stream>>>(verts, faces, V, F, normals);
+  vertex_normals_kernel<<<N, 256, (size_t)V * 40, (cudaStream_t)stream>>>(verts, faces, V, F, normals);
   TAMF_LAUNCH_CHECK();
   return TAMF_OK;
 }

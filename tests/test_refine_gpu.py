@@ -75,10 +75,18 @@ def test_vertex_normals_vs_oracle():
     A = synth.mano_assets("right")
     rng = np.random.default_rng(4)
     v = (0.05 * rng.standard_normal((5, 778, 3))).astype(np.float32)
-    n = tamf_b200.vertex_normals(torch.from_numpy(v).cuda(), torch.from_numpy(A["faces"]))
+    vd, fd = torch.from_numpy(v).cuda(), torch.from_numpy(A["faces"])
+    n = tamf_b200.vertex_normals(vd, fd)
     ref = orc.vertex_normals(v, A["faces"])
-    # accumulation order differs (shared-memory atomics): compare by value
-    assert np.abs(n.cpu().numpy() - ref).max() < 2e-4
+    # the kernel sums the face contributions exactly (64-bit fixed point) and rounds once; the oracle sums in fp32 in
+    # face order: they differ by the oracle's own rounding only
+    assert np.abs(n.cpu().numpy() - ref).max() < 2e-5
+    for _ in range(20):  # order-independent accumulation: bit-identical from run to run
+        assert torch.equal(tamf_b200.vertex_normals(vd, fd), n)
+    bad = v.copy()
+    bad[1, int(A["faces"][0, 0])] = np.nan
+    nb = tamf_b200.vertex_normals(torch.from_numpy(bad).cuda(), fd).cpu().numpy()
+    assert np.isnan(nb[1, int(A["faces"][0, 0])]).all() and np.isfinite(nb[0]).all()
     used = np.zeros(778, bool)
     used[np.unique(A["faces"])] = True  # vertices no face references keep a zero normal (eps clamp)
     assert np.abs(np.linalg.norm(n.cpu().numpy(), axis=-1)[:, used] - 1.0).max() < 1e-5
