@@ -51,7 +51,7 @@ def flops_per_seq_step(cfg, T=T_FRAMES):
     return L * (8 * S * d * d + 4 * S * S * d + 4 * S * d * ff) + 4 * T * 99 * d + 4 * T * d * d
 
 
-def kernel_classes(cfg, B, T=T_FRAMES, chain=True):
+def kernel_classes(cfg, B, T=T_FRAMES, chain=True, stack=False):
     """(name, algorithmic FLOPs per launch) in the launch order tamf_denoiser_profile_step reports.  chain=True: the
     layer-kernel form of the encoder (csrc/layer_chain.cuh): in_proj of layer 0, then per layer attention | out_proj+LN1 ->
     linear1+GELU -> linear2+LN2 -> in_proj of the next layer in ONE kernel; chain=False: the five-kernel layer (TAMF_CHAIN=0)."""
@@ -60,7 +60,10 @@ def kernel_classes(cfg, B, T=T_FRAMES, chain=True):
     M, Mf = B * S, B * T
     out = [("prep", 0), ("embed_a", 2 * Mf * 99 * d), ("embed_b", 2 * Mf * d * d)]
     f_in, f_att, f_out, f_l1, f_l2 = 2 * M * 3 * d * d, 4 * B * S * S * d, 2 * M * d * d, 2 * M * d * ff, 2 * M * ff * d
-    if chain:
+    if stack:  # TAMF_CHAIN=2: one persistent attention launch + one persistent layer-kernel launch for all layers
+        out += [("in_proj0", f_in), ("attention_all_layers", L * f_att),
+                ("layers_ln1_l1_ln2_inproj_all", L * (f_out + f_l1 + f_l2) + (L - 1) * f_in)]
+    elif chain:
         out.append(("in_proj0", f_in))
         for l in range(L):
             out += [("attention", f_att), ("layer_ln1_l1_ln2_inproj", f_out + f_l1 + f_l2 + (f_in if l + 1 < L else 0))]
@@ -432,7 +435,9 @@ def run_ours(args):
         ms_buf, n_out = (C.c_float * 64)(), C.c_int(0)
         _lib.check(L.tamf_denoiser_profile_step(model._handle, _lib.ptr(x), 500, 7, ms_buf, 64, C.byref(n_out),
                                                 _lib.stream_ptr(dev)), "profile_step")
-        if n_out.value != len(classes):  # TAMF_CHAIN=0: the five-kernel layer of round 1
+        if n_out.value == 7:  # TAMF_CHAIN=2: the stack form
+            classes = kernel_classes(cfg, B, stack=True)
+        elif n_out.value != len(classes):  # TAMF_CHAIN=0: the five-kernel layer of round 1
             classes = kernel_classes(cfg, B, chain=False)
         iso = {}
         for r in range(args.profile_reps + 2):

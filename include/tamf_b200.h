@@ -303,6 +303,10 @@ int tamf_debug_chain_trace(long long* trace, int layer);
  * 3 INP); makespan_out: the cost model's estimate in cycles.  Returns the pair count, or a negative TAMF_E_* code. */
 int tamf_layer_schedule(int M, int d, int ff, int n_inp, int slots, int* off_out, int* units_out, int cap,
                         double* makespan_out);
+/* Same for the stack form (TAMF_CHAIN=2): all `layers` layers in ONE launch on `slots` pairs next to a persistent attention
+ * kernel of `att_ctas` CTAs; unit codes kind << 28 | layer << 24 | row tile << 8 | column tile. */
+int tamf_stack_schedule(int M, int d, int ff, int layers, int slots, int att_ctas, int S, int heads, double att_unit,
+                        int* off_out, int* units_out, int cap, double* makespan_out);
 
 #ifdef __cplusplus
 }

@@ -47,13 +47,18 @@ int num_sms() {
   return n;
 }
 
+// Programmatic dependent launch is on unless TAMF_PDL=0, or the caller holds a PdlBlock (common.cuh): a kernel that must
+// not become resident before everything older has finished (the kernel after the two co-resident persistent kernels of
+// the encoder's stack form: parked early on free SMs it would starve the one that is launched last).
+static thread_local int g_pdl_blocked = 0;
+void pdl_block(int delta) { g_pdl_blocked += delta; }
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TAMF_PDL");
     v = (e && e[0] == '0') ? 0 : 1;
   }
-  return v == 1;
+  return v == 1 && g_pdl_blocked == 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

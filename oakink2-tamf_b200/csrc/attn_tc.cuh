@@ -106,7 +106,13 @@ __device__ __forceinline__ void atc_sts128(uint32_t addr, uint32_t a, uint32_t b
 template <int HD>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmO, int S, int d,
-                   int dbg, long long* trace, long long* ktime, const unsigned* rq, unsigned rq_target, unsigned* ra) {
+                   int dbg, long long* trace, long long* ktime, const unsigned* rq, unsigned rq_target, unsigned* ra,
+                   int stack_layers, int H, int B) {
+  // stack_layers > 0 (stack form of the encoder, encoder.cu): a PERSISTENT grid of gridDim.x CTAs walks the units
+  // g = (layer * B + b) * H + h of ALL layers in order, CTA c taking g = c, c + gridDim.x, ...; a unit of layer l >= 1
+  // waits for rq[row tile] >= l * rq_target (the in_proj tiles the layer kernel stored for layer l), layer 0 reads the
+  // plain in_proj GEMM's output (complete before this kernel starts: stream order).  Otherwise one unit per CTA,
+  // grid (H, B).
   // rq / ra (layer-kernel form of the encoder, layer_chain.cuh): instead of waiting for the whole previous grid, the CTA
   // of sequence b waits until the in_proj tiles of the row tiles its tokens lie in have been stored (rq[row tile] >=
   // rq_target, bumped by the layer kernel's epilogue warps after their TMA stores completed), and announces its own
@@ -119,14 +125,20 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
   using C = AttnTcCfg<HD>;
   constexpr int NB = C::NB;
   extern __shared__ uint8_t atc_raw[];
-  __shared__ uint64_t bars[8];  // 0: Q+K landed, 1: V landed, 2+t: scores of tile t, 4+t: P of tile t, 6+t: O of tile t
+  // 0: Q+K landed, 1: V landed, 2+t: scores of tile t, 4+t: P of tile t, 6+t: O of tile t, 8: unit drained (every
+  // softmax warp has read its accumulators and its output stores have left shared memory: the next unit may load)
+  __shared__ uint64_t bars[9];
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(atc_raw) + 1023u) & ~1023u;
   const uint32_t sP1 = base + C::OFF_P1, sP0 = base + C::OFF_P0, sQ = base + C::OFF_Q, sK = base + C::OFF_K,
                  sV = base + C::OFF_V;
-  const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntile = S > 128 ? 2 : 1;
+  const bool stack = stack_layers > 0;
+  const int g_first = stack ? (int)blockIdx.x : (int)(blockIdx.y * gridDim.x + blockIdx.x);
+  const int g_step = stack ? (int)gridDim.x : 1;
+  const int g_end = stack ? stack_layers * B * H : g_first + 1;
+  const int heads = stack ? H : (int)gridDim.x;
   if (threadIdx.x == 0) {
     ATC_TRACE(0);
     ktime_entry(ktime);
@@ -148,6 +160,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       mbar_init(&bars[2], 1), mbar_init(&bars[3], 1);
       mbar_init(&bars[4], 4), mbar_init(&bars[5], 2);
       mbar_init(&bars[6], 1), mbar_init(&bars[7], 1);
+      mbar_init(&bars[8], ntile == 2 ? 6 : 4);
       fence_mbar_init();
     }
     __syncwarp();
@@ -162,28 +175,37 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
   if (threadIdx.x == 0) ATC_TRACE(1);
 
   if (warp == 6) {
+   int iter = 0;
+   for (int g = g_first; g < g_end; g += g_step, ++iter) {
+    const uint32_t ph = (uint32_t)(iter & 1);
+    const int layer = g / (B > 0 && stack ? B * heads : 1 << 30), h = g % heads, b = (g / heads) % (stack ? B : 1 << 30);
+    const unsigned unit_target = stack ? (unsigned)layer * rq_target : rq_target;
+    if (iter > 0) {  // the previous unit has left shared memory and TMEM
+      mbar_wait(&bars[8], ph ^ 1u);
+      tc_fence_after();
+    }
     // all lanes run the issue sequence (uniform descriptors / coordinates, see elect_one()); one elected lane issues
     if (elect_one()) {
       if (rq == nullptr) {
         pdl_wait();  // QKV is the previous kernel's output
-      } else {
+      } else if (!stack || layer > 0) {
         const int m0 = (b * S) >> 8, m1 = (b * S + S - 1) >> 8;
         for (int m = m0; m <= m1; ++m) {
           unsigned v;
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(rq + m) : "memory");
-          if ((int)(v - rq_target) < 0) {
+          if ((int)(v - unit_target) < 0) {
             const long long t0 = clock64();
             do {
               __nanosleep(40);
               asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(rq + m) : "memory");
               if (clock64() - t0 > 4000000000LL) __trap();
-            } while ((int)(v - rq_target) < 0);
+            } while ((int)(v - unit_target) < 0);
           }
         }
         // the rows were written by TMA stores and are read by the TMA loads below: order the two proxies behind the acquire
         asm volatile("fence.proxy.async;" ::: "memory");
       }
-      ktime_ready(ktime);
+      if (iter == 0) ktime_ready(ktime);
       mbar_arrive_expect_tx(&bars[0], 2 * NB * C::BLK);
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
@@ -197,7 +219,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     __syncwarp();
     // ---- scores = Q K^T, one 128 x 176 accumulator per query tile ----
     constexpr uint32_t id_s = umma_idesc_bf16(128, ATC_KP);
-    mbar_wait(&bars[0], 0);
+    mbar_wait(&bars[0], ph);
     tc_fence_after();
     if (lane == 0) ATC_TRACE(2);
     for (int t = 0; t < ntile; ++t) {
@@ -214,10 +236,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     }
     // ---- O = P V ----
     constexpr uint32_t id_o = umma_idesc_bf16_bmn(128, HD);
-    mbar_wait(&bars[1], 0);
+    mbar_wait(&bars[1], ph);
     if (lane == 0) ATC_TRACE(3);
     for (int t = 0; t < ntile; ++t) {
-      mbar_wait(&bars[4 + t], 0);
+      mbar_wait(&bars[4 + t], ph);
       tc_fence_after();
       if (lane == 0) ATC_TRACE(4 + t);
       const uint32_t pb = t ? sP1 : sP0, pblk = t ? C::P1_BLK : C::P0_BLK;
@@ -232,13 +254,18 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       }
       __syncwarp();
     }
+   }
   } else {
     const int t = warp >> 2, lq = warp & 3;
     if (t < ntile) {
+     int iter = 0;
+     for (int g = g_first; g < g_end; g += g_step, ++iter) {
+      const uint32_t ph = (uint32_t)(iter & 1);
+      const int h = g % heads, b = (g / heads) % (stack ? B : 1 << 30);
       const int r = lq * 32 + lane;  // row inside the tile
       const uint32_t lane_sel = (uint32_t)(lq * 32) << 16;
       // ---- softmax over the 176 keys of this row ----
-      mbar_wait(&bars[2 + t], 0);
+      mbar_wait(&bars[2 + t], ph);
       tc_fence_after();
       if (lane == 0 && lq == 0) ATC_TRACE(6 + t);
       // The row's 176 scores come out of TMEM with all six loads in flight at once (a chunk-by-chunk pipeline against the
@@ -315,7 +342,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       if (lane == 0) mbar_arrive(&bars[4 + t]);
 
       // ---- O * inv -> bf16 -> warp-private staging (dead Q/K region) -> TMA store ----
-      mbar_wait(&bars[6 + t], 0);
+      mbar_wait(&bars[6 + t], ph);
       tc_fence_after();
       if (lane == 0 && lq == 0) ATC_TRACE(8 + t);
       const uint32_t oa = tmem + lane_sel + (t ? 0u : (uint32_t)ATC_O0_COL);
@@ -354,6 +381,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         }
       }
       if (lane == 0 && lq == 0) ATC_TRACE(10 + t);
+      // unit drained: accumulators read, output stores have left the staging tile (lane 0 waited for its bulk group)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[8]);
+     }
     }
   }
   tc_fence_before();
@@ -391,16 +423,24 @@ int configure_attn_tc() {
 
 template <int HD>
 int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t stream, long long* trace = nullptr,
-                   long long* ktime = nullptr, const unsigned* rq = nullptr, unsigned rq_target = 0, unsigned* ra = nullptr) {
+                   long long* ktime = nullptr, const unsigned* rq = nullptr, unsigned rq_target = 0, unsigned* ra = nullptr,
+                   int stack_layers = 0, int stack_ctas = 0) {
+  // stack_layers > 0: ONE persistent launch of `stack_ctas` CTAs (even: launched as clusters of 2 so that it occupies
+  // whole TPCs next to the layer kernel's CTA pairs) for the attention of all layers; rq_target is then per layer.
   TAMF_REQUIRE(S <= ATC_KP, TAMF_E_BADARG, "attention: at most 176 tokens per sequence");
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(H, B);
+  cfg.gridDim = stack_layers > 0 ? dim3(stack_ctas) : dim3(H, B);
   cfg.blockDim = dim3(ATC_THREADS);
   cfg.dynamicSmemBytes = AttnTcCfg<HD>::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int na = 0;
-  if (pdl_enabled()) {
+  if (stack_layers > 0) {
+    TAMF_REQUIRE(stack_ctas >= 2 && stack_ctas % 2 == 0 && rq && ra, TAMF_E_BADARG, "attention (stack form): bad launch");
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+    ++na;
+  } else if (pdl_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -408,7 +448,8 @@ int launch_attn_tc(const AttnTcMaps& m, int B, int S, int H, int d, cudaStream_t
   cfg.attrs = attr;
   cfg.numAttrs = na;
   static const int dbg = getenv("TAMF_ATTN_DBG") ? atoi(getenv("TAMF_ATTN_DBG")) : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel<HD>, m.kv, m.o, S, d, dbg, trace, ktime, rq, rq_target, ra);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel<HD>, m.kv, m.o, S, d, dbg, trace, ktime, rq, rq_target, ra,
+                                     stack_layers, H, B);
   count_launch();
   if (e != cudaSuccess) {
     set_error(std::string("attention launch failed: ") + cudaGetErrorString(e));

@@ -61,6 +61,12 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* gptr, uint64_t inner /*elemen
 int make_tmap_3d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t mid, uint64_t outer,
                       uint64_t mid_pitch_bytes, uint64_t outer_pitch_bytes, uint32_t box_mid, uint32_t box_inner = 64);
 bool pdl_enabled();  // TAMF_PDL=0 turns programmatic dependent launch off (debug aid)
+void pdl_block(int delta);
+struct PdlBlock {  // launches inside the scope carry no programmatic-serialization attribute (api.cu)
+  bool on;
+  explicit PdlBlock(bool enable) : on(enable) { if (on) pdl_block(+1); }
+  ~PdlBlock() { if (on) pdl_block(-1); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // device side

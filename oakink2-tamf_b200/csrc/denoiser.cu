@@ -214,6 +214,7 @@ static int enqueue_step(tamf_denoiser* h, const float* x_t, int* t_ptr, float* x
   }
   if ((rc = enqueue_encoder(h->enc, h->buf, s, marks, ktime, &kidx))) return rc;
   {  // final projection + DDPM posterior
+    PdlBlock no_early_launch(h->buf.stack);  // stack form: must not be parked on the SMs the attention kernel is waiting for
     GemmParams p{};
     p.M = M, p.N = h->nfeat, p.K = d, p.bias = h->b_fin, p.T = T, p.S = S, p.P0 = 5, p.nfeat = h->nfeat;
     p.x_t = x_t, p.x_out = x_out, p.x0_out = x0_out, p.noise = noise, p.t_ptr = advance ? h->t_cur : t_ptr, p.c1 = h->k1, p.c2 = h->k2,
@@ -239,6 +240,7 @@ static void drop_graph(tamf_denoiser* h) {
 extern "C" int tamf_denoiser_destroy(tamf_denoiser* h) {
   if (!h) return TAMF_OK;
   drop_graph(h);
+  h->buf.release();
   h->pool.free_all();
   delete h;
   return TAMF_OK;
@@ -436,7 +438,7 @@ extern "C" int tamf_denoiser_bind(tamf_denoiser* h, int B, int T, void* ws, size
   h->t_cur = h->t_dev + B;
   const int d = h->d, ff = h->ff;
   int rc;
-  if ((rc = h->buf.make_maps(d, ff))) return rc;
+  if ((rc = h->buf.make_maps(d, ff, h->L, h->H))) return rc;
   h->tm_Xb_fin = h->buf.tm_Xb;
   if ((rc = make_tmap_2d_bf16(&h->tm_A0, h->A0, KPAD, h->Mf, (uint64_t)KPAD * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_H0, h->H0, d, h->Mf, (uint64_t)d * 2, 64, 128))) return rc;

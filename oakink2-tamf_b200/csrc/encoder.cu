@@ -189,6 +189,21 @@ int EncoderStack::upload(DevPool& pool, const tamf_layer_weights* w, int d_, int
     TRY(make_tmap_2d_bf16(&o.tm_w1, o.w1, d, ff, (uint64_t)d * 2, 64, wbox));
     TRY(make_tmap_2d_bf16(&o.tm_w2, o.w2, ff, d, (uint64_t)ff * 2, 64, wbox));
   }
+  if (L <= CH_MAX_STACK_LAYERS) {  // device copies for the stack form of the layer kernel
+    std::vector<CUtensorMap> maps((size_t)L * 4);
+    std::vector<LayerWeightPtrs> ptrs(L);
+    for (int l = 0; l < L; ++l) {
+      const LayerDev& o = layers[l];
+      const LayerDev& nx = layers[l + 1 < L ? l + 1 : l];  // (the last layer has no INP units)
+      maps[l * 4 + CK_LN1] = o.tm_out, maps[l * 4 + CK_L1] = o.tm_w1, maps[l * 4 + CK_LN2] = o.tm_w2, maps[l * 4 + CK_INP] = nx.tm_in;
+      ptrs[l].bias[CK_LN1] = o.b_out, ptrs[l].bias[CK_L1] = o.b1, ptrs[l].bias[CK_LN2] = o.b2, ptrs[l].bias[CK_INP] = nx.b_in;
+      ptrs[l].gamma[0] = o.g1, ptrs[l].beta[0] = o.be1, ptrs[l].gamma[1] = o.g2, ptrs[l].beta[1] = o.be2;
+    }
+    TRY(pool.alloc((void**)&d_wmaps, maps.size() * sizeof(CUtensorMap)));
+    TRY(pool.alloc((void**)&d_lw, ptrs.size() * sizeof(LayerWeightPtrs)));
+    TAMF_CUDA_CHECK(cudaMemcpy(d_wmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    TAMF_CUDA_CHECK(cudaMemcpy(d_lw, ptrs.data(), ptrs.size() * sizeof(LayerWeightPtrs), cudaMemcpyHostToDevice));
+  }
 #undef TRY
   return TAMF_OK;
 }
@@ -196,7 +211,7 @@ int EncoderStack::upload(DevPool& pool, const tamf_layer_weights* w, int d_, int
 // aux layout: [counters | statistics words | schedule (with next in_proj) | schedule (last layer)], 256-byte aligned
 struct ChainLayout {
   int M, tiles_m, halves;
-  size_t ctr_words, stats_words, off_ctr, off_stats, off_sched, off_schedL, sched_bytes, total;
+  size_t ctr_words, stats_words, off_ctr, off_stats, off_sched, off_schedL, off_schedS, sched_bytes, schedS_bytes, total;
 };
 static ChainLayout chain_layout(int M, int d, int ff) {
   ChainLayout L{};
@@ -212,6 +227,9 @@ static ChainLayout chain_layout(int M, int d, int ff) {
   L.off_stats = o, o += al(L.stats_words * 8);
   L.off_sched = o, o += L.sched_bytes;
   L.off_schedL = o, o += L.sched_bytes;
+  L.schedS_bytes = al(((size_t)num_sms() / 2 + 1 +
+                       (size_t)CH_MAX_STACK_LAYERS * L.tiles_m * (2 * L.halves + (ff + 3 * d) / CH_BN)) * 4);
+  L.off_schedS = o, o += L.schedS_bytes;
   L.total = o;
   return L;
 }
@@ -237,7 +255,7 @@ static int upload_schedule(int* dst, const LayerSchedule& sc, size_t cap_bytes, 
 
 size_t encoder_aux_bytes(int M, int d, int ff) { return chain_layout(M, d, ff).total; }
 
-int EncoderBuffers::make_maps(int d, int ff) {
+int EncoderBuffers::make_maps(int d, int ff, int layers, int heads) {
   int rc;
   if ((rc = make_tmap_2d_bf16(&tm_Xb, Xb, d, M, (uint64_t)d * 2, 64, 128))) return rc;
   // A operands of the two LayerNorm GEMMs: 32-row boxes (one per TMEM lane quarter, ln_rq rows apart; gemm_ln_rq())
@@ -275,10 +293,36 @@ int EncoderBuffers::make_maps(int d, int ff) {
   pairs = sc.pairs, pairsL = sl.pairs;
   if ((rc = upload_schedule(sched, sc, lay.sched_bytes, nullptr)) || (rc = upload_schedule(schedL, sl, lay.sched_bytes, nullptr)))
     return rc;
+  // ---- stack form: one launch for all layers + one persistent attention launch ----
+  static const bool env_stack = getenv("TAMF_CHAIN") && getenv("TAMF_CHAIN")[0] == '2';
+  stack = env_stack && layers >= 2 && layers <= CH_MAX_STACK_LAYERS && heads > 0 && num_sms() >= 16;
+  if (stack) {
+    static const int env_att = getenv("TAMF_STACK_ATT") ? atoi(getenv("TAMF_STACK_ATT")) : 28;
+    // (splits with more than 28 attention CTAs fail with a launch failure on the B200s of this pool -- not understood; the
+    // form is experimental and off by default, so the range is clamped to what has been validated: 20, 24, 28)
+    att_ctas = std::max(8, std::min(env_att & ~1, 28));
+    static const double env_unit = getenv("TAMF_STACK_ATT_UNIT") ? atof(getenv("TAMF_STACK_ATT_UNIT")) : 9600.0;
+    AttnModel am;
+    am.ctas = att_ctas, am.S = S, am.heads = heads, am.unit = env_unit;
+    const LayerSchedule ss = build_stack_schedule(M, d, ff, layers, false, (num_sms() - att_ctas) / 2, costs, am);
+    schedS = reinterpret_cast<int*>(a + lay.off_schedS);
+    pairsS = ss.pairs;
+    if ((rc = upload_schedule(schedS, ss, lay.schedS_bytes, nullptr))) return rc;
+    if (!side) TAMF_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    if (!ev_fork) TAMF_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    if (!ev_join) TAMF_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
   TAMF_CUDA_CHECK(cudaMemset(ctr, 0, lay.ctr_words * 4));          // (cleared again at the start of every evaluation)
   ctr_bytes = lay.ctr_words * 4;
   TAMF_CUDA_CHECK(cudaMemset(stats, 0xFF, lay.stats_words * 8));   // "not posted"; every reader resets its word
   return TAMF_OK;
+}
+
+void EncoderBuffers::release() {
+  if (side) cudaStreamDestroy(side);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
+  side = nullptr, ev_fork = nullptr, ev_join = nullptr;
 }
 
 int configure_encoder_kernels() {
@@ -340,6 +384,41 @@ static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& 
     mark_event(marks, s);
   }
   static const int dbg = getenv("TAMF_CHAIN_DBG") ? atoi(getenv("TAMF_CHAIN_DBG")) : 0;
+  if (buf.stack && enc.d_wmaps) {
+    // ---- stack form: ONE persistent attention kernel (att_ctas CTAs, second stream) next to ONE persistent layer kernel
+    // (pairsS CTA pairs) for all layers; units of both walk the layers in order and meet only through the counters.
+    // Both grids are launched as clusters of 2 (whole TPCs) and together hold <= every SM once, so all CTAs of both are
+    // co-resident whatever the placement order: every agent's unit list is a subsequence of one topological order. ----
+    TAMF_CUDA_CHECK(cudaEventRecord(buf.ev_fork, s));
+    TAMF_CUDA_CHECK(cudaStreamWaitEvent(buf.side, buf.ev_fork, 0));
+    {
+      AttnTcMaps at;
+      at.kv = buf.tm_att_kv, at.o = buf.tm_att_o;
+      long long* k = kt();
+      rc = (d / enc.H == 128) ? launch_attn_tc<128>(at, buf.B, buf.S, enc.H, d, buf.side, nullptr, k, r_q, t_q, r_att, enc.L, buf.att_ctas)
+                              : launch_attn_tc<64>(at, buf.B, buf.S, enc.H, d, buf.side, nullptr, k, r_q, t_q, r_att, enc.L, buf.att_ctas);
+      if (rc) return rc;
+      mark_event(marks, s);  // (profiling: keeps one mark per kernel; the attention kernel runs on the side stream)
+    }
+    {
+      LayerParams p{};
+      fill_layer_params(p, enc, buf, 0);
+      p.n_inp = 3 * d;
+      p.sched_off = buf.schedS, p.sched = buf.schedS + buf.pairsS + 1;
+      p.wmaps = enc.d_wmaps, p.lw = enc.d_lw;
+      p.dbg = dbg;
+      p.ktime = kt();
+      if (g_dbg_trace_layer >= 0) p.trace = g_dbg_trace;
+      const LayerDev& w = enc.layers[0];
+      LayerMaps tm{&buf.tm_ATT128, &w.tm_out, &buf.tm_Xb, &buf.tm_Xlo128, &w.tm_w1, &buf.tm_H_st, &buf.tm_H128, &w.tm_w2,
+                   &enc.layers[1].tm_in, &buf.tm_QKV_st, &buf.tm_Xh_st, &buf.tm_Xl_st, &buf.tm_ident};
+      if ((rc = launch_layer_chain(tm, p, buf.pairsS, s))) return rc;
+    }
+    TAMF_CUDA_CHECK(cudaEventRecord(buf.ev_join, buf.side));
+    TAMF_CUDA_CHECK(cudaStreamWaitEvent(s, buf.ev_join, 0));
+    mark_event(marks, s);
+    return TAMF_OK;
+  }
   // debug: TAMF_FINE bit 0 = attention waits per sequence (else for the whole previous grid), bit 1 = the layer kernel
   // starts without a grid-wide wait
   static const int fine = getenv("TAMF_FINE") ? atoi(getenv("TAMF_FINE")) : 3;
@@ -514,6 +593,24 @@ extern "C" int tamf_layer_schedule(int M, int d, int ff, int n_inp, int slots, i
                TAMF_E_BADARG, "tamf_layer_schedule: bad argument");
   const LayerSchedule sc = build_layer_schedule(M, d, ff, n_inp, slots, layer_costs_from_env());
   TAMF_REQUIRE((int)sc.units.size() <= cap, TAMF_E_BADARG, "tamf_layer_schedule: units_out too small");
+  for (int i = 0; i <= sc.pairs; ++i) off_out[i] = sc.off[i];
+  for (size_t i = 0; i < sc.units.size(); ++i) units_out[i] = sc.units[i];
+  if (makespan_out) *makespan_out = sc.makespan;
+  return sc.pairs;
+}
+
+// Host-only: the schedule of the STACK form (all `layers` layers in one launch on `slots` pairs, attention on `att_ctas`
+// CTAs with `att_unit` cycles per (sequence, head) unit).  Unit codes: chain_code (kind << 28 | layer << 24 | m << 8 | n).
+extern "C" int tamf_stack_schedule(int M, int d, int ff, int layers, int slots, int att_ctas, int S, int heads,
+                                   double att_unit, int* off_out, int* units_out, int cap, double* makespan_out) {
+  using namespace tamf;
+  TAMF_REQUIRE(M > 0 && (d == 256 || d == 512) && ff > 0 && ff % 256 == 0 && layers >= 1 && layers <= CH_MAX_STACK_LAYERS &&
+                   slots >= 1 && off_out && units_out && S > 0 && heads > 0,
+               TAMF_E_BADARG, "tamf_stack_schedule: bad argument");
+  AttnModel am;
+  am.ctas = att_ctas, am.S = S, am.heads = heads, am.unit = att_unit > 0 ? att_unit : am.unit;
+  const LayerSchedule sc = build_stack_schedule(M, d, ff, layers, false, slots, layer_costs_from_env(), am);
+  TAMF_REQUIRE((int)sc.units.size() <= cap, TAMF_E_BADARG, "tamf_stack_schedule: units_out too small");
   for (int i = 0; i <= sc.pairs; ++i) off_out[i] = sc.off[i];
   for (size_t i = 0; i < sc.units.size(); ++i) units_out[i] = sc.units[i];
   if (makespan_out) *makespan_out = sc.makespan;

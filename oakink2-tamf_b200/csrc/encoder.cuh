@@ -34,9 +34,14 @@ struct LayerDev {
   CUtensorMap tm_in, tm_out, tm_w1, tm_w2;
 };
 
+struct LayerWeightPtrs;  // layer_chain.cuh
 struct EncoderStack {
   int d = 0, ff = 0, L = 0, H = 0;
   std::vector<LayerDev> layers;
+  // stack form of the layer kernel (one launch for all layers): per-layer weight tensor maps [L][4] (out_proj, linear1,
+  // linear2, in_proj of the NEXT layer) and parameter pointers [L] in device memory
+  CUtensorMap* d_wmaps = nullptr;
+  LayerWeightPtrs* d_lw = nullptr;
   int upload(DevPool& pool, const tamf_layer_weights* w, int d, int ff, int L, int H);
 };
 
@@ -67,7 +72,15 @@ struct EncoderBuffers {
   int tiles_m = 0, halves = 0;
   int *sched = nullptr, *schedL = nullptr;  // [pairs + 1 offsets | unit codes]: with / without the next in_proj
   int pairs = 0, pairsL = 0;
-  int make_maps(int d, int ff);
+  // stack form (TAMF_CHAIN=2): ONE persistent layer kernel on `pairsS` CTA pairs for all layers next to ONE persistent
+  // attention kernel on `att_ctas` CTAs (a second stream inside the same graph); same counters
+  bool stack = false;
+  int* schedS = nullptr;
+  int pairsS = 0, att_ctas = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int make_maps(int d, int ff, int layers = 0, int heads = 0);
+  void release();  // the side stream / events of the stack form (handle destruction)
 };
 // bytes of EncoderBuffers::aux for an [M, d] problem (256-byte multiple)
 size_t encoder_aux_bytes(int M, int d, int ff);

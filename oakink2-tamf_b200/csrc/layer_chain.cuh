@@ -51,6 +51,20 @@ namespace tamf {
 
 enum ChainKind { CK_LN1 = 0, CK_L1 = 1, CK_LN2 = 2, CK_INP = 3 };
 
+// Unit code: layer << 24 | kind << 28 is NOT used -- layout: bits 28-29 kind, 24-27 layer (stack form, else 0), 8-23 row
+// tile, 0-7 column tile.
+__host__ __device__ inline int chain_code(int layer, int kind, int m, int n) { return (kind << 28) | (layer << 24) | (m << 8) | n; }
+__host__ __device__ inline int chain_kind(int code) { return (code >> 28) & 3; }
+__host__ __device__ inline int chain_layer(int code) { return (code >> 24) & 15; }
+__host__ __device__ inline int chain_m(int code) { return (code >> 8) & 0xFFFF; }
+__host__ __device__ inline int chain_n(int code) { return code & 0xFF; }
+constexpr int CH_MAX_STACK_LAYERS = 16;
+
+struct LayerWeightPtrs {
+  const float* bias[4];             // as LayerParams::bias
+  const float *gamma[2], *beta[2];  // norm1, norm2
+};
+
 struct LayerParams {
   int M, d, ff, n_inp;                // n_inp = 3 d, or 0 when there is no next layer
   const float* bias[4];               // LN1: out_proj bias [d] | L1: linear1 bias [ff] | LN2: linear2 bias [d] | INP: [3d]
@@ -72,6 +86,10 @@ struct LayerParams {
   long long* trace;                   // debug only: [grid][GEMM_TRACE_SLOTS] clock64 stamps
   long long* ktime;                   // debug only: in-graph timing slots of this launch (common.cuh ktime_*)
   unsigned target_att;  // updates of rA[b] per layer: heads x ceil(S / 32) (attn_tc.cuh, one per stored 32-row slab)
+  // Stack form (ONE launch for all layers, encoder.cu): unit codes carry a layer index; the weights of layer l come from
+  // these device arrays instead of the kernel's own tensor maps / the pointers above (null in the per-layer form).
+  const CUtensorMap* wmaps;     // [L][4]: Wo, W1, W2, Win(next layer) -- 64-byte aligned, written by the host at upload
+  const LayerWeightPtrs* lw;    // [L]
   int dbg;
   int grid_wait;  // debug: wait for the whole previous grid instead of relying on the per-unit dependencies alone
 };
@@ -269,13 +287,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     // ===================== TMA producer (both CTAs of the pair) =====================
     uint32_t stage = 0, phase = 0;
     int it = 0;
+    const bool stalls = p.trace && (p.dbg & 16);  // debug: accumulate wait cycles (tools/stack_stalls.py, slots 64..)
+    long long st_dep = 0, st_empty = 0;
     const uint32_t full_leader = mapa_cluster(smem_u32(&full_bar[0]), 0);
     for (int ui = u_begin; ui < u_end; ++ui, ++it) {
       const int code = p.sched[ui];
-      const int kind = code >> 28, m = (code >> 8) & 0xFFFFF, n = code & 0xFF;
+      const int kind = chain_kind(code), m = chain_m(code), n = chain_n(code), ul = chain_layer(code);
       const int m0 = m * 256 + (int)rank * GEMM_BM, n0 = n * BN;
       const CUtensorMap* ta = kind == CK_LN1 ? &tmATT : (kind == CK_LN2 ? &tmH : &tmXh);
-      const CUtensorMap* tb = kind == CK_LN1 ? &tmWo : (kind == CK_L1 ? &tmW1 : (kind == CK_LN2 ? &tmW2 : &tmWin));
+      const CUtensorMap* tb = p.wmaps ? p.wmaps + ul * 4 + kind
+                                      : (kind == CK_LN1 ? &tmWo : (kind == CK_L1 ? &tmW1 : (kind == CK_LN2 ? &tmW2 : &tmWin)));
       const int num_kb = (kind == CK_LN2 ? p.ff : p.d) / 64;
       const int res_kb = (kind & 1) ? 0 : CH_RES_KB;  // LayerNorm units: the residual stages come FIRST
       const int total_kb = num_kb + res_kb;
@@ -293,11 +314,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           } while (seen < need);
         }
       };
-      wait_dep((uint32_t)(2 * it + (res_kb ? 1 : 2)));
+      {
+        const long long t0 = stalls ? clock64() : 0;
+        wait_dep((uint32_t)(2 * it + (res_kb ? 1 : 2)));
+        if (stalls) st_dep += clock64() - t0;
+      }
       if (lane == 0) CHAIN_TRACE_UNIT(0, it);
       for (int kk = 0; kk < total_kb; ++kk) {
-        if (res_kb && kk == res_kb) wait_dep((uint32_t)(2 * it + 2));
-        mbar_wait_q(&empty_bar[stage], phase ^ 1u);
+        if (res_kb && kk == res_kb) {
+          const long long t0 = stalls ? clock64() : 0;
+          wait_dep((uint32_t)(2 * it + 2));
+          if (stalls) st_dep += clock64() - t0;
+        }
+        {
+          const long long t0 = stalls ? clock64() : 0;
+          mbar_wait_q(&empty_bar[stage], phase ^ 1u);
+          if (stalls) st_empty += clock64() - t0;
+        }
         uint8_t* a_dst = sA + stage * CH_A_BYTES;
         uint8_t* b_dst = sB + stage * CH_B_BYTES;
         const uint32_t bar = full_leader + stage * 8;
@@ -322,6 +355,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       }
       if (lane == 0) CHAIN_TRACE_UNIT(1, it);
     }
+    if (stalls && lane == 0) {
+      long long* z = p.trace + (size_t)gridDim.x * GEMM_TRACE_SLOTS + (size_t)blockIdx.x * 8;
+      z[0] = st_dep, z[1] = st_empty, z[7] = it;
+    }
    } else if (warp == PW + 1) {
     // ===================== MMA issuer (leader CTA) =====================
     if (rank == 0) {
@@ -331,9 +368,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       bool ident_ready = false;
       int it = 0;
+      const bool stalls = p.trace && (p.dbg & 16);
+      long long st_full = 0, st_tempty = 0;
       for (int ui = u_begin; ui < u_end; ++ui, ++it) {
         const int code = p.sched[ui];
-        const int kind = code >> 28;
+        const int kind = chain_kind(code);
         const int num_kb = (kind == CK_LN2 ? p.ff : p.d) / 64;
         const int res_kb = (kind & 1) ? 0 : CH_RES_KB;
         const int total_kb = num_kb + res_kb;
@@ -341,11 +380,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           mbar_wait_q(ident_bar, 0);
           ident_ready = true;
         }
-        mbar_wait_q(&tempty_bar[acc], acc_phase ^ 1u);
+        {
+          const long long t0 = stalls ? clock64() : 0;
+          mbar_wait_q(&tempty_bar[acc], acc_phase ^ 1u);
+          if (stalls) st_tempty += clock64() - t0;
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kk = 0; kk < total_kb; ++kk) {
-          mbar_wait_q(&full_bar[stage], phase);
+          {
+            const long long t0 = stalls ? clock64() : 0;
+            mbar_wait_q(&full_bar[stage], phase);
+            if (stalls) st_full += clock64() - t0;
+          }
           tc_fence_after();
           if (lane == 0 && kk == 0) CHAIN_TRACE_UNIT(2, it);
           const uint32_t a_addr = smem_u32(sA + stage * CH_A_BYTES);
@@ -382,6 +429,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         if (lane == 0) CHAIN_TRACE_UNIT(3, it);
         if (++acc == 2) acc = 0, acc_phase ^= 1u;
       }
+      if (stalls && lane == 0) {
+        long long* z = p.trace + (size_t)gridDim.x * GEMM_TRACE_SLOTS + (size_t)blockIdx.x * 8;
+        z[2] = st_full, z[3] = st_tempty;
+      }
     }
    } else if (warp == PW + 2) {
     // ===================== dependency scout =====================
@@ -390,13 +441,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     // polling and fencing in the producer itself drained the ring at every unit boundary (+2 k cycles per tile,
     // measured).  No proxy fence: a counter is bumped only after the TMA stores have COMPLETED in L2, which is where the
     // producer's TMA loads read (no L1 in that path, nothing can be stale).
-    const unsigned li = (unsigned)p.launch_idx;
-    const unsigned t_ln = li * p.target_ln, t_h = li * p.target_h;
     const unsigned* r_att = p.ctr + 6 * tiles_m;
     int it = 0;
     for (int ui = u_begin; ui < u_end; ++ui, ++it) {
       const int code = p.sched[ui];
-      const int kind = code >> 28, m = (code >> 8) & 0xFFFFF;
+      const int kind = chain_kind(code), m = chain_m(code);
+      const unsigned li = (unsigned)(p.launch_idx + chain_layer(code));  // 1-based layer kernel index of the evaluation
+      const unsigned t_ln = li * p.target_ln, t_h = li * p.target_h;
       auto publish = [&](uint32_t v) {
         if (lane == 0) {
           // the inputs were written through the async proxy (TMA stores) and will be read through it (TMA loads of the
@@ -440,7 +491,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     uint32_t seq = 0;
     for (int ui = u_begin; ui < u_end; ++ui) {
       const int code = p.sched[ui];
-      const int kind = code >> 28, m = (code >> 8) & 0xFFFFF;
+      const int kind = chain_kind(code), m = chain_m(code);
       const int nsig = (kind & 1) ? 1 : 2;
       for (int j = 0; j < nsig; ++j, ++seq) {
         const int c = kind == CK_LN1 ? j : (kind == CK_L1 ? 2 : (kind == CK_LN2 ? 3 + j : 5));
@@ -456,21 +507,26 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   } else {
     // ===================== epilogue (warps 0..15, both CTAs) =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-    // LayerNorm parameters of this pair's column half for both norms (weights, constant over the chain).  LayerNorm unit
-    // (row tile, half h) always runs on a pair with pair % halves == h (host schedule).
-    {
+    // LayerNorm parameters of this pair's column half for both norms of the layer being processed (weights).  LayerNorm
+    // unit (row tile, half h) always runs on a pair with pair % halves == h (host schedule).  Stack form: restaged when
+    // the unit list moves on to the next layer (all 16 warps walk the same list: two barriers per switch).
+    auto weights_of = [&](int ul) -> const LayerWeightPtrs* { return p.lw ? p.lw + ul : nullptr; };
+    auto stage_ln = [&](int ul) {
+      const LayerWeightPtrs* lw = weights_of(ul);
       const int c0 = (pair % halves) * BN;
       for (int i = threadIdx.x; i < BN; i += PT) {
 #pragma unroll
         for (int ln = 0; ln < 2; ++ln) {
-          const float* b = p.bias[ln ? CK_LN2 : CK_LN1];
+          const float* b = lw ? lw->bias[ln ? CK_LN2 : CK_LN1] : p.bias[ln ? CK_LN2 : CK_LN1];
           s_ln[(ln * 3 + 0) * BN + i] = b ? b[c0 + i] : 0.f;
-          s_ln[(ln * 3 + 1) * BN + i] = p.gamma[ln][c0 + i];
-          s_ln[(ln * 3 + 2) * BN + i] = p.beta[ln][c0 + i];
+          s_ln[(ln * 3 + 1) * BN + i] = (lw ? lw->gamma[ln] : p.gamma[ln])[c0 + i];
+          s_ln[(ln * 3 + 2) * BN + i] = (lw ? lw->beta[ln] : p.beta[ln])[c0 + i];
         }
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");
-    }
+    };
+    int cur_layer = u_begin < u_end ? chain_layer(p.sched[u_begin]) : 0;
+    stage_ln(cur_layer);
     const int lq = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter (64 columns)
     const int row_in_tile = lq * 32 + lane;
     const uint32_t tempty_leader = mapa_cluster(smem_u32(&tempty_bar[0]), 0);
@@ -498,9 +554,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       }
     };
     int it = 0;
+    const bool stalls = p.trace && (p.dbg & 16);
+    long long st_tfull = 0, st_stats = 0;
     for (int ui = u_begin; ui < u_end; ++ui, ++it) {
       const int code = p.sched[ui];
-      const int kind = code >> 28, m = (code >> 8) & 0xFFFFF, n = code & 0xFF;
+      const int kind = chain_kind(code), m = chain_m(code), n = chain_n(code), ul = chain_layer(code);
+      if (ul != cur_layer) {
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // every warp has finished the previous layer's units
+        stage_ln(ul);
+        cur_layer = ul;
+      }
       const int n0 = n * BN;
       const int grow0 = m * 256 + (int)rank * GEMM_BM + lq * 32;  // first global row of this warp
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lq * 32) << 16) + cl;
@@ -510,9 +573,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
       };
       if (kind & 1) {
-        const int key = kind * 256 + n;
+        const int key = (ul * 4 + kind) * 256 + n;
         if (key != staged_key) {  // this warp's 64 bias values (a private slice: no barrier between the warps)
-          const float* bsrc = p.bias[kind];
+          const LayerWeightPtrs* lw = weights_of(ul);
+          const float* bsrc = lw ? lw->bias[kind] : p.bias[kind];
           const int c = n0 + cl + lane;
           __syncwarp();
           s_bias2[warp * 64 + lane] = bsrc ? bsrc[c] : 0.f;
@@ -525,7 +589,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       }
       if (!mbar_try_wait(&tfull_bar[acc], acc_phase)) {
         flush_pending();
+        const long long t0 = stalls ? clock64() : 0;
         mbar_wait_q(&tfull_bar[acc], acc_phase);
+        if (stalls) st_tfull += clock64() - t0;
       }
       tc_fence_after();
       if (threadIdx.x == 0) CHAIN_TRACE_UNIT(4, it);
@@ -590,6 +656,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
               __nanosleep(20);
               if (clock64() - t0 > 4000000000LL) __trap();
             }
+            if (stalls) st_stats += clock64() - t0;
           }
           st_relaxed_gpu_u64(p.stats + theirs, ~0ull);  // single reader: reset for the next launch
           tot_s += __uint_as_float((uint32_t)o), tot_q += __uint_as_float((uint32_t)(o >> 32));
@@ -739,12 +806,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     }
     flush_pending();
     if (elect_one()) bulk_wait<0>();  // this thread's TMA stores have been performed before the CTA retires
+    if (stalls && threadIdx.x == 0) {
+      long long* z = p.trace + (size_t)gridDim.x * GEMM_TRACE_SLOTS + (size_t)blockIdx.x * 8;
+      z[4] = st_tfull, z[5] = st_stats;
+    }
   }
   tc_fence_before();
   cluster_sync_all();  // the peer may still signal our barriers / read our TMEM half
   if (threadIdx.x == 0) {
     CHAIN_TRACE(3);
     ktime_exit(p.ktime);
+    if (p.trace && (p.dbg & 16)) p.trace[(size_t)gridDim.x * GEMM_TRACE_SLOTS + (size_t)blockIdx.x * 8 + 6] = clock64();  // (slot 0 holds the start)
   }
   if (warp == PW + 1) {
     tc_fence_after();
@@ -778,13 +850,26 @@ struct LayerCosts {
 // tile is a job for a DUO of neighbouring pairs (2k, 2k + 1: the two column halves run at the same list position and
 // exchange statistics).  Units are placed in order of their simulated start time, so every pair's list is a subsequence
 // of one global topological order.
-inline LayerSchedule build_layer_schedule(int M, int d, int ff, int n_inp, int slots, const LayerCosts& c) {
+// Attention side of the stack form: `ctas` persistent attention CTAs, `unit` cycles per (sequence, head) unit.
+struct AttnModel {
+  int ctas = 0, S = 1, heads = 1;
+  double unit = 9600.0;
+};
+
+// List scheduling of `L` layers of the per-row-tile chain LN1 -> L1 -> LN2 -> INP on `slots` CTA pairs.  L == 1 is the
+// per-layer form (one launch per layer; `last_has_inp` says whether the launch ends with the next layer's in_proj, all row
+// tiles are ready at t = 0).  L > 1 is the stack form (ONE launch for all layers; only the last layer has no INP): the
+// attention of a row tile between INP of layer l and LN1 of layer l + 1 runs on other SMs and is modelled as a server
+// with `att.ctas` units in flight.  Unit codes carry the layer (chain_code).
+inline LayerSchedule build_stack_schedule(int M, int d, int ff, int L, bool last_has_inp, int slots, const LayerCosts& c,
+                                          const AttnModel& att) {
   LayerSchedule s;
   s.tiles_m = (M + 255) / 256;
   s.halves = d / CH_BN;
-  const int T = s.tiles_m, H = s.halves, n1 = ff / CH_BN, n3 = n_inp / CH_BN;
+  const int T = s.tiles_m, H = s.halves, n1 = ff / CH_BN, n3 = 3 * d / CH_BN;
   int pairs = slots;
-  const long total_units = (long)T * (2 * H + n1 + n3);
+  const long units_full = (long)T * (2 * H + n1 + n3), units_last = (long)T * (2 * H + n1 + (last_has_inp ? n3 : 0));
+  const long total_units = units_full * (L - 1) + units_last;
   if ((long)pairs > total_units) pairs = (int)total_units;
   if (H == 2) pairs &= ~1;
   if (pairs < H) pairs = H;
@@ -809,9 +894,21 @@ inline LayerSchedule build_layer_schedule(int M, int d, int ff, int n_inp, int s
     return epi_end;
   };
   const double mma_ln1 = c.kb * d / 64 + c.res, mma_ln2 = c.kb * ff / 64 + c.res, mma_t = c.kb * d / 64;
-  // per row tile: stage (0 LN1 pending, 1 L1 tiles, 2 LN2 pending, 3 INP tiles, 4 done), tiles left, input-ready time
+  // per row tile: stage = 4 * layer + (0 LN1 pending, 1 L1 tiles, 2 LN2 pending, 3 INP tiles); 4 L = done
+  const int done_stage = 4 * L;
   std::vector<int> stage(T, 0), next_n(T, 0);
   std::vector<double> ready(T, 0.0), acc_ready(T, 0.0);
+  // attention server: time per row tile with all CTAs busy, and the latency of one unit
+  const double att_tile = att.ctas > 0 ? att.unit * att.heads * 256.0 / att.S / att.ctas : 0.0;
+  double att_free = 0.0;
+  auto attention = [&](double inputs_ready) {  // -> time at which the row tile's attention output is complete
+    if (att.ctas <= 0) return inputs_ready;
+    const double start = std::max(inputs_ready, att_free);
+    att_free = start + att_tile;
+    return att_free + att.unit;
+  };
+  if (L > 1)
+    for (int m = 0; m < T; ++m) ready[m] = attention(0.0);  // the first layer's attention, row tiles in order
   long remaining = total_units;
   std::vector<double> load(pairs, 0.0);  // tensor-pipe work assigned to a pair so far
   while (remaining > 0) {
@@ -822,8 +919,9 @@ inline LayerSchedule build_layer_schedule(int M, int d, int ff, int n_inp, int s
     int best_m = -1, best_pr = -1;
     double best_start = 1e300;
     for (int m = 0; m < T; ++m) {
-      if (stage[m] > 3) continue;
-      const bool ln = (stage[m] == 0 || stage[m] == 2);
+      if (stage[m] >= done_stage) continue;
+      const int k4 = stage[m] & 3;
+      const bool ln = (k4 == 0 || k4 == 2);
       const int step = ln ? H : 1;
       double st_min = 1e300;
       for (int k = 0; k + step <= pairs; k += step) {
@@ -839,7 +937,8 @@ inline LayerSchedule build_layer_schedule(int M, int d, int ff, int n_inp, int s
     }
     {
       const int m = best_m;
-      const bool ln = (stage[m] == 0 || stage[m] == 2);
+      const int k4 = stage[m] & 3;
+      const bool ln = (k4 == 0 || k4 == 2);
       const int step = ln ? H : 1;
       const double limit = best_start + 1e-3 * stage[m] + c.slack;
       double best_load = 1e300;
@@ -854,7 +953,8 @@ inline LayerSchedule build_layer_schedule(int M, int d, int ff, int n_inp, int s
       }
     }
     const int m = best_m;
-    const int st = stage[m];
+    const int st = stage[m] & 3, lay = stage[m] >> 2;
+    const bool has_inp = lay + 1 < L || last_has_inp;
     if (st == 0 || st == 2) {
       double done = 0, duo_start = ready[m];
       for (int h = 0; h < H; ++h) {
@@ -866,23 +966,24 @@ inline LayerSchedule build_layer_schedule(int M, int d, int ff, int n_inp, int s
         // both halves start together: feed the common start time as the ready time
         place(best_pr + h, duo_start, st == 0 ? mma_ln1 : mma_ln2, c.epi_ln, true, &es);
         done = std::max(done, es + c.ln_ready + c.signal);
-        lists[best_pr + h].push_back(((st == 0 ? CK_LN1 : CK_LN2) << 28) | (m << 8) | h);
+        lists[best_pr + h].push_back(chain_code(lay, st == 0 ? CK_LN1 : CK_LN2, m, h));
         load[best_pr + h] += st == 0 ? mma_ln1 : mma_ln2;
         --remaining;
       }
       ready[m] = done, acc_ready[m] = 0.0;
-      stage[m] = st + 1, next_n[m] = 0;
-      if (stage[m] == 3 && n3 == 0) stage[m] = 4;
+      ++stage[m], next_n[m] = 0;
+      if (st == 2 && !has_inp) stage[m] = 4 * (lay + 1);  // (only the last layer: the row tile is finished)
     } else {
       const int nt = st == 1 ? n1 : n3;
       const double end = place(best_pr, ready[m], mma_t, st == 1 ? c.epi_gelu : c.epi_bias, true, nullptr);
-      lists[best_pr].push_back(((st == 1 ? CK_L1 : CK_INP) << 28) | (m << 8) | next_n[m]);
+      lists[best_pr].push_back(chain_code(lay, st == 1 ? CK_L1 : CK_INP, m, next_n[m]));
       load[best_pr] += mma_t;
       --remaining;
       acc_ready[m] = std::max(acc_ready[m], end + c.signal);
       if (++next_n[m] == nt) {
-        stage[m] = st + 1;
-        ready[m] = acc_ready[m];  // LN2 needs every H tile of the row tile
+        ++stage[m];
+        // LN2 needs every H tile of the row tile; the next layer's LN1 the attention over the row tile's in_proj tiles
+        ready[m] = st == 1 ? acc_ready[m] : attention(acc_ready[m]);
       }
     }
   }
@@ -893,6 +994,11 @@ inline LayerSchedule build_layer_schedule(int M, int d, int ff, int n_inp, int s
     s.makespan = std::max(s.makespan, ps[pr].epi_free);
   }
   return s;
+}
+
+// One layer per launch (every row tile ready at t = 0); n_inp = 0: the last layer (no next in_proj).
+inline LayerSchedule build_layer_schedule(int M, int d, int ff, int n_inp, int slots, const LayerCosts& c) {
+  return build_stack_schedule(M, d, ff, 1, n_inp > 0, slots, c, AttnModel{});
 }
 
 inline int configure_layer_chain() {

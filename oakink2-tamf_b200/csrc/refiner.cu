@@ -82,6 +82,7 @@ struct tamf_refiner {
 
 extern "C" int tamf_refiner_destroy(tamf_refiner* h) {
   if (!h) return TAMF_OK;
+  h->buf.release();
   h->pool.free_all();
   delete h;
   return TAMF_OK;
@@ -218,7 +219,7 @@ extern "C" int tamf_refiner_bind(tamf_refiner* h, int B, int T, void* ws, size_t
   h->shapemean = (float*)(p + L.off[11]);
   h->embmean = (float*)(p + L.off[12]);
   int rc;
-  if ((rc = h->buf.make_maps(h->d, h->ff))) return rc;
+  if ((rc = h->buf.make_maps(h->d, h->ff, h->enc.L, h->enc.H))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_A0, h->A0, R_K, h->Mf, (uint64_t)R_K * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_H0, h->H0, h->d, h->Mf, (uint64_t)h->d * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&h->tm_H0_st, h->H0, h->d, h->Mf, (uint64_t)h->d * 2, 64, 32))) return rc;
@@ -275,6 +276,7 @@ extern "C" int tamf_refiner_forward(tamf_refiner* h, const float* sample_pose_re
   }
   if ((rc = enqueue_encoder(h->enc, h->buf, s, nullptr))) return rc;
   {
+    PdlBlock no_early_launch(h->buf.stack);  // (see denoiser.cu: the kernel after the encoder's stack form)
     GemmParams p{};
     p.M = M, p.N = h->nfeat, p.K = d, p.bias = h->b_fin, p.T = T, p.S = S, p.P0 = R_PREFIX, p.nfeat = h->nfeat;
     p.x_t = sample_pose_repr, p.x_out = refine_out;

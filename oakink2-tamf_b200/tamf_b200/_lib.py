@@ -23,7 +23,7 @@ SYMBOLS = [
     "tamf_gemm_selftest", "tamf_refiner_create", "tamf_refiner_destroy", "tamf_refiner_workspace_bytes",
     "tamf_refiner_bind", "tamf_refiner_forward", "tamf_mano_fk_select", "tamf_vertex_normals", "tamf_gemm_trace",
     "tamf_attn_selftest", "tamf_attn_trace", "tamf_denoiser_set_sampler", "tamf_denoiser_sampler_steps",
-    "tamf_layer_aux_bytes", "tamf_layer_run", "tamf_debug_chain_trace", "tamf_layer_schedule",
+    "tamf_layer_aux_bytes", "tamf_layer_run", "tamf_debug_chain_trace", "tamf_layer_schedule", "tamf_stack_schedule",
 ]
 
 
@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
     L.tamf_layer_run.argtypes = [vp] * 12 + [i32, i32, i32, i32, vp, sz, vp, vp]
     L.tamf_debug_chain_trace.argtypes = [vp, i32]
     L.tamf_layer_schedule.argtypes = [i32, i32, i32, i32, i32, vp, vp, i32, vp]
+    L.tamf_stack_schedule.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, C.c_double, vp, vp, i32, vp]
     _lib = L
     return L
 
