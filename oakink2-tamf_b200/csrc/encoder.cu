@@ -276,8 +276,10 @@ int EncoderBuffers::make_maps(int d, int ff, int layers, int heads) {
   if ((rc = make_tmap_2d_bf16(&tm_ATT128, ATT, d, M, (uint64_t)d * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_H128, Hb, ff, M, (uint64_t)ff * 2, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tm_Xlo128, Xlo, d, M, (uint64_t)d * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tm_Xh_st, Xb, d, M, (uint64_t)d * 2, 64, 32))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tm_Xl_st, Xlo, d, M, (uint64_t)d * 2, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_Xh_st, Xb, d, M, (uint64_t)d * 2, 32, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_Xl_st, Xlo, d, M, (uint64_t)d * 2, 32, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_H_st32, Hb, ff, M, (uint64_t)ff * 2, 32, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tm_QKV_st32, QKV, 3 * d, M, (uint64_t)3 * d * 2, 32, 32))) return rc;
   if ((rc = chain_identity_map(&tm_ident))) return rc;
   const ChainLayout lay = chain_layout(M, d, ff);
   tiles_m = lay.tiles_m, halves = lay.halves;
@@ -410,8 +412,8 @@ static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& 
       p.ktime = kt();
       if (g_dbg_trace_layer >= 0) p.trace = g_dbg_trace;
       const LayerDev& w = enc.layers[0];
-      LayerMaps tm{&buf.tm_ATT128, &w.tm_out, &buf.tm_Xb, &buf.tm_Xlo128, &w.tm_w1, &buf.tm_H_st, &buf.tm_H128, &w.tm_w2,
-                   &enc.layers[1].tm_in, &buf.tm_QKV_st, &buf.tm_Xh_st, &buf.tm_Xl_st, &buf.tm_ident};
+      LayerMaps tm{&buf.tm_ATT128, &w.tm_out, &buf.tm_Xb, &buf.tm_Xlo128, &w.tm_w1, &buf.tm_H_st32, &buf.tm_H128, &w.tm_w2,
+                   &enc.layers[1].tm_in, &buf.tm_QKV_st32, &buf.tm_Xh_st, &buf.tm_Xl_st, &buf.tm_ident};
       if ((rc = launch_layer_chain(tm, p, buf.pairsS, s))) return rc;
     }
     TAMF_CUDA_CHECK(cudaEventRecord(buf.ev_join, buf.side));
@@ -444,8 +446,8 @@ static int enqueue_encoder_chain(const EncoderStack& enc, const EncoderBuffers& 
     p.grid_wait = !(fine & 2);
     p.ktime = kt();
     if (l == g_dbg_trace_layer) p.trace = g_dbg_trace;
-    LayerMaps tm{&buf.tm_ATT128, &w.tm_out, &buf.tm_Xb, &buf.tm_Xlo128, &w.tm_w1, &buf.tm_H_st, &buf.tm_H128, &w.tm_w2,
-                 last ? nullptr : &enc.layers[l + 1].tm_in, last ? nullptr : &buf.tm_QKV_st, &buf.tm_Xh_st, &buf.tm_Xl_st,
+    LayerMaps tm{&buf.tm_ATT128, &w.tm_out, &buf.tm_Xb, &buf.tm_Xlo128, &w.tm_w1, &buf.tm_H_st32, &buf.tm_H128, &w.tm_w2,
+                 last ? nullptr : &enc.layers[l + 1].tm_in, last ? nullptr : &buf.tm_QKV_st32, &buf.tm_Xh_st, &buf.tm_Xl_st,
                  &buf.tm_ident};
     if ((rc = launch_layer_chain(tm, p, last ? buf.pairsL : buf.pairs, s))) return rc;
     mark_event(marks, s);
@@ -545,15 +547,15 @@ extern "C" int tamf_layer_run(const uint16_t* att, const uint16_t* w_out, const 
   if ((rc = make_tmap_2d_bf16(&tXh, Xh, d, M, pd, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tXl, Xl, d, M, pd, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tW1, w1, d, ff, pd, 64, wbox))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tHst, Hbuf, ff, M, pf, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tHst, Hbuf, ff, M, pf, 32, 32))) return rc;
   if ((rc = make_tmap_2d_bf16(&tH, Hbuf, ff, M, pf, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(&tW2, w2, ff, d, pf, 64, wbox))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tXhs, Xh, d, M, pd, 64, 32))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tXls, Xl, d, M, pd, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tXhs, Xh, d, M, pd, 32, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tXls, Xl, d, M, pd, 32, 32))) return rc;
   if ((rc = chain_identity_map(&tI))) return rc;
   if (n_inp) {
     if ((rc = make_tmap_2d_bf16(&tWin, w_in, d, n_inp, pd, 64, wbox))) return rc;
-    if ((rc = make_tmap_2d_bf16(&tQst, qkv, n_inp, M, (uint64_t)n_inp * 2, 64, 32))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tQst, qkv, n_inp, M, (uint64_t)n_inp * 2, 32, 32))) return rc;
   }
   const LayerSchedule sc = build_layer_schedule(M, d, ff, n_inp, num_sms() / 2, layer_costs_from_env());
   uint8_t* a = static_cast<uint8_t*>(aux);

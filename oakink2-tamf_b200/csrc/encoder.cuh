@@ -64,7 +64,8 @@ struct EncoderBuffers {
   void* aux = nullptr;                // caller-owned (workspace): counters, row statistics, schedules
   CUtensorMap tm_ATT128, tm_H128;     // A operands of LN1 / LN2, box {64, 128}
   CUtensorMap tm_Xlo128;              // low residual plane, box {64, 128} (the high plane is tm_Xb)
-  CUtensorMap tm_Xh_st, tm_Xl_st;     // residual planes, box {64, 32}: LayerNorm result stores
+  CUtensorMap tm_Xh_st, tm_Xl_st;     // residual planes, box {32, 32}: LayerNorm result stores (half-slab staging tiles)
+  CUtensorMap tm_H_st32, tm_QKV_st32; // H / QKV stores of the layer kernel, box {32, 32}
   CUtensorMap tm_ident;               // 64 x 64 identity (layer_chain.cuh chain_identity_map)
   unsigned* ctr = nullptr;            // [6][tiles_m] row-tile counters + [B] sequence counters (layer_chain.cuh)
   size_t ctr_bytes = 0;

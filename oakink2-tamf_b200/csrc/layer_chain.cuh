@@ -97,13 +97,15 @@ struct LayerParams {
 // 20 warps = 5 warpgroups: 16 epilogue warps, then one warpgroup with the TMA producer (16), the MMA issuer (17), the
 // dependency scout (18) and the signal warp (19); register reallocation (setmaxnreg) always involves whole warpgroups.
 constexpr int CH_THREADS = GEMM_EPI_THREADS + 128;
-constexpr int CH_STAGES = 4;
+constexpr int CH_STAGES = 5;
 constexpr int CH_BN = 256;
 constexpr int CH_A_BYTES = GEMM_BM * 64 * 2;       // 128 rows x 64 k
 constexpr int CH_B_BYTES = (CH_BN / 2) * 64 * 2;   // this CTA's half of the 256 W rows
 constexpr int CH_STAGE_BYTES = CH_A_BYTES + CH_B_BYTES;
 constexpr int CH_PIPE_BYTES = CH_STAGES * CH_STAGE_BYTES;
-constexpr int CH_STG_BYTES = GEMM_EPI_WARPS * GEMM_STG_WARP;
+constexpr int CH_STG_WARP = 2048;                 // warp-private staging tile: 32 rows x 32 bf16 columns (64-byte rows, 64 B swizzle);
+                                                  // a warp's 32 x 64 slab leaves as TWO TMA stores, which frees the 32 KB of a fifth ring stage
+constexpr int CH_STG_BYTES = GEMM_EPI_WARPS * CH_STG_WARP;
 constexpr int CH_IDENT_BYTES = 32 * 128;  // this CTA's 32 rows of the 64 x 64 bf16 identity (K-major, 128-byte swizzle)
 constexpr int CH_SIG_BARS = 16;           // output-signal barriers of a CTA in flight (a warp runs < 2 units = 4 signals ahead)
 constexpr int CH_RES_KB = 4;              // residual ring stages of a LayerNorm unit: 2 planes x 2 stages, each holding
@@ -133,7 +135,9 @@ __device__ __forceinline__ void red_relaxed_gpu_add(unsigned* p, unsigned v) {
 }
 
 // Bounded mbarrier wait without printf (a call site keeps many registers alive around it; the trap alone reports the
-// protocol bug as a CUDA error).
+// protocol bug as a CUDA error).  All lanes re-issue try_wait.  Tried against the board's power cap and rejected: one
+// waiting lane with a 20 us suspend-time hint + warp sync (5 % slower: the parked lane wakes late); __nanosleep(100)
+// between the polls of the epilogue and signal warps (no change in time, clock or power).
 __device__ __forceinline__ void mbar_wait_q(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -177,7 +181,7 @@ __device__ __forceinline__ long long chain_globaltimer() {
 
 // Tensor maps.  tmATT / tmH / tmXh / tmXl: A operands [M, K] with box {64, 128} (tmXh = Xb is the A operand of L1 and INP
 // AND the high residual plane, tmXl = Xlo the low one); tmWo / tmW1 / tmW2 / tmWin: weights [N, K], box {64, 128};
-// tmHst / tmQst: bf16 outputs H / QKV, box {64, 32}; tmXh_st / tmXl_st: the residual planes with box {64, 32};
+// tmHst / tmQst: bf16 outputs H / QKV, box {32, 32} (64 B swizzle); tmXh_st / tmXl_st: the residual planes, box {32, 32};
 // tmI: the 64 x 64 identity, box {64, 32}.
 __global__ void __launch_bounds__(CH_THREADS, 1)
     layer_chain_kernel(const __grid_constant__ CUtensorMap tmATT, const __grid_constant__ CUtensorMap tmWo,
@@ -530,7 +534,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     const int lq = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter (64 columns)
     const int row_in_tile = lq * 32 + lane;
     const uint32_t tempty_leader = mapa_cluster(smem_u32(&tempty_bar[0]), 0);
-    const uint32_t wst = smem_u32(s_stage) + warp * GEMM_STG_WARP;
+    const uint32_t wst = smem_u32(s_stage) + warp * CH_STG_WARP;
     const int cl = cq * 64;  // first column of this warp's slab inside the 256-column tile
     uint32_t acc = 0, acc_phase = 0, ln_count = 0;
     int staged_key = -1;
@@ -678,7 +682,21 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         const f32x2 rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
         // y = ((acc - mean) rstd) gamma + beta on packed pairs; the hi plane bf16(y) goes to the staging tile, the
         // register pair is replaced by the lo plane's input y - bf16(y) (exact in fp32)
-        auto norm_hi = [&](uint32_t (&v)[32], int cbase, int j0) {
+        // The warp's staging tile holds 32 columns: the 64-column slab leaves in two halves per plane, each half staged
+        // once the previous half's store has finished READING the tile (the math of the next half runs under that read).
+        auto wait_tile_free = [&]() {
+          if (elect_one()) bulk_wait_read<0>();
+          __syncwarp();
+        };
+        auto store_half = [&](const CUtensorMap* tm, int col) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one() && !(p.dbg & 1)) {
+            tma_store_2d(tm, wst, col, grow0);  // rows past M are clipped by the tensor map
+            bulk_commit();
+          }
+        };
+        auto norm_hi = [&](uint32_t (&v)[32], int cbase, bool wait_first) {
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             uint32_t hi[4];
@@ -694,45 +712,32 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
               const f32x2 r = add2(y, pk2(-bf16lo_f32(hi[e]), -bf16hi_f32(hi[e])));
               v[c] = __float_as_uint(pk_lo(r)), v[c + 1] = __float_as_uint(pk_hi(r));
             }
-            sts128(wst + stg128_off(lane, j0 + jj), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            if (wait_first && jj == 0) wait_tile_free();  // (after the first chunk's math)
+            sts128(wst + stg64_off(lane, jj), make_uint4(hi[0], hi[1], hi[2], hi[3]));
           }
         };
-        norm_hi(v0, cl, 0);
-        norm_hi(v1, cl + 32, 4);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (elect_one() && !(p.dbg & 1)) {
-          tma_store_2d(&tmXh_st, wst, col0, grow0);  // rows past M are clipped by the tensor map
-          bulk_commit();
-        }
-        if (threadIdx.x == 0 && it == 0) CHAIN_TRACE(59);  // hi plane staged + store issued
-        if (elect_one()) bulk_wait_read<0>();  // the hi store has finished reading the tile
-        __syncwarp();
+        norm_hi(v0, cl, false);
+        store_half(&tmXh_st, col0);
+        norm_hi(v1, cl + 32, true);
+        store_half(&tmXh_st, col0 + 32);
+        if (threadIdx.x == 0 && it == 0) CHAIN_TRACE(59);  // hi plane staged + stores issued
+        auto stage_lo = [&](const uint32_t (&v)[32]) {  // lo = bf16(y - bf16(y)), the difference is in v
+          uint32_t lo[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) lo[q] = pack_bf16x2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+          wait_tile_free();
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            sts128(wst + stg64_off(lane, jj), make_uint4(lo[4 * jj], lo[4 * jj + 1], lo[4 * jj + 2], lo[4 * jj + 3]));
+        };
+        stage_lo(v0);
         if (threadIdx.x == 0 && it == 0) CHAIN_TRACE(60);
-        auto stage_lo = [&](const uint32_t (&v)[32], int j0) {  // lo = bf16(y - bf16(y)), the difference is in v
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            uint32_t lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              lo[e] = pack_bf16x2(__uint_as_float(v[jj * 8 + 2 * e]), __uint_as_float(v[jj * 8 + 2 * e + 1]));
-            sts128(wst + stg128_off(lane, j0 + jj), make_uint4(lo[0], lo[1], lo[2], lo[3]));
-          }
-        };
-        stage_lo(v0, 0);
-        stage_lo(v1, 4);
-        fence_proxy_async_smem();
-        __syncwarp();
-        // The HIGH plane (the A operand of the L1 / INP units of this row tile) is complete in L2 -> bump the row tile's
-        // counter.  The update is relaxed: the store has COMPLETED, the rows are in L2 (where TMA loads read) before the
-        // update is even issued; a release would add a gpu-scope fence, 3.3 k cycles on the critical path (measured).
+        store_half(&tmXl_st, col0);
+        // The HIGH plane (the A operand of the L1 / INP units of this row tile) is announced as soon as its two stores
+        // have completed: all but the newest bulk group of this thread.
         if (elect_one()) {
-          if (!(p.dbg & 1)) {
-            tma_store_2d(&tmXl_st, wst, col0, grow0);
-            bulk_commit();
-          }
           if (threadIdx.x == 0 && it == 0) CHAIN_TRACE(61);
-          bulk_wait<1>();  // all but the newest group: the hi-plane store of this warp has completed
+          bulk_wait<1>();
           if (threadIdx.x == 0 && it == 0) {
             CHAIN_TRACE(62);
             CHAIN_TRACE_NS(55);
@@ -742,6 +747,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
                       (unsigned long long)chain_globaltimer());
           mbar_arrive(&sig_bar[sig_seq & (CH_SIG_BARS - 1)]);
         }
+        __syncwarp();
+        stage_lo(v1);
+        store_half(&tmXl_st, col0 + 32);
         __syncwarp();
         // the low plane is the residual input of the next LayerNorm of this row tile (LN2 here, LN1 of the next layer
         // kernel): owed once the store has completed
@@ -756,46 +764,54 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           if (elect_one()) bulk_wait_read<0>();  // the previous unit's store has finished reading the staging tile
           __syncwarp();
         }
-        auto half = [&](const uint32_t (&vv)[32], int j0, auto gelu) {
+        // 32 columns at a time: the second half is computed into registers while the first half's store reads the tile
+        auto half = [&](const uint32_t (&vv)[32], int j0, uint32_t (&o)[16], auto gelu) {
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int j = j0 + jj;
             const uint32_t* v = vv + jj * 8;
-            uint32_t o[4];
             if constexpr (decltype(gelu)::value) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {  // packed pairs: bias add + GELU as FADD2 / FFMA2 chains
                 const float2 b2 = *reinterpret_cast<const float2*>(wb + j * 8 + 2 * e);
                 const f32x2 y = gelu_erf2(add2(pk2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), pk2(b2.x, b2.y)));
-                o[e] = pack_bf16x2(pk_lo(y), pk_hi(y));
+                o[4 * jj + e] = pack_bf16x2(pk_lo(y), pk_hi(y));
               }
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 b2 = *reinterpret_cast<const float2*>(wb + j * 8 + 2 * e);
-                o[e] = pack_bf16x2(__uint_as_float(v[2 * e]) + b2.x, __uint_as_float(v[2 * e + 1]) + b2.y);
+                o[4 * jj + e] = pack_bf16x2(__uint_as_float(v[2 * e]) + b2.x, __uint_as_float(v[2 * e + 1]) + b2.y);
               }
             }
-            sts128(wst + stg128_off(lane, j), make_uint4(o[0], o[1], o[2], o[3]));
           }
         };
-        if (kind == CK_L1) {
-          half(v0, 0, std::true_type{});
-          tc_wait_ld_dep(v1);
-          release_acc();
-          half(v1, 4, std::true_type{});
-        } else {
-          half(v0, 0, std::false_type{});
-          tc_wait_ld_dep(v1);
-          release_acc();
-          half(v1, 4, std::false_type{});
-        }
-        fence_proxy_async_smem();
+        auto stage_store = [&](const uint32_t (&o)[16], int col) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            sts128(wst + stg64_off(lane, jj), make_uint4(o[4 * jj], o[4 * jj + 1], o[4 * jj + 2], o[4 * jj + 3]));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one() && !(p.dbg & 1)) {
+            tma_store_2d(kind == CK_L1 ? &tmHst : &tmQst, wst, col, grow0);  // rows past M are clipped
+            bulk_commit();
+          }
+        };
+        uint32_t o[16];
+        if (kind == CK_L1)
+          half(v0, 0, o, std::true_type{});
+        else
+          half(v0, 0, o, std::false_type{});
+        stage_store(o, n0 + cl);
+        tc_wait_ld_dep(v1);
+        release_acc();
+        if (kind == CK_L1)
+          half(v1, 4, o, std::true_type{});
+        else
+          half(v1, 4, o, std::false_type{});
+        if (elect_one()) bulk_wait_read<0>();  // the first half's store has finished reading the tile
         __syncwarp();
-        if (elect_one() && !(p.dbg & 1)) {
-          tma_store_2d(kind == CK_L1 ? &tmHst : &tmQst, wst, n0 + cl, grow0);  // rows past M are clipped
-          bulk_commit();
-        }
+        stage_store(o, n0 + cl + 32);
         // an H tile is an input of this row tile's LN2 units, a QKV tile of the attention CTAs of the next layer: owed
         // once the store has completed
         pending = true, pending_seq = sig_seq;
