@@ -288,7 +288,7 @@ def _dist_setup():
     return world, rank, local, dev
 
 
-def in_graph_breakdown(model, L, x, classes, n_steps=8):
+def in_graph_breakdown(model, L, x, classes, batch, n_steps=8, warm_steps=500):
     """Per-kernel figures INSIDE the captured step (tamf_denoiser_profile_graph: globaltimer stamps at every kernel's
     entry / end of its dependency wait / exit, the same graph and programmatic launches as the chain).  Returns
     {class: {"us": busy time ready->exit summed over its launches, "launches", "flops"}}, the step period and the share of
@@ -298,6 +298,9 @@ def in_graph_breakdown(model, L, x, classes, n_steps=8):
     cap = 128
     en, rd, ex = (C.c_double * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
     n_out, step_us = C.c_int(0), C.c_double(0)
+    # The board throttles under its power cap within tens of milliseconds: queue half a chain ahead (asynchronous), so
+    # that the stamped replays run at the SUSTAINED clock of the timed chain and not at the boost clock of an idle GPU.
+    model.p_sample_chain(x, DIFF_STEPS - 1, DIFF_STEPS - warm_steps, batch, seed=5)
     _lib.check(L.tamf_denoiser_profile_graph(model._handle, _lib.ptr(x), 700, n_steps, 11, en, rd, ex, cap, C.byref(n_out),
                                              C.byref(step_us), _lib.stream_ptr(x.device)), "profile_graph")
     n = n_out.value
@@ -446,7 +449,7 @@ def run_ours(args):
             if r >= 2:
                 for i, (name, _) in enumerate(classes):
                     iso[name] = iso.get(name, 0.0) + ms_buf[i] / args.profile_reps
-        per, step_us, idle = in_graph_breakdown(model, L, x, classes)
+        per, step_us, idle = in_graph_breakdown(model, L, x, classes, dev_batch)
         top = max(per, key=lambda k: per[k]["us"])
         c = per[top]
         achieved = c["flops"] / (c["us"] * 1e-6) / 1e12
@@ -463,7 +466,8 @@ def run_ours(args):
             "launch_us_in_graph": c["us"] / c["launches"], "launches_per_step": c["launches"],
             "flops_per_launch": c["flops"] / c["launches"], "share_of_step": c["us"] / step_us,
             "how": "globaltimer stamps (end of dependency wait -> last CTA exit) of every launch inside the captured "
-                   "step graph, mean of 3 replays (tamf_denoiser_profile_graph)",
+                   "step graph (tamf_denoiser_profile_graph), replayed right behind 500 steps of the chain so that the "
+                   "clock is the sustained one",
             "isolated": {"launch_ms": iso[top] / c["launches"],
                          "achieved": c["flops"] / (iso[top] * 1e-3) / 1e12, "peak": pk["burst"],
                          "frac": c["flops"] / (iso[top] * 1e-3) / 1e12 / pk["burst"],

@@ -563,8 +563,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     for (int ui = u_begin; ui < u_end; ++ui, ++it) {
       const int code = p.sched[ui];
       const int kind = chain_kind(code), m = chain_m(code), n = chain_n(code), ul = chain_layer(code);
-      if (ul != cur_layer) {
-        asm volatile("bar.sync 1, 512;" ::: "memory");  // every warp has finished the previous layer's units
+      if (!(kind & 1) && ul != cur_layer) {  // (only LayerNorm units read the staged parameters)
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // every warp has finished the LayerNorm units staged before
         stage_ln(ul);
         cur_layer = ul;
       }

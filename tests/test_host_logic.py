@@ -205,3 +205,77 @@ def test_encode_text_clip_branch(monkeypatch):
     assert out.dtype == torch.float32 and out.shape == (2, 4) and float(out[0, 0]) == 0.5
     m.encode_text(["again"])
     assert calls["tokenize"][0] == ["again"]  # the tower is loaded once
+
+
+def test_stack_schedule_is_complete_and_deadlock_free():
+    """The schedule of the stack form (TAMF_CHAIN=2: all layers in one launch, csrc/layer_chain.cuh build_stack_schedule):
+    every unit of every layer exactly once (the last layer without the next in_proj); LayerNorm halves on neighbouring
+    pairs; and a replay with the attention CTAs as agents of their own (unit g = (layer * B + b) * H + h on CTA g mod A, in
+    order) completes: every agent's list is a subsequence of one topological order."""
+    import ctypes as C
+    from tamf_b200 import _lib
+    lib = _lib.lib()
+    M, d, ff, L, slots, A, S, heads, B = 10560, 512, 2048, 8, 60, 28, 165, 4, 64
+    off = np.zeros(slots + 1, np.int32)
+    units = np.zeros(1 << 17, np.int32)
+    mk = C.c_double()
+    pairs = lib.tamf_stack_schedule(M, d, ff, L, slots, A, S, heads, 0.0, off.ctypes.data, units.ctypes.data, len(units),
+                                    C.byref(mk))
+    assert pairs == slots and mk.value > 0
+    T, H, n1, n3 = (M + 255) // 256, d // 256, ff // 256, 3 * d // 256
+    dec = lambda c: ((int(c) >> 24) & 15, (int(c) >> 28) & 3, (int(c) >> 8) & 0xFFFF, int(c) & 255)  # layer, kind, m, n
+    lists = [[dec(c) for c in units[off[p]:off[p + 1]]] for p in range(pairs)]
+    allu = [u for l in lists for u in l]
+    expect = set()
+    for l in range(L):
+        expect |= {(l, 0, m, h) for m in range(T) for h in range(H)} | {(l, 1, m, n) for m in range(T) for n in range(n1)}
+        expect |= {(l, 2, m, h) for m in range(T) for h in range(H)}
+        if l + 1 < L:
+            expect |= {(l, 3, m, n) for m in range(T) for n in range(n3)}
+    assert len(allu) == len(expect) and set(allu) == expect
+    for p, l in enumerate(lists):
+        for lay, k, m, n in l:
+            if k in (0, 2):
+                assert p % H == n and (lay, k, m, n ^ 1) in lists[p ^ 1]
+    # replay: GEMM pairs + attention CTAs
+    att_lists = [[g for g in range(a, L * B * heads, A)] for a in range(A)]
+    att_pos, pos = [0] * A, [0] * pairs
+    done = {}  # (layer, kind, m) -> finished units
+    att_done = {}  # (layer, b) -> finished heads
+    cnt = lambda key: done.get(key, 0)
+    left = len(allu) + L * B * heads
+    while left:
+        progressed = False
+        for a in range(A):
+            while att_pos[a] < len(att_lists[a]):
+                g = att_lists[a][att_pos[a]]
+                lay, b = g // (B * heads), (g // heads) % B
+                if lay > 0 and any(cnt((lay - 1, 3, m)) < n3 for m in range(b * S // 256, (b * S + S - 1) // 256 + 1)):
+                    break
+                att_done[(lay, b)] = att_done.get((lay, b), 0) + 1
+                att_pos[a] += 1
+                left -= 1
+                progressed = True
+        for p in range(pairs):
+            while pos[p] < len(lists[p]):
+                lay, k, m, n = lists[p][pos[p]]
+                if k == 0:
+                    b0, b1 = m * 256 // S, min(B - 1, (m * 256 + 255) // S)
+                    ok = all(att_done.get((lay, b), 0) == heads for b in range(b0, b1 + 1))
+                    ok = ok and (lay == 0 or cnt((lay - 1, 2, m)) == H)
+                elif k == 1:
+                    ok = cnt((lay, 0, m)) == H
+                elif k == 2:
+                    ok = cnt((lay, 1, m)) == n1
+                else:
+                    ok = cnt((lay, 2, m)) == H
+                if ok and k in (0, 2):  # the partner half must be the partner pair's next unit, or already done
+                    q = p ^ 1
+                    ok = (lay, k, m, n ^ 1) in lists[q][pos[q]:pos[q] + 1] or (lay, k, m, n ^ 1) in lists[q][:pos[q]]
+                if not ok:
+                    break
+                done[(lay, k, m)] = cnt((lay, k, m)) + 1
+                pos[p] += 1
+                left -= 1
+                progressed = True
+        assert progressed, "the stack schedule deadlocks"

@@ -58,3 +58,23 @@ def test_sample_then_refine_launchers(tmp_path):
                       "refine_pose_repr"}
     assert d["refine_pose_repr"].shape == (24, 99) and d["joints"].shape == (24, 21, 3) and d["verts"].shape == (24, 778, 3)
     assert d["process_key"] == "scene/003" and np.isfinite(d["verts"]).all()
+
+    # contact-ratio score over what sample_refine wrote (script/compute_score/compute_score_cr.py)
+    s_args = ["--data.source", f"items:{tmp_path / 'items.pkl'}", "--debug.synthetic_mano", "--runtime.device_id", "0",
+              "--debug.sample_refine_filepath", str(rout)]
+    r = _run("tamf_b200.launch.compute_score_cr", s_args, tmp_path)
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert lines[-2] == "(120,) (120,)"  # 5 items x 24 frames
+    gt_ratio, refined_ratio = (float(v) for v in lines[-1].split())
+    assert 0.0 <= gt_ratio <= 1.0 and 0.0 <= refined_ratio <= 1.0
+    gt = np.load(tmp_path / "tmp" / "compute_score" / "contact_ratio" / "gt_contact_dist.npy")
+    assert gt.shape == (120,) and np.isfinite(gt).all() and (gt >= 0).all()
+    # the minimum over the nearest-neighbour distances is the minimum of the full distance matrix
+    from tamf_b200 import transf_merge_obj_pointcloud
+    it = items[0]
+    merged = transf_merge_obj_pointcloud(np.asarray(it["obj_pointcloud"]), np.asarray(it["obj_traj"]))
+    with open(rout / "scene++000" / "0" / "0" / "save_dict.pkl", "rb") as f:
+        v0 = pickle.load(f)["verts"]
+    ref = np.sqrt(((v0[:, :, None, :] - merged[:, None, :, :]) ** 2).sum(-1)).reshape(24, -1).min(1)
+    got = np.load(tmp_path / "tmp" / "compute_score" / "contact_ratio" / "refined_contact_dist.npy")[:24]
+    assert np.abs(got - ref).max() < 1e-5
