@@ -358,6 +358,8 @@ static void fill_layer_params(LayerParams& p, const EncoderStack& enc, const Enc
   p.target_ln = (unsigned)(buf.halves * 2 * GEMM_EPI_WARPS);
   p.target_h = (unsigned)((enc.ff / CH_BN) * 2 * GEMM_EPI_WARPS);
   p.target_att = (unsigned)(enc.H * ((buf.S + 31) / 32));
+  static const int env_ooo = getenv("TAMF_CHAIN_OOO") ? atoi(getenv("TAMF_CHAIN_OOO")) : 0;
+  p.ooo = std::max(0, std::min(env_ooo, 24));  // run-time unit selection window (0: list order)
 }
 
 // The dependency counters of an evaluation start from zero.  Called ahead of the FIRST kernel of the evaluation (so that the

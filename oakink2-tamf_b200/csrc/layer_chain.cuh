@@ -90,6 +90,11 @@ struct LayerParams {
   // these device arrays instead of the kernel's own tensor maps / the pointers above (null in the per-layer form).
   const CUtensorMap* wmaps;     // [L][4]: Wo, W1, W2, Win(next layer) -- 64-byte aligned, written by the host at upload
   const LayerWeightPtrs* lw;    // [L]
+  int ooo;   // > 0: run-time unit selection -- the leader's scout emits any READY unit among the next `ooo` of the pair's
+             // list (LayerNorm units in list order); 0 (default): the list order, waiting for each unit in turn.
+             // EXPERIMENTAL (TAMF_CHAIN_OOO): parity-green, but 4-6 % slower than the list order in both forms -- the
+             // scan + the relay to the peer CTA sit on every unit's critical path, the scout cannot clear units ahead of
+             // time and the residual-first phase is lost (profiles/r02_exp_stack_form.txt)
   int dbg;
   int grid_wait;  // debug: wait for the whole previous grid instead of relying on the per-unit dependencies alone
 };
@@ -209,6 +214,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_bar + 1);
   uint32_t* s_dep = tmem_slot + 1;  // units whose dependencies the scout warp has seen satisfied
   uint64_t* sig_bar = reinterpret_cast<uint64_t*>(s_dep + 1);  // [CH_SIG_BARS] output signals owed by this CTA (signal warp)
+  // Order of execution: s_order[k & 15] = code of the k-th unit this pair runs, written by the scout BEFORE it publishes
+  // 2 k + 1 / 2 k + 2 in s_dep (every other warp reads the unit from here).  s_prog[r]: units whose signals the signal
+  // warp of CTA r has published (ring space); s_prod: units the producer has finished loading (late binding);
+  // s_inbox: (rank 1, run-time selection) the leader scout's choices, one self-validating 64-bit word per ring entry.
+  int* s_order = reinterpret_cast<int*>(sig_bar + CH_SIG_BARS);
+  uint32_t* s_prog = reinterpret_cast<uint32_t*>(s_order + 16);
+  uint32_t* s_prod = s_prog + 2;
+  unsigned long long* s_inbox = reinterpret_cast<unsigned long long*>(s_prod + 2);  // [16] (rank 1, run-time selection)
   float* s_ln = reinterpret_cast<float*>(ctrl + CH_CTRL_BYTES);  // [2 LN][bias | gamma | beta][256]
   float* s_bias2 = s_ln + 6 * BN;           // [16 warps][64]
   float* s_stat = s_bias2 + PW * 64;        // [2 buffers][sum, sq][4 column quarters][128 rows]
@@ -219,6 +232,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   const int halves = p.d / BN;
   const int tiles_m = p.tiles_m;
   const int u_begin = p.sched_off[pair], u_end = p.sched_off[pair + 1];  // host data (written at bind time)
+  const int n_units = u_end - u_begin;
+  // every warp but the scout takes the k-th unit from s_order once the scout has published it (phase 1: the residual
+  // planes of a LayerNorm unit may be loaded; phase 2: everything may)
+  auto dep_seen = [&]() {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(s_dep)) : "memory");
+    return v;
+  };
+  auto wait_published = [&](uint32_t need, unsigned sleep_ns) {
+    if (dep_seen() >= need) return;
+    const long long t0 = clock64();
+    while (dep_seen() < need) {
+      if (sleep_ns) __nanosleep(sleep_ns);
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  };
+  auto unit_code = [&](int k) { return *reinterpret_cast<volatile int*>(s_order + (k & 15)); };
 
   if (threadIdx.x == 0) {
     CHAIN_TRACE(0);
@@ -251,6 +281,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     mbar_init(ident_bar, 1);
     for (int i = 0; i < CH_SIG_BARS; ++i) mbar_init(&sig_bar[i], PW);  // one elected lane per epilogue warp of this CTA
     *s_dep = 0u;
+    s_prog[0] = 0u, s_prog[1] = 0u, *s_prod = 0u;
+    for (int i = 0; i < 16; ++i) s_inbox[i] = 0ull;
     fence_mbar_init();
   }
   if (warp == PW + 1) {
@@ -294,8 +326,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     const bool stalls = p.trace && (p.dbg & 16);  // debug: accumulate wait cycles (tools/stack_stalls.py, slots 64..)
     long long st_dep = 0, st_empty = 0;
     const uint32_t full_leader = mapa_cluster(smem_u32(&full_bar[0]), 0);
-    for (int ui = u_begin; ui < u_end; ++ui, ++it) {
-      const int code = p.sched[ui];
+    for (; it < n_units; ++it) {
+      {
+        const long long t0 = stalls ? clock64() : 0;
+        wait_published((uint32_t)(2 * it + 1), 100);  // (sleeping: a busy spin on all SMs is paid for in clock)
+        if (stalls) st_dep += clock64() - t0;
+      }
+      const int code = unit_code(it);
       const int kind = chain_kind(code), m = chain_m(code), n = chain_n(code), ul = chain_layer(code);
       const int m0 = m * 256 + (int)rank * GEMM_BM, n0 = n * BN;
       const CUtensorMap* ta = kind == CK_LN1 ? &tmATT : (kind == CK_LN2 ? &tmH : &tmXh);
@@ -304,23 +341,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       const int num_kb = (kind == CK_LN2 ? p.ff : p.d) / 64;
       const int res_kb = (kind & 1) ? 0 : CH_RES_KB;  // LayerNorm units: the residual stages come FIRST
       const int total_kb = num_kb + res_kb;
-      // dependencies: the scout warp publishes two phases per unit (2 it + 1: the residual planes of a LayerNorm unit
-      // are in L2; 2 it + 2: all inputs are)
-      auto wait_dep = [&](uint32_t need) {
-        uint32_t seen;
-        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_dep)) : "memory");
-        if (seen < need) {
-          const long long t0 = clock64();
-          do {
-            __nanosleep(100);  // the board runs at its power limit: a busy spin on all 148 SMs is paid for in clock
-            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_dep)) : "memory");
-            if (clock64() - t0 > 4000000000LL) __trap();
-          } while (seen < need);
-        }
-      };
-      {
+      auto wait_dep = [&](uint32_t need) { wait_published(need, 100); };
+      if (!res_kb) {
         const long long t0 = stalls ? clock64() : 0;
-        wait_dep((uint32_t)(2 * it + (res_kb ? 1 : 2)));
+        wait_dep((uint32_t)(2 * it + 2));
         if (stalls) st_dep += clock64() - t0;
       }
       if (lane == 0) CHAIN_TRACE_UNIT(0, it);
@@ -357,7 +381,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         __syncwarp();
         if (++stage == STAGES) stage = 0, phase ^= 1u;
       }
-      if (lane == 0) CHAIN_TRACE_UNIT(1, it);
+      if (lane == 0) {
+        CHAIN_TRACE_UNIT(1, it);
+        asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(s_prod)), "r"((uint32_t)(it + 1)) : "memory");
+      }
     }
     if (stalls && lane == 0) {
       long long* z = p.trace + (size_t)gridDim.x * GEMM_TRACE_SLOTS + (size_t)blockIdx.x * 8;
@@ -374,8 +401,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       int it = 0;
       const bool stalls = p.trace && (p.dbg & 16);
       long long st_full = 0, st_tempty = 0;
-      for (int ui = u_begin; ui < u_end; ++ui, ++it) {
-        const int code = p.sched[ui];
+      for (; it < n_units; ++it) {
+        wait_published((uint32_t)(2 * it + 1), 0);
+        const int code = unit_code(it);
         const int kind = chain_kind(code);
         const int num_kb = (kind == CK_LN2 ? p.ff : p.d) / 64;
         const int res_kb = (kind & 1) ? 0 : CH_RES_KB;
@@ -446,44 +474,157 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     // measured).  No proxy fence: a counter is bumped only after the TMA stores have COMPLETED in L2, which is where the
     // producer's TMA loads read (no L1 in that path, nothing can be stale).
     const unsigned* r_att = p.ctr + 6 * tiles_m;
-    int it = 0;
-    for (int ui = u_begin; ui < u_end; ++ui, ++it) {
-      const int code = p.sched[ui];
-      const int kind = chain_kind(code), m = chain_m(code);
-      const unsigned li = (unsigned)(p.launch_idx + chain_layer(code));  // 1-based layer kernel index of the evaluation
-      const unsigned t_ln = li * p.target_ln, t_h = li * p.target_h;
-      auto publish = [&](uint32_t v) {
-        if (lane == 0) {
-          // the inputs were written through the async proxy (TMA stores) and will be read through it (TMA loads of the
-          // producer warp): the acquire of the poll orders generic accesses only
-          asm volatile("fence.proxy.async;" ::: "memory");
-          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(s_dep)), "r"(v) : "memory");
+    // ring space: entry k & 15 of s_order may be rewritten once both CTAs' signal warps are done with unit k - 16
+    auto ring_space = [&](int k) {
+      if (lane == 0) {
+        const long long t0 = clock64();
+        for (;;) {
+          uint32_t a, b;
+          asm volatile("ld.relaxed.cta.shared::cta.u32 %0, [%1];" : "=r"(a) : "r"(smem_u32(&s_prog[0])) : "memory");
+          asm volatile("ld.relaxed.cta.shared::cta.u32 %0, [%1];" : "=r"(b) : "r"(smem_u32(&s_prog[1])) : "memory");
+          if (k - (int)min(a, b) < 12) break;
+          __nanosleep(100);
+          if (clock64() - t0 > 4000000000LL) __trap();
         }
-        __syncwarp();
-      };
-      if (kind == CK_LN1) {
-        // residual: the previous layer's LN2 planes of the row tile (low plane counter: a CTA announces it after both of
-        // its stores).  In the first layer the planes come from the embed kernels, ordered only through the attention
-        // kernel's grid-wide wait, so there the attention counters are waited for first.
-        const int b0 = (m * 256) / p.S, b1 = min(p.B - 1, (m * 256 + 255) / p.S);
-        if (li == 1u)
-          for (int b = b0; b <= b1; ++b) chain_wait_ge(r_att + b, li * p.target_att);
-        chain_wait_ge(p.ctr + 4 * tiles_m + m, (li - 1u) * p.target_ln);
-        publish((uint32_t)(2 * it + 1));
-        // the attention output of every sequence that overlaps the row tile
-        for (int b = b0; b <= b1; ++b) chain_wait_ge(r_att + b, li * p.target_att);
-      } else if (kind == CK_L1) {
-        chain_wait_ge(p.ctr + 0 * tiles_m + m, t_ln);  // LN1 high plane of the row tile
-      } else if (kind == CK_LN2) {
-        chain_wait_ge(p.ctr + 1 * tiles_m + m, t_ln);  // LN1 low plane (the residual of this unit)
-        publish((uint32_t)(2 * it + 1));
-        chain_wait_ge(p.ctr + 2 * tiles_m + m, t_h);   // every H tile of the row tile
-      } else {
-        chain_wait_ge(p.ctr + 3 * tiles_m + m, t_ln);  // LN2 high plane
       }
-      if (kind == CK_L1 && lane == 0 && p.trace && p.trace[(size_t)blockIdx.x * GEMM_TRACE_SLOTS + 54] == 0)
-        CHAIN_TRACE_NS(54);
-      publish((uint32_t)(2 * it + 2));
+      __syncwarp();
+    };
+    // the inputs were written through the async proxy (TMA stores) and will be read through it (TMA loads of the
+    // producer warp): the acquire of the poll orders generic accesses only
+    auto publish = [&](uint32_t v) {
+      if (lane == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(s_dep)), "r"(v) : "memory");
+      }
+      __syncwarp();
+    };
+    auto set_order = [&](int k, int code) {
+      if (lane == 0) *reinterpret_cast<volatile int*>(s_order + (k & 15)) = code;
+      __syncwarp();
+    };
+    // non-blocking: are all inputs of the unit in L2?  (one thread; acquire loads at gpu scope)
+    auto unit_ready = [&](int code) -> bool {
+      const int kind = chain_kind(code), m = chain_m(code);
+      const unsigned li = (unsigned)(p.launch_idx + chain_layer(code));
+      const unsigned t_ln = li * p.target_ln, t_h = li * p.target_h;
+      auto ge = [&](const unsigned* c, unsigned target) { return (int)(ld_acquire_gpu(c) - target) >= 0; };
+      if (kind == CK_LN1) {
+        if (!ge(p.ctr + 4 * tiles_m + m, (li - 1u) * p.target_ln)) return false;
+        const int b0 = (m * 256) / p.S, b1 = min(p.B - 1, (m * 256 + 255) / p.S);
+        for (int b = b0; b <= b1; ++b)
+          if (!ge(r_att + b, li * p.target_att)) return false;
+        return true;
+      }
+      if (kind == CK_L1) return ge(p.ctr + 0 * tiles_m + m, t_ln);
+      if (kind == CK_LN2) return ge(p.ctr + 1 * tiles_m + m, t_ln) && ge(p.ctr + 2 * tiles_m + m, t_h);
+      return ge(p.ctr + 3 * tiles_m + m, t_ln);
+    };
+    if (p.ooo <= 0) {
+      // ---- list order: wait for each unit in turn (both CTAs of the pair walk the same list on their own) ----
+      for (int it = 0; it < n_units; ++it) {
+        const int code = p.sched[u_begin + it];
+        const int kind = chain_kind(code), m = chain_m(code);
+        const unsigned li = (unsigned)(p.launch_idx + chain_layer(code));  // 1-based layer kernel index of the evaluation
+        const unsigned t_ln = li * p.target_ln, t_h = li * p.target_h;
+        ring_space(it);
+        set_order(it, code);
+        if (kind == CK_LN1) {
+          // residual: the previous layer's LN2 planes of the row tile (low plane counter: a CTA announces it after both
+          // of its stores).  In the first layer the planes come from the embed kernels, ordered only through the
+          // attention kernel's grid-wide wait, so there the attention counters are waited for first.
+          const int b0 = (m * 256) / p.S, b1 = min(p.B - 1, (m * 256 + 255) / p.S);
+          if (li == 1u)
+            for (int b = b0; b <= b1; ++b) chain_wait_ge(r_att + b, li * p.target_att);
+          chain_wait_ge(p.ctr + 4 * tiles_m + m, (li - 1u) * p.target_ln);
+          publish((uint32_t)(2 * it + 1));
+          // the attention output of every sequence that overlaps the row tile
+          for (int b = b0; b <= b1; ++b) chain_wait_ge(r_att + b, li * p.target_att);
+        } else if (kind == CK_L1) {
+          chain_wait_ge(p.ctr + 0 * tiles_m + m, t_ln);  // LN1 high plane of the row tile
+        } else if (kind == CK_LN2) {
+          chain_wait_ge(p.ctr + 1 * tiles_m + m, t_ln);  // LN1 low plane (the residual of this unit)
+          publish((uint32_t)(2 * it + 1));
+          chain_wait_ge(p.ctr + 2 * tiles_m + m, t_h);   // every H tile of the row tile
+        } else {
+          chain_wait_ge(p.ctr + 3 * tiles_m + m, t_ln);  // LN2 high plane
+        }
+        if (kind == CK_L1 && lane == 0 && p.trace && p.trace[(size_t)blockIdx.x * GEMM_TRACE_SLOTS + 54] == 0)
+          CHAIN_TRACE_NS(54);
+        publish((uint32_t)(2 * it + 2));
+      }
+    } else if (rank == 0) {
+      // ---- run-time selection (leader CTA decides for the pair): among the next p.ooo un-emitted units of the list,
+      // plus the earliest un-emitted LayerNorm unit (LayerNorm units keep their list order: both pairs of a duo hold the
+      // same LayerNorm sequence, and a half must never wait for a partner whose window does not reach it), emit the first
+      // one whose inputs are all in L2.  Late binding: at most two units ahead of the TMA producer.  The choice goes to
+      // the peer CTA as ONE 64-bit word (unit number + 1 | code) per ring entry, which its scout re-validates. ----
+      int head = 0, emitted = 0;
+      uint32_t mask = 0;  // bit k: unit head + k already emitted
+      long long t_idle = clock64();
+      while (emitted < n_units) {
+        ring_space(emitted);
+        uint32_t prod = 0;
+        if (lane == 0) asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(prod) : "r"(smem_u32(s_prod)) : "memory");
+        prod = __shfl_sync(0xffffffffu, prod, 0);
+        if (emitted - (int)prod >= 2) {
+          __nanosleep(60);
+          if (clock64() - t_idle > 4000000000LL) __trap();
+          continue;
+        }
+        const int k = lane;
+        const bool valid = head + k < n_units && !((mask >> k) & 1u);
+        const int code = valid ? p.sched[u_begin + head + k] : 0;
+        const bool is_ln = valid && !(chain_kind(code) & 1);
+        const uint32_t ln_bits = __ballot_sync(0xffffffffu, is_ln), valid_bits = __ballot_sync(0xffffffffu, valid);
+        const int before = __popc(valid_bits & ((1u << k) - 1u));
+        const bool eligible = valid && (is_ln ? (k == __ffs(ln_bits) - 1) : (before < p.ooo));
+        const bool ready = eligible && unit_ready(code);
+        const uint32_t rb = __ballot_sync(0xffffffffu, ready);
+        if (rb == 0u) {
+          __nanosleep(40);
+          if (clock64() - t_idle > 4000000000LL) __trap();
+          continue;
+        }
+        const int kk = __ffs(rb) - 1;
+        const int chosen = __shfl_sync(0xffffffffu, code, kk);
+        asm volatile("fence.proxy.async;" ::: "memory");  // (every lane: the ready lane's acquire is ordered before it)
+        __syncwarp();
+        if (lane == 0) {
+          const unsigned long long w = ((unsigned long long)(uint32_t)(emitted + 1) << 32) | (uint32_t)chosen;
+          asm volatile("st.relaxed.cluster.shared::cluster.u64 [%0], %1;" ::"r"(
+                           mapa_cluster(smem_u32(s_inbox + (emitted & 15)), 1)), "l"(w) : "memory");
+        }
+        set_order(emitted, chosen);
+        publish((uint32_t)(2 * emitted + 2));
+        mask |= 1u << kk;
+        ++emitted;
+        while (mask & 1u) mask >>= 1, ++head;
+        t_idle = clock64();
+      }
+    } else {
+      // ---- run-time selection, peer CTA: take the leader's choice from the inbox, acquire the unit's counters in THIS
+      // thread (they are satisfied: one pass; formally this CTA's TMA loads need their own acquire + proxy fence) ----
+      for (int it = 0; it < n_units; ++it) {
+        ring_space(it);
+        int code = 0;
+        if (lane == 0) {
+          const long long t0 = clock64();
+          unsigned long long w;
+          for (;;) {
+            asm volatile("ld.relaxed.cluster.shared::cta.u64 %0, [%1];" : "=l"(w) : "r"(smem_u32(s_inbox + (it & 15))) : "memory");
+            if ((uint32_t)(w >> 32) == (uint32_t)(it + 1)) break;
+            __nanosleep(40);
+            if (clock64() - t0 > 4000000000LL) __trap();
+          }
+          code = (int)(uint32_t)w;
+          while (!unit_ready(code)) {
+            if (clock64() - t0 > 4000000000LL) __trap();
+          }
+        }
+        code = __shfl_sync(0xffffffffu, code, 0);
+        set_order(it, code);
+        publish((uint32_t)(2 * it + 2));
+      }
     }
    } else {
     // ===================== signal warp =====================
@@ -493,8 +634,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     // warp), then publishes with a gpu-scope release: fence + counter update (cumulative over the 16 warps' stores).
     // Without the fence the dependents occasionally read stale rows (1 evaluation in ~300 at the production shape).
     uint32_t seq = 0;
-    for (int ui = u_begin; ui < u_end; ++ui) {
-      const int code = p.sched[ui];
+    const uint32_t prog_peer = mapa_cluster(smem_u32(&s_prog[rank]), rank ^ 1u);
+    for (int k = 0; k < n_units; ++k) {
+      wait_published((uint32_t)(2 * k + 1), 200);
+      const int code = unit_code(k);
       const int kind = chain_kind(code), m = chain_m(code);
       const int nsig = (kind & 1) ? 1 : 2;
       for (int j = 0; j < nsig; ++j, ++seq) {
@@ -505,6 +648,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           red_relaxed_gpu_add(p.ctr + c * tiles_m + m, (unsigned)PW);
         }
         __syncwarp();
+      }
+      if (lane == 0) {  // this CTA is done with entry k of the order ring (flow control of the scouts, both CTAs)
+        asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&s_prog[rank])), "r"((uint32_t)(k + 1)) : "memory");
+        asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(prog_peer), "r"((uint32_t)(k + 1)) : "memory");
       }
     }
    }
@@ -529,8 +676,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");
     };
-    int cur_layer = u_begin < u_end ? chain_layer(p.sched[u_begin]) : 0;
-    stage_ln(cur_layer);
+    int cur_layer = -1;  // staged at the first LayerNorm unit
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     const int lq = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter (64 columns)
     const int row_in_tile = lq * 32 + lane;
     const uint32_t tempty_leader = mapa_cluster(smem_u32(&tempty_bar[0]), 0);
@@ -560,8 +707,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     int it = 0;
     const bool stalls = p.trace && (p.dbg & 16);
     long long st_tfull = 0, st_stats = 0;
-    for (int ui = u_begin; ui < u_end; ++ui, ++it) {
-      const int code = p.sched[ui];
+    for (; it < n_units; ++it) {
+      if (dep_seen() < (uint32_t)(2 * it + 1)) {
+        flush_pending();  // (a warp never blocks while it owes a signal)
+        wait_published((uint32_t)(2 * it + 1), 100);
+      }
+      const int code = unit_code(it);
       const int kind = chain_kind(code), m = chain_m(code), n = chain_n(code), ul = chain_layer(code);
       if (!(kind & 1) && ul != cur_layer) {  // (only LayerNorm units read the staged parameters)
         asm volatile("bar.sync 1, 512;" ::: "memory");  // every warp has finished the LayerNorm units staged before
