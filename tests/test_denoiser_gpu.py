@@ -196,9 +196,20 @@ def test_b64_forward_and_chain_vs_live_oracle():
     r, a = rel_l2(out.numpy(), ref.numpy()), float((out - ref).abs().max())
     print(f"B=64 forward vs oracle rel_l2={r:.3e} max_abs={a:.3e}")
     assert r <= REL_TOL and a <= ABS_TOL
+    # (a') one p_sample with injected noise against the oracle's update of the oracle's own x0 (gaussian_diffusion.py:412-460)
+    tamf_b200.create_gaussian_diffusion(1000, "cosine")._install(m, "ancestral")
+    tq = 377
+    eps_in = torch.randn(B, 99, 1, T, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        x0_ref = orc.g_forward(sd, cfg, x, torch.full((B,), tq, dtype=torch.long), batch, text)
+        want = orc.p_sample_update(tab, x, x0_ref, tq, eps_in)
+    got = m.p_sample_step(x.cuda().clone(), tq, dbatch, noise=eps_in.cuda())
+    r, a = rel_l2(got["sample"].cpu().numpy(), want.numpy()), float((got["sample"].cpu() - want).abs().max())
+    print(f"B=64 p_sample (injected noise) vs oracle rel_l2={r:.3e} max_abs={a:.3e}")
+    assert r <= REL_TOL and a <= ABS_TOL
+    assert rel_l2(got["pred_xstart"].cpu().numpy(), x0_ref.numpy()) <= REL_TOL
     # (b) graph chain == stepwise
     t0, t1, seed = 519, 500, 2024
-    tamf_b200.create_gaussian_diffusion(1000, "cosine")._install(m, "ancestral")
     chain = m.p_sample_chain(x.cuda().clone(), t0, t1, dbatch, seed=seed)
     cur, eps = x.cuda().clone(), {}
     for t in range(t0, t1 - 1, -1):
