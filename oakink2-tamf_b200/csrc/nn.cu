@@ -426,6 +426,7 @@ __global__ void __launch_bounds__(NNP_QWARPS * 32, 1)
                       unsigned long long* __restrict__ packed, int stats) {
   extern __shared__ float4 nnp_smem[];
   __shared__ float sR[12];
+  __shared__ float4 ssup[2 * (NNP_MAXP / NNP_BS / 4)];  // super-block boxes (lo, hi)
   __shared__ float s_boxmax;
   __shared__ int s_prune;
   const int f = blockIdx.x, b = f / T, t = f % T, o = blockIdx.y;
@@ -471,11 +472,37 @@ __global__ void __launch_bounds__(NNP_QWARPS * 32, 1)
   }
   for (int j = tid; j < 2 * nblk; j += blockDim.x) sbox[j] = bo[j];
   __syncthreads();
+  if (tid < (nblk + 3) / 4) {
+    // super boxes: union of 4 consecutive block boxes.  fminf / fmaxf drop a NaN operand, and a block whose box has a NaN
+    // (or infinite) corner must never be rejected: `poison` turns the whole super box into NaN then (NaN bound: kept).
+    float4 l = sbox[8 * tid], h = sbox[8 * tid + 1];
+    float poison = ((l.x - l.x) + (l.y - l.y) + (l.z - l.z)) + ((h.x - h.x) + (h.y - h.y) + (h.z - h.z));
+    for (int j = 1; j < 4 && 4 * tid + j < nblk; ++j) {
+      const float4 l2 = sbox[2 * (4 * tid + j)], h2 = sbox[2 * (4 * tid + j) + 1];
+      poison += ((l2.x - l2.x) + (l2.y - l2.y) + (l2.z - l2.z)) + ((h2.x - h2.x) + (h2.y - h2.y) + (h2.z - h2.z));
+      l.x = fminf(l.x, l2.x), l.y = fminf(l.y, l2.y), l.z = fminf(l.z, l2.z);
+      h.x = fmaxf(h.x, h2.x), h.y = fmaxf(h.y, h2.y), h.z = fmaxf(h.z, h2.z);
+    }
+    l.x += poison;
+    ssup[2 * tid] = l, ssup[2 * tid + 1] = h;
+  }
+  __syncthreads();
 
   const bool prune = s_prune != 0;
   const float tmax = fmaxf(fmaxf(fabsf(sR[9]), fabsf(sR[10])), fabsf(sR[11]));
   const float* xn = verts + (size_t)f * V * 3;
-  constexpr int KMAX = NNP_MAXP / NNP_BS / 32;  // block-LB registers per lane (4)
+  // Two levels of boxes: a SUPER block = 4 consecutive blocks of the Morton order (256 points), its box the union of
+  // theirs -- at most 32 of them, one per lane.  A query computes the 32 super bounds once and the 4 block bounds only of
+  // the supers it cannot reject (the 128 block bounds of the one-level form were half of the per-vertex work).  A bound
+  // of a union is <= the bounds of its parts, so rejecting a super under the same rule rejects only blocks the rule
+  // would have rejected: the result stays bit-identical to the exhaustive scan.
+  const int nsup = (nblk + 3) >> 2;
+  auto box_lb = [&](const float4& l, const float4& h, float px, float py, float pz) {
+    const float dx = fmaxf(fmaxf(l.x - px, px - h.x), 0.f);
+    const float dy = fmaxf(fmaxf(l.y - py, py - h.y), 0.f);
+    const float dz = fmaxf(fmaxf(l.z - pz, pz - h.z), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+  };
   for (int q = warp; q < V; q += NNP_QWARPS) {
     const float vx = xn[3 * q], vy = xn[3 * q + 1], vz = xn[3 * q + 2];
     // the query in the object frame
@@ -486,31 +513,20 @@ __global__ void __launch_bounds__(NNP_QWARPS * 32, 1)
     const float mag = fmaxf(fmaxf(fmaxf(fabsf(vx), fabsf(vy)), fabsf(vz)),
                             fmaxf(fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz)), fmaxf(tmax, s_boxmax)));
     const float absm = 2e-5f * mag + 1e-30f;
-    float lb[KMAX];
-    float lmin = inf;
-    int lblk = -1;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int blk = k * 32 + lane;
-      lb[k] = inf;
-      if (blk < nblk) {
-        const float4 l = sbox[2 * blk], h = sbox[2 * blk + 1];
-        const float dx = fmaxf(fmaxf(l.x - px, px - h.x), 0.f);
-        const float dy = fmaxf(fmaxf(l.y - py, py - h.y), 0.f);
-        const float dz = fmaxf(fmaxf(l.z - pz, pz - h.z), 0.f);
-        lb[k] = dx * dx + dy * dy + dz * dz;
-        if (lb[k] < lmin || lblk < 0) lmin = lb[k], lblk = blk;  // NaN bounds: the lane keeps its first block
-      }
-    }
-    // warp argmin of the block bounds: bounds are sums of squares (>= +0 or NaN), so their bit patterns order like
-    // the values (NaN patterns above +inf) and one REDUX finds the minimum; any block is a valid start
+    // bounds are sums of squares (>= +0 or NaN): their bit patterns order like the values (NaN patterns above +inf), so
+    // one REDUX finds a minimum; any block is a valid start
+    const float slb = lane < nsup ? box_lb(ssup[2 * lane], ssup[2 * lane + 1], px, py, pz) : inf;
+    int s0;
     {
-      const unsigned mine = lblk >= 0 ? __float_as_uint(lmin) : 0xFFFFFFFFu;
+      const unsigned mine = lane < nsup ? __float_as_uint(slb) : 0xFFFFFFFFu;
       const unsigned wmin = __reduce_min_sync(0xffffffffu, mine);
-      const unsigned who = __ballot_sync(0xffffffffu, mine == wmin);
-      lblk = __shfl_sync(0xffffffffu, lblk, __ffs(who) - 1);
+      s0 = __ffs(__ballot_sync(0xffffffffu, mine == wmin)) - 1;
     }
-    const int fb = lblk;  // warp-uniform
+    // the four block bounds of a super: lane j & 3 takes block 4 s + (j & 3) (all lanes compute, lanes 0..3 count)
+    auto block_lbs = [&](int s) {
+      const int blk = 4 * s + (lane & 3);
+      return blk < nblk ? box_lb(sbox[2 * blk], sbox[2 * blk + 1], px, py, pz) : inf;
+    };
     float bd = inf;
     unsigned bi = NNP_PAD;
     auto eval_block = [&](int blk) {
@@ -525,29 +541,40 @@ __global__ void __launch_bounds__(NNP_QWARPS * 32, 1)
     auto warp_min = [&]() {  // bd >= +0 or +inf, never NaN: unsigned order of the bits == order of the values
       return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(bd)));
     };
+    auto bound_now = [&]() {
+      if (!prune) return inf;
+      const float r = sqrtf(warp_min()) * 1.001f + absm;
+      return r * r;
+    };
+    // first block: the best block of the best super
+    int fb;
+    {
+      const float b0 = block_lbs(s0);
+      const bool have = (lane & 3) == lane && 4 * s0 + lane < nblk;  // lanes 0..3 with an existing block
+      const unsigned mine = have ? __float_as_uint(b0) : 0xFFFFFFFFu;
+      const unsigned wmin = __reduce_min_sync(0xffffffffu, mine);
+      fb = 4 * s0 + (__ffs(__ballot_sync(0xffffffffu, have && mine == wmin)) - 1);
+    }
     eval_block(fb);
     int n_eval = 1;
-    float bound2 = inf;
-    if (prune) {
-      const float r = sqrtf(warp_min()) * 1.001f + absm;
-      bound2 = r * r;
-    }
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int blk = k * 32 + lane;
-      const bool want = blk < nblk && blk != fb && !(lb[k] > bound2);
-      unsigned m = __ballot_sync(0xffffffffu, want);
-      const bool any = m != 0;
-      while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        eval_block(k * 32 + bit);
+    float bound2 = bound_now();
+    // every super that cannot be rejected, the first one included (its other blocks), in index order
+    unsigned sm = __ballot_sync(0xffffffffu, lane < nsup && !(slb > bound2));
+    while (sm) {
+      const int s = __ffs(sm) - 1;
+      sm &= sm - 1;
+      if (__shfl_sync(0xffffffffu, slb, s) > bound2) continue;  // (the bound has tightened since the ballot)
+      const float bl = block_lbs(s);
+      const int blk_l = 4 * s + (lane & 3);
+      unsigned bm = __ballot_sync(0xffffffffu, lane < 4 && blk_l < nblk && blk_l != fb && !(bl > bound2));
+      const bool any = bm != 0;
+      while (bm) {
+        const int j = __ffs(bm) - 1;
+        bm &= bm - 1;
+        eval_block(4 * s + j);
         ++n_eval;
       }
-      if (any && prune && k + 1 < KMAX) {  // tighten the bound for the remaining groups
-        const float r = sqrtf(warp_min()) * 1.001f + absm;
-        bound2 = r * r;
-      }
+      if (any && sm) bound2 = bound_now();  // tighten for the remaining supers
     }
     // lexicographic (d2, index) minimum over the lanes: smallest distance first, lowest index among its holders
     {
