@@ -568,10 +568,14 @@ def run_refine(args):
     # e2e: host tensors in (pinned), the 13-key dict back on the host
     keys_in = ("sample_pose_repr", "pose_repr", "shape", "obj_traj", "obj_embedding")
     h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys_in) + B * nobj * P * 12
+    # (the results land in pinned host buffers allocated once: 681 MB per step through pageable memory ran at 2 GB/s)
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in out.items()}
+    torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         o = m({k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in pinned.items()})
-        host_out = {k: v.cpu() for k, v in o.items()}
+        for k, v in o.items():
+            host_out[k].copy_(v, non_blocking=True)
     torch.cuda.synchronize(dev)
     dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
